@@ -1,0 +1,16 @@
+"""B200-native drop-in for the deterministic compositor hot path of
+FelixMul/image_transformation.
+
+Public surface (same names and semantics as the reference modules):
+
+* ``image_transformation_b200.compositor``          -> /root/reference/compositor.py
+* ``image_transformation_b200.background_resizing`` -> /root/reference/background_resizing.py
+* ``image_transformation_b200.batch``               -> device-resident batched API (many
+  independent canvases per launch, sharded by canvas across GPUs)
+
+All arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI of
+``include/b200comp.h`` (``_lib/libb200comp.so``); there is no CPU fallback.
+"""
+__version__ = "0.1.0"
+
+from . import _native  # noqa: F401  (fails loudly if the library is missing and cannot be built)

@@ -1,0 +1,950 @@
+// libb200comp.so -- kernels and C ABI of the B200 compositor hot path (include/b200comp.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo (see build.py).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/b200comp.h"
+#include "coeffs.h"
+#include "kernels.cuh"
+
+namespace b200comp {
+
+// =====================================================================================
+// Kernels
+// =====================================================================================
+
+// ---- generic one-axis pass (stand-alone resampler, extreme scales) --------------------
+// One thread per output pixel; coefficients from global memory (any ksize).
+// axis 0: horizontal (in: in_h x in_w -> out: in_h x out_n), axis 1: vertical.
+__global__ void resample_axis_kernel(const uint8_t *__restrict__ in, int64_t in_pitch, int in_w, int in_h,
+                                     uint8_t *__restrict__ out, int64_t out_pitch, int out_w, int out_h,
+                                     const int32_t *__restrict__ k, const int32_t *__restrict__ bounds, int ks,
+                                     int axis, int premul_in, int unpremul_out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out_w || y >= out_h) return;
+    (void)in_w;
+    (void)in_h;
+    const int o = axis == 0 ? x : y;
+    const int lo = __ldg(bounds + 2 * o), n = __ldg(bounds + 2 * o + 1);
+    const int32_t *kk = k + (int64_t)o * ks;
+    int32_t a0, a1, a2, a3;
+    a0 = a1 = a2 = a3 = 1 << (kPrecisionBits - 1);
+    for (int t = 0; t < n; ++t) {
+        const int64_t off = axis == 0 ? (int64_t)y * in_pitch + (int64_t)(lo + t) * 4
+                                      : (int64_t)(lo + t) * in_pitch + (int64_t)x * 4;
+        uint32_t p = ld_px(in, off);
+        if (premul_in) p = premultiply_px(p);
+        mac_px(a0, a1, a2, a3, p, __ldg(kk + t));
+    }
+    uint32_t r = pack_clip(a0, a1, a2, a3);
+    if (unpremul_out) r = unpremultiply_px(r);
+    *reinterpret_cast<uint32_t *>(out + (int64_t)y * out_pitch + (int64_t)x * 4) = r;
+}
+
+// plain / premultiplying / un-premultiplying copy (passes whose size does not change)
+__global__ void convert_copy_kernel(const uint8_t *__restrict__ in, int64_t in_pitch, uint8_t *__restrict__ out,
+                                    int64_t out_pitch, int w, int h, int premul, int unpremul) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    uint32_t p = ld_px(in, (int64_t)y * in_pitch + (int64_t)x * 4);
+    if (premul) p = premultiply_px(p);
+    if (unpremul) p = unpremultiply_px(p);
+    *reinterpret_cast<uint32_t *>(out + (int64_t)y * out_pitch + (int64_t)x * 4) = p;
+}
+
+// ---- in-place alpha-over of one overlay ------------------------------------------------
+__global__ void alpha_over_kernel(uint8_t *__restrict__ canvas, int W, int H, int64_t pitch,
+                                  const uint8_t *__restrict__ src, int w, int h, int64_t spitch, int x0, int y0) {
+    // grid covers the clipped intersection [cx0,cx1) x [cy0,cy1)
+    const int cx0 = max(0, x0), cy0 = max(0, y0);
+    const int cx1 = min(W, x0 + w), cy1 = min(H, y0 + h);
+    const int cx = cx0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int cy = cy0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (cx >= cx1 || cy >= cy1) return;
+    uint32_t *d = reinterpret_cast<uint32_t *>(canvas + (int64_t)cy * pitch + (int64_t)cx * 4);
+    const uint32_t s = ld_px(src, (int64_t)(cy - y0) * spitch + (int64_t)(cx - x0) * 4);
+    *d = over_px(*d, s);
+}
+
+// ---- fills -----------------------------------------------------------------------------
+__global__ void fill_rows_kernel(uint8_t *__restrict__ dst, int W, int H, int64_t pitch, uint32_t rgba) {
+    // generic pitch: one row per blockIdx.y, 32-bit stores
+    const int y = blockIdx.y;
+    uint32_t *row = reinterpret_cast<uint32_t *>(dst + (int64_t)y * pitch);
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) row[x] = rgba;
+    (void)H;
+}
+
+__global__ void fill_flat_kernel(uint4 *__restrict__ dst, size_t n_vec, uint32_t rgba) {
+    // contiguous, 16-byte aligned canvas: 128-bit stores, grid-stride
+    const uint4 v = make_uint4(rgba, rgba, rgba, rgba);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = v;
+}
+
+// fill_gradient (background_resizing.py:74-97): lut[i] = trunc(f32(1-t)*c1 + f32(t)*c2), t = i/max(1,n-1) in double
+__global__ void gradient_lut_kernel(uint32_t *__restrict__ lut, int n, int c1r, int c1g, int c1b, int c2r, int c2g,
+                                    int c2b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double t = (double)i / (double)max(1, n - 1);
+    const float a = (float)(1.0 - t);
+    const float b = (float)t;
+    const uint32_t r = (uint32_t)(int)__fadd_rn(__fmul_rn(a, (float)c1r), __fmul_rn(b, (float)c2r)) & 0xffu;
+    const uint32_t g = (uint32_t)(int)__fadd_rn(__fmul_rn(a, (float)c1g), __fmul_rn(b, (float)c2g)) & 0xffu;
+    const uint32_t bl = (uint32_t)(int)__fadd_rn(__fmul_rn(a, (float)c1b), __fmul_rn(b, (float)c2b)) & 0xffu;
+    lut[i] = r | (g << 8) | (bl << 16) | 0xff000000u;
+}
+
+__global__ void gradient_fill_kernel(uint8_t *__restrict__ dst, int W, int H, int64_t pitch,
+                                     const uint32_t *__restrict__ lut, int horizontal) {
+    const int y = blockIdx.y;
+    uint32_t *row = reinterpret_cast<uint32_t *>(dst + (int64_t)y * pitch);
+    const uint32_t rowv = horizontal ? 0u : __ldg(lut + y);
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x)
+        row[x] = horizontal ? __ldg(lut + x) : rowv;
+    (void)H;
+}
+
+// ---- masked RGB histogram + median -----------------------------------------------------
+// hist layout: [2][3][256] uint64: set 0 = pixels with alpha > 0, set 1 = all pixels; counts[2].
+__global__ void hist_rgb_kernel(const uint8_t *__restrict__ img, int64_t pitch, int x0, int y0, int x1, int y1,
+                                unsigned long long *__restrict__ hist, unsigned long long *__restrict__ counts) {
+    __shared__ unsigned int sh[2 * 3 * 256];
+    __shared__ unsigned int scount[2];
+    for (int i = threadIdx.x; i < 2 * 3 * 256; i += blockDim.x) sh[i] = 0;
+    if (threadIdx.x < 2) scount[threadIdx.x] = 0;
+    __syncthreads();
+    const int rw = x1 - x0;
+    const int64_t total = (int64_t)rw * (y1 - y0);
+    // each thread walks runs of 8 consecutive pixels and merges equal neighbours before the
+    // shared-memory atomics (flat backgrounds would otherwise serialise on one bin)
+    constexpr int RUN = 8;
+    const int64_t n_runs = (total + RUN - 1) / RUN;
+    unsigned int cnt_m = 0, cnt_a = 0;
+    for (int64_t run = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; run < n_runs;
+         run += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t prev = 0;
+        unsigned int len = 0;
+        bool have = false;
+        for (int i = 0; i < RUN; ++i) {
+            const int64_t idx = run * RUN + i;
+            if (idx >= total) break;
+            const int yy = (int)(idx / rw), xx = (int)(idx - (int64_t)yy * rw);
+            const uint32_t p = ld_px(img, (int64_t)(y0 + yy) * pitch + (int64_t)(x0 + xx) * 4);
+            // key merges pixels with equal rgb and equal "masked" state
+            const uint32_t key = (p & 0x00ffffffu) | ((p >> 24) ? 0x01000000u : 0u);
+            if (have && key == prev) {
+                ++len;
+            } else {
+                if (have) {
+                    const int set0 = (prev >> 24) & 1;
+                    atomicAdd(&sh[768 + (prev & 0xff)], len);
+                    atomicAdd(&sh[768 + 256 + ((prev >> 8) & 0xff)], len);
+                    atomicAdd(&sh[768 + 512 + ((prev >> 16) & 0xff)], len);
+                    cnt_a += len;
+                    if (set0) {
+                        atomicAdd(&sh[prev & 0xff], len);
+                        atomicAdd(&sh[256 + ((prev >> 8) & 0xff)], len);
+                        atomicAdd(&sh[512 + ((prev >> 16) & 0xff)], len);
+                        cnt_m += len;
+                    }
+                }
+                prev = key;
+                len = 1;
+                have = true;
+            }
+        }
+        if (have) {
+            const int set0 = (prev >> 24) & 1;
+            atomicAdd(&sh[768 + (prev & 0xff)], len);
+            atomicAdd(&sh[768 + 256 + ((prev >> 8) & 0xff)], len);
+            atomicAdd(&sh[768 + 512 + ((prev >> 16) & 0xff)], len);
+            cnt_a += len;
+            if (set0) {
+                atomicAdd(&sh[prev & 0xff], len);
+                atomicAdd(&sh[256 + ((prev >> 8) & 0xff)], len);
+                atomicAdd(&sh[512 + ((prev >> 16) & 0xff)], len);
+                cnt_m += len;
+            }
+        }
+    }
+    // warp-shuffle reduction of the two pixel counts, one shared atomic per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt_m += __shfl_xor_sync(0xffffffffu, cnt_m, o);
+        cnt_a += __shfl_xor_sync(0xffffffffu, cnt_a, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&scount[0], cnt_m);
+        atomicAdd(&scount[1], cnt_a);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * 3 * 256; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+    if (threadIdx.x < 2 && scount[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)scount[threadIdx.x]);
+}
+
+// np.median semantics: (v[(N-1)/2] + v[N/2]) / 2 per channel; masked set if it has pixels, else all pixels
+__global__ void median_from_hist_kernel(const unsigned long long *__restrict__ hist,
+                                        const unsigned long long *__restrict__ counts, int32_t *__restrict__ out) {
+    const int c = threadIdx.x;
+    if (c >= 3) return;
+    const int set = counts[0] > 0 ? 0 : 1;
+    const unsigned long long n = counts[set];
+    if (n == 0) {
+        out[c] = 0;
+        return;
+    }
+    const unsigned long long *h = hist + set * 768 + c * 256;
+    const unsigned long long lo_rank = (n - 1) / 2, hi_rank = n / 2;
+    unsigned long long acc = 0;
+    int lo = -1, hi = -1;
+    for (int v = 0; v < 256; ++v) {
+        acc += h[v];
+        if (lo < 0 && acc > lo_rank) lo = v;
+        if (hi < 0 && acc > hi_rank) {
+            hi = v;
+            break;
+        }
+    }
+    out[c] = (lo + hi) / 2;
+}
+
+// ---- fused resample + alpha-over tile kernel ---------------------------------------------
+// One CTA per 64x32 output tile.  The canvas tile stays in shared memory while the CTA walks
+// the canvas' placements in z-order; for each placement that touches the tile it stages the
+// needed source patch (premultiplied) in shared memory, runs the horizontal pass into a
+// uint8 intermediate (rounded, as Pillow's two-pass resampler does), then the vertical pass,
+// un-premultiplies and composites onto the resident tile.  The tile is written once.
+
+// Horizontal pass: lane <-> output column (coefficients in registers), loop over patch rows.
+template <int KS>
+__device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int PP, uint32_t *__restrict__ I, int NR,
+                                           int c0, int ox0, int two, const int32_t *__restrict__ kx,
+                                           const int32_t *__restrict__ bx, int ksx) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ncg = (two + 31) >> 5;  // column groups of 32 (1 or 2)
+    const int cg = warp % ncg;
+    const int rstep = kWarps / ncg;
+    const int jj = cg * 32 + lane;  // column inside the tile part
+    if (jj >= two) return;
+    const int j = ox0 + jj;
+    const int base = __ldg(bx + 2 * j) - c0;
+    if (KS > 0) {
+        int32_t kreg[KS > 0 ? KS : 1];
+#pragma unroll
+        for (int t = 0; t < KS; ++t) kreg[t] = __ldg(kx + (int64_t)j * KS + t);
+        for (int r = warp / ncg; r < NR; r += rstep) {
+            const uint32_t *row = P + r * PP + base;
+            int32_t a0, a1, a2, a3;
+            a0 = a1 = a2 = a3 = 1 << (kPrecisionBits - 1);
+#pragma unroll
+            for (int t = 0; t < KS; ++t) mac_px(a0, a1, a2, a3, row[t], kreg[t]);
+            I[r * kInterPitch + jj] = pack_clip(a0, a1, a2, a3);
+        }
+    } else {
+        const int n = __ldg(bx + 2 * j + 1);
+        const int32_t *kk = kx + (int64_t)j * ksx;
+        for (int r = warp / ncg; r < NR; r += rstep) {
+            const uint32_t *row = P + r * PP + base;
+            int32_t a0, a1, a2, a3;
+            a0 = a1 = a2 = a3 = 1 << (kPrecisionBits - 1);
+            for (int t = 0; t < n; ++t) mac_px(a0, a1, a2, a3, row[t], __ldg(kk + t));
+            I[r * kInterPitch + jj] = pack_clip(a0, a1, a2, a3);
+        }
+    }
+}
+
+// Vertical pass + un-premultiply + over: lane <-> output row, loop over tile columns.
+template <int KS>
+__device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, uint32_t *__restrict__ ctile, int r0,
+                                                int oy0, int tho, int two, int tile_dx, int tile_dy,
+                                                const int32_t *__restrict__ ky, const int32_t *__restrict__ by,
+                                                int ksy) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane >= tho) return;
+    const int y = oy0 + lane;
+    const int base = __ldg(by + 2 * y) - r0;
+    uint32_t *crow = ctile + (tile_dy + lane) * kCtPitch + tile_dx;
+    if (KS > 0) {
+        int32_t kreg[KS > 0 ? KS : 1];
+#pragma unroll
+        for (int t = 0; t < KS; ++t) kreg[t] = __ldg(ky + (int64_t)y * KS + t);
+        for (int x = warp; x < two; x += kWarps) {
+            const uint32_t *col = I + base * kInterPitch + x;
+            int32_t a0, a1, a2, a3;
+            a0 = a1 = a2 = a3 = 1 << (kPrecisionBits - 1);
+#pragma unroll
+            for (int t = 0; t < KS; ++t) mac_px(a0, a1, a2, a3, col[t * kInterPitch], kreg[t]);
+            const uint32_t s = unpremultiply_px(pack_clip(a0, a1, a2, a3));
+            crow[x] = over_px(crow[x], s);
+        }
+    } else {
+        const int n = __ldg(by + 2 * y + 1);
+        const int32_t *kk = ky + (int64_t)y * ksy;
+        for (int x = warp; x < two; x += kWarps) {
+            const uint32_t *col = I + base * kInterPitch + x;
+            int32_t a0, a1, a2, a3;
+            a0 = a1 = a2 = a3 = 1 << (kPrecisionBits - 1);
+            for (int t = 0; t < n; ++t) mac_px(a0, a1, a2, a3, col[t * kInterPitch], __ldg(kk + t));
+            const uint32_t s = unpremultiply_px(pack_clip(a0, a1, a2, a3));
+            crow[x] = over_px(crow[x], s);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) composite_tiles_kernel(const DevCanvas *__restrict__ canvases,
+                                                                    int n_canvases,
+                                                                    const DevPlacement *__restrict__ placements,
+                                                                    int patch_words, int inter_words,
+                                                                    int *__restrict__ status) {
+    extern __shared__ uint32_t smem[];
+    uint32_t *ctile = smem;                    // kTileH * kCtPitch
+    uint32_t *P = ctile + kTileH * kCtPitch;   // patch_words (premultiplied source patch)
+    uint32_t *I = P + patch_words;             // inter_words (H-pass result, uint8x4)
+
+    // ---- which canvas / tile ----
+    const int64_t tile = blockIdx.x;
+    int lo = 0, hi = n_canvases - 1;
+    while (lo < hi) {  // last canvas with tile_base <= tile
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&canvases[mid].tile_base) <= tile) lo = mid; else hi = mid - 1;
+    }
+    const DevCanvas cv = canvases[lo];
+    const int local = (int)(tile - cv.tile_base);
+    const int ty = local / cv.tiles_x, tx = local - ty * cv.tiles_x;
+    const int tx0 = tx * kTileW, ty0 = ty * kTileH;
+    const int tx1 = min(cv.W, tx0 + kTileW), ty1 = min(cv.H, ty0 + kTileH);
+    const int tw = tx1 - tx0, th = ty1 - ty0;
+
+    // ---- load the canvas tile (background or solid colour) ----
+    for (int i = threadIdx.x; i < kTileW * kTileH; i += kThreads) {
+        const int yy = i / kTileW, xx = i - yy * kTileW;
+        if (yy < th && xx < tw) {
+            ctile[yy * kCtPitch + xx] =
+                cv.bg ? ld_px(cv.bg, (int64_t)(ty0 + yy) * cv.bg_pitch + (int64_t)(tx0 + xx) * 4) : cv.solid;
+        }
+    }
+    __syncthreads();
+
+    // ---- z-order walk ----
+    for (int pi = 0; pi < cv.count; ++pi) {
+        const DevPlacement *pp = placements + cv.first + pi;
+        const int px = __ldg(&pp->x), py = __ldg(&pp->y), pw = __ldg(&pp->w), ph = __ldg(&pp->h);
+        const int ix0 = max(tx0, px), iy0 = max(ty0, py);
+        const int ix1 = min(tx1, px + pw), iy1 = min(ty1, py + ph);
+        if (ix0 >= ix1 || iy0 >= iy1) continue;  // uniform across the CTA
+        const int two = ix1 - ix0, tho = iy1 - iy0;
+        const uint8_t *src = pp->src;
+        const int spitch = __ldg(&pp->src_pitch);
+        if (__ldg(&pp->mode) == 0) {
+            // identity-size placement: plain over straight from the cutout
+            for (int i = threadIdx.x; i < two * tho; i += kThreads) {
+                const int yy = i / two, xx = i - yy * two;
+                const uint32_t s = ld_px(src, (int64_t)(iy0 + yy - py) * spitch + (int64_t)(ix0 + xx - px) * 4);
+                uint32_t *d = ctile + (iy0 + yy - ty0) * kCtPitch + (ix0 + xx - tx0);
+                *d = over_px(*d, s);
+            }
+            __syncthreads();
+            continue;
+        }
+        const int32_t *kx = pp->kx, *bx = pp->bx, *ky = pp->ky, *by = pp->by;
+        const int ksx = __ldg(&pp->ksx), ksy = __ldg(&pp->ksy);
+        const int ox0 = ix0 - px, ox1 = ix1 - px, oy0 = iy0 - py, oy1 = iy1 - py;
+        const int c0 = __ldg(bx + 2 * ox0);
+        const int c1 = __ldg(bx + 2 * (ox1 - 1)) + __ldg(bx + 2 * (ox1 - 1) + 1);
+        const int r0 = __ldg(by + 2 * oy0);
+        const int r1 = __ldg(by + 2 * (oy1 - 1)) + __ldg(by + 2 * (oy1 - 1) + 1);
+        const int NC = c1 - c0, NR = r1 - r0;
+        const int PP = NC | 1;
+        if (NR * PP + ksx > patch_words || (NR + ksy) * kInterPitch > inter_words) {
+            if (threadIdx.x == 0) atomicOr(status, NR * PP + ksx > patch_words ? kStatusPatchOverflow : kStatusInterOverflow);
+            continue;  // host sizing bug: flagged, never silently wrong
+        }
+        // stage the premultiplied source patch
+        for (int i = threadIdx.x; i < NR * NC; i += kThreads) {
+            const int rr = i / NC, cc = i - rr * NC;
+            P[rr * PP + cc] = premultiply_px(ld_px(src, (int64_t)(r0 + rr) * spitch + (int64_t)(c0 + cc) * 4));
+        }
+        __syncthreads();
+        switch (ksx) {
+            case 1: tile_hpass<1>(P, PP, I, NR, c0, ox0, two, kx, bx, ksx); break;
+            case 7: tile_hpass<7>(P, PP, I, NR, c0, ox0, two, kx, bx, ksx); break;
+            case 9: tile_hpass<9>(P, PP, I, NR, c0, ox0, two, kx, bx, ksx); break;
+            case 11: tile_hpass<11>(P, PP, I, NR, c0, ox0, two, kx, bx, ksx); break;
+            case 13: tile_hpass<13>(P, PP, I, NR, c0, ox0, two, kx, bx, ksx); break;
+            default: tile_hpass<0>(P, PP, I, NR, c0, ox0, two, kx, bx, ksx); break;
+        }
+        __syncthreads();
+        switch (ksy) {
+            case 1: tile_vpass_over<1>(I, ctile, r0, oy0, tho, two, ix0 - tx0, iy0 - ty0, ky, by, ksy); break;
+            case 7: tile_vpass_over<7>(I, ctile, r0, oy0, tho, two, ix0 - tx0, iy0 - ty0, ky, by, ksy); break;
+            case 9: tile_vpass_over<9>(I, ctile, r0, oy0, tho, two, ix0 - tx0, iy0 - ty0, ky, by, ksy); break;
+            case 11: tile_vpass_over<11>(I, ctile, r0, oy0, tho, two, ix0 - tx0, iy0 - ty0, ky, by, ksy); break;
+            case 13: tile_vpass_over<13>(I, ctile, r0, oy0, tho, two, ix0 - tx0, iy0 - ty0, ky, by, ksy); break;
+            default: tile_vpass_over<0>(I, ctile, r0, oy0, tho, two, ix0 - tx0, iy0 - ty0, ky, by, ksy); break;
+        }
+        __syncthreads();
+    }
+
+    // ---- write the tile once ----
+    for (int i = threadIdx.x; i < kTileW * kTileH; i += kThreads) {
+        const int yy = i / kTileW, xx = i - yy * kTileW;
+        if (yy < th && xx < tw)
+            *reinterpret_cast<uint32_t *>(cv.out + (int64_t)(ty0 + yy) * cv.out_pitch + (int64_t)(tx0 + xx) * 4) =
+                ctile[yy * kCtPitch + xx];
+    }
+}
+
+// =====================================================================================
+// Host side
+// =====================================================================================
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(B200COMP_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+static inline cudaStream_t S(void *stream) { return reinterpret_cast<cudaStream_t>(stream); }
+
+static bool aligned4(const void *p, int64_t pitch) {
+    return (reinterpret_cast<uintptr_t>(p) & 3u) == 0 && (pitch & 3) == 0;
+}
+
+// identity table for a skipped pass: one tap of 1.0 at the same index
+static void identity_table(int n, int32_t *k, int32_t *b) {
+    for (int i = 0; i < n; ++i) {
+        k[i] = 1 << kPrecisionBits;
+        b[2 * i] = i;
+        b[2 * i + 1] = 1;
+    }
+}
+
+// Upper bound of the source extent needed by `n_out` consecutive output samples.
+static int extent_bound(int in_size, int out_size, int n_out) {
+    if (in_size == out_size) return n_out;
+    const double scale = (double)in_size / out_size;
+    const double support = 3.0 * std::max(1.0, scale);
+    const double e = (std::min(n_out, out_size) - 1) * scale + 2.0 * support + 1.0;
+    return std::min(in_size, (int)std::floor(e) + 2);
+}
+
+static int launch_axis(const uint8_t *in, int64_t in_pitch, int in_w, int in_h, uint8_t *out, int64_t out_pitch,
+                       int out_w, int out_h, const int32_t *k, const int32_t *b, int ks, int axis, int premul,
+                       int unpremul, cudaStream_t st) {
+    dim3 blk(32, 8), grd((out_w + 31) / 32, (out_h + 7) / 8);
+    if (ks > 0)
+        resample_axis_kernel<<<grd, blk, 0, st>>>(in, in_pitch, in_w, in_h, out, out_pitch, out_w, out_h, k, b, ks,
+                                                   axis, premul, unpremul);
+    else
+        convert_copy_kernel<<<grd, blk, 0, st>>>(in, in_pitch, out, out_pitch, out_w, out_h, premul, unpremul);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Two-pass resample with device tables; scratch holds the uint8 intermediate.
+static int resample_two_pass(const uint8_t *src, int sw, int sh, int64_t sp, uint8_t *dst, int w, int h, int64_t dp,
+                             const int32_t *kx, const int32_t *bx, int ksx, const int32_t *ky, const int32_t *by,
+                             int ksy, uint8_t *scratch, int flags, cudaStream_t st) {
+    if (w == sw && h == sh) {  // Image.resize identity short-cut: copy, no premultiply round trip
+        CUDA_TRY(cudaMemcpy2DAsync(dst, dp, src, sp, (size_t)w * 4, h, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    const bool need_h = w != sw, need_v = h != sh;
+    int rc;
+    if (need_h && need_v) {
+        if (!scratch) return fail(B200COMP_EINVAL, "scratch buffer required for a two-pass resample");
+        if (flags & B200COMP_VERTICAL_FIRST) {
+            rc = launch_axis(src, sp, sw, sh, scratch, (int64_t)sw * 4, sw, h, ky, by, ksy, 1, 1, 0, st);
+            if (rc) return rc;
+            rc = launch_axis(scratch, (int64_t)sw * 4, sw, h, dst, dp, w, h, kx, bx, ksx, 0, 0, 1, st);
+        } else {
+            rc = launch_axis(src, sp, sw, sh, scratch, (int64_t)w * 4, w, sh, kx, bx, ksx, 0, 1, 0, st);
+            if (rc) return rc;
+            rc = launch_axis(scratch, (int64_t)w * 4, w, sh, dst, dp, w, h, ky, by, ksy, 1, 0, 1, st);
+        }
+        return rc;
+    }
+    if (need_h) return launch_axis(src, sp, sw, sh, dst, dp, w, h, kx, bx, ksx, 0, 1, 1, st);
+    return launch_axis(src, sp, sw, sh, dst, dp, w, h, ky, by, ksy, 1, 1, 1, st);
+}
+
+// ---- coefficient table cache for one plan / call ----------------------------------------
+struct TableRef {
+    int64_t k_off = 0;  // offsets in int32 units into the table buffer
+    int64_t b_off = 0;
+    int ks = 0;
+};
+
+struct TableSet {
+    // key: (in, out); out == -in marks the identity table of a skipped pass
+    std::map<std::pair<int, int>, TableRef> refs;
+    std::vector<std::pair<int, int>> order;
+    std::vector<int32_t> host;
+    int64_t total = 0;
+
+    TableRef &want(int in_size, int out_size, bool identity) {
+        std::pair<int, int> key(in_size, identity ? -in_size : out_size);
+        auto it = refs.find(key);
+        if (it != refs.end()) return it->second;
+        TableRef r;
+        r.ks = identity ? 1 : lanczos_ksize(in_size, out_size);
+        const int n = identity ? in_size : out_size;
+        r.k_off = total;
+        total += (int64_t)n * r.ks;
+        r.b_off = total;
+        total += (int64_t)n * 2;
+        total = (total + 3) & ~(int64_t)3;  // keep every table 16-byte aligned
+        order.push_back(key);
+        return refs.emplace(key, r).first->second;
+    }
+
+    void build(int n_threads) {
+        host.assign((size_t)total + 4, 0);
+        if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+        n_threads = std::max(1, std::min<int>(n_threads, (int)order.size()));
+        auto work = [&](int tid) {
+            for (size_t i = tid; i < order.size(); i += n_threads) {
+                const auto &key = order[i];
+                const TableRef &r = refs[key];
+                if (key.second < 0)
+                    identity_table(key.first, host.data() + r.k_off, host.data() + r.b_off);
+                else
+                    build_lanczos_table(key.first, key.second, host.data() + r.k_off, host.data() + r.b_off);
+            }
+        };
+        if (n_threads == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
+            for (auto &t : th) t.join();
+        }
+    }
+};
+
+}  // namespace b200comp
+
+using namespace b200comp;
+
+// =====================================================================================
+// Plan
+// =====================================================================================
+struct b200comp_plan {
+    int device = 0;
+    cudaStream_t create_stream = nullptr;
+    int n_canvases = 0;
+    int64_t n_tiles = 0;
+    int32_t *d_tables = nullptr;
+    DevPlacement *d_placements = nullptr;
+    DevCanvas *d_canvases = nullptr;
+    int *d_status = nullptr;
+    int patch_words = 0, inter_words = 0;
+    size_t smem_bytes = 0;
+    int64_t info[B200COMP_INFO_COUNT] = {0};
+    // placements resampled by the generic kernels before the tile kernel (extreme scales, vertical-first)
+    struct Pre {
+        const uint8_t *src;
+        int64_t sp;
+        int sw, sh, w, h, flags;
+        TableRef tx, ty;
+        uint8_t *dst;      // w*h*4 temp
+        uint8_t *scratch;  // intermediate
+    };
+    std::vector<Pre> pre;
+    std::vector<void *> owned;  // device allocations freed with the plan
+};
+
+static const size_t kMaxSmemBytes = 200 * 1024;  // per-CTA budget for the tile kernel
+static const int kFusedMaxKs = 61;               // up to 10x downscale inside the tile kernel
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int b200comp_abi_version(void) { return B200COMP_ABI_VERSION; }
+// internal helper shared with host_api.cu (not part of the public header)
+int b200comp_set_error_(int code, const char *msg) { return fail(code, msg ? msg : ""); }
+const char *b200comp_last_error(void) { return g_err.c_str(); }
+
+int b200comp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int b200comp_ksize(int in_size, int out_size) {
+    if (in_size < 1 || out_size < 1) return fail(B200COMP_EINVAL, "sizes must be positive");
+    return lanczos_ksize(in_size, out_size);
+}
+
+int b200comp_build_coeffs(int in_size, int out_size, int32_t *k_host, int32_t *bounds_host, int *ksize) {
+    if (in_size < 1 || out_size < 1 || !k_host || !bounds_host)
+        return fail(B200COMP_EINVAL, "b200comp_build_coeffs: bad argument");
+    const int ks = build_lanczos_table(in_size, out_size, k_host, bounds_host);
+    if (ksize) *ksize = ks;
+    return 0;
+}
+
+int b200comp_resample_rgba(const uint8_t *src, int sw, int sh, size_t src_pitch, uint8_t *dst, int w, int h,
+                           size_t dst_pitch, const int32_t *kx, const int32_t *bx, int ksx, const int32_t *ky,
+                           const int32_t *by, int ksy, uint8_t *scratch, int flags, void *stream) {
+    if (!src || !dst || sw < 1 || sh < 1 || w < 1 || h < 1) return fail(B200COMP_EINVAL, "resample: bad size/pointer");
+    if (!aligned4(src, (int64_t)src_pitch) || !aligned4(dst, (int64_t)dst_pitch))
+        return fail(B200COMP_EINVAL, "resample: buffers must be 4-byte aligned with pitch % 4 == 0");
+    if ((w != sw && (!kx || !bx || ksx < 1)) || (h != sh && (!ky || !by || ksy < 1)))
+        return fail(B200COMP_EINVAL, "resample: missing coefficient table");
+    return resample_two_pass(src, sw, sh, (int64_t)src_pitch, dst, w, h, (int64_t)dst_pitch, kx, bx, ksx, ky, by, ksy,
+                             scratch, flags, S(stream));
+}
+
+int b200comp_resize_rgba_lanczos(const uint8_t *src, int sw, int sh, size_t src_pitch, uint8_t *dst, int w, int h,
+                                 size_t dst_pitch, int flags, void *stream) {
+    if (!src || !dst || sw < 1 || sh < 1 || w < 1 || h < 1) return fail(B200COMP_EINVAL, "resize: bad size/pointer");
+    if (!aligned4(src, (int64_t)src_pitch) || !aligned4(dst, (int64_t)dst_pitch))
+        return fail(B200COMP_EINVAL, "resize: buffers must be 4-byte aligned with pitch % 4 == 0");
+    cudaStream_t st = S(stream);
+    if (w == sw && h == sh)
+        return resample_two_pass(src, sw, sh, (int64_t)src_pitch, dst, w, h, (int64_t)dst_pitch, nullptr, nullptr, 0,
+                                 nullptr, nullptr, 0, nullptr, flags, st);
+    TableSet ts;
+    TableRef tx, ty;
+    if (w != sw) tx = ts.want(sw, w, false);
+    if (h != sh) ty = ts.want(sh, h, false);
+    ts.build(1);
+    const size_t tbytes = ts.host.size() * sizeof(int32_t);
+    const size_t sbytes = (size_t)std::max((int64_t)sh * w, (int64_t)h * sw) * 4;
+    uint8_t *d_mem = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)&d_mem, tbytes + sbytes + 16, st));
+    int32_t *d_t = reinterpret_cast<int32_t *>(d_mem);
+    uint8_t *d_s = d_mem + ((tbytes + 15) & ~(size_t)15);
+    cudaError_t e = cudaMemcpyAsync(d_t, ts.host.data(), tbytes, cudaMemcpyHostToDevice, st);
+    int rc = 0;
+    if (e == cudaSuccess) {
+        // the pageable-source copy above is staged before it returns, so ts may go out of scope
+        rc = resample_two_pass(src, sw, sh, (int64_t)src_pitch, dst, w, h, (int64_t)dst_pitch, d_t + tx.k_off,
+                               d_t + tx.b_off, tx.ks, d_t + ty.k_off, d_t + ty.b_off, ty.ks, d_s, flags, st);
+    }
+    cudaFreeAsync(d_mem, st);
+    if (e != cudaSuccess) return fail(B200COMP_ECUDA, std::string("table upload: ") + cudaGetErrorString(e));
+    return rc;
+}
+
+int b200comp_alpha_over(uint8_t *canvas, int W, int H, size_t pitch, const uint8_t *src, int w, int h,
+                        size_t src_pitch, int x, int y, void *stream) {
+    if (!canvas || !src || W < 1 || H < 1 || w < 1 || h < 1) return fail(B200COMP_EINVAL, "alpha_over: bad argument");
+    if (!aligned4(canvas, (int64_t)pitch) || !aligned4(src, (int64_t)src_pitch))
+        return fail(B200COMP_EINVAL, "alpha_over: buffers must be 4-byte aligned with pitch % 4 == 0");
+    const int64_t cx0 = std::max<int64_t>(0, x), cy0 = std::max<int64_t>(0, y);
+    const int64_t cx1 = std::min<int64_t>(W, (int64_t)x + w), cy1 = std::min<int64_t>(H, (int64_t)y + h);
+    if (cx0 >= cx1 || cy0 >= cy1) return 0;  // fully outside: nothing changes
+    dim3 blk(32, 8), grd((unsigned)((cx1 - cx0 + 31) / 32), (unsigned)((cy1 - cy0 + 7) / 8));
+    alpha_over_kernel<<<grd, blk, 0, S(stream)>>>(canvas, W, H, (int64_t)pitch, src, w, h, (int64_t)src_pitch, x, y);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int b200comp_fill_rgba(uint8_t *dst, int W, int H, size_t pitch, uint32_t rgba, void *stream) {
+    if (!dst || W < 1 || H < 1) return fail(B200COMP_EINVAL, "fill: bad argument");
+    if (!aligned4(dst, (int64_t)pitch)) return fail(B200COMP_EINVAL, "fill: buffer must be 4-byte aligned");
+    cudaStream_t st = S(stream);
+    const size_t bytes = (size_t)W * 4 * H;
+    if (pitch == (size_t)W * 4 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && bytes >= 16) {
+        const size_t n_vec = bytes / 16;
+        const int blocks = (int)std::min<size_t>((n_vec + 255) / 256, 148 * 16);
+        fill_flat_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4 *>(dst), n_vec, rgba);
+        const size_t tail_px = (bytes - n_vec * 16) / 4;
+        if (tail_px) fill_rows_kernel<<<dim3(1, 1), 32, 0, st>>>(dst + n_vec * 16, (int)tail_px, 1, 0, rgba);
+    } else {
+        dim3 grd((unsigned)std::min(16, (W + 255) / 256), (unsigned)H);
+        fill_rows_kernel<<<grd, 256, 0, st>>>(dst, W, H, (int64_t)pitch, rgba);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int b200comp_fill_gradient(uint8_t *dst, int W, int H, size_t pitch, int horizontal, const int32_t c1[3],
+                           const int32_t c2[3], void *stream) {
+    if (!dst || W < 1 || H < 1 || !c1 || !c2) return fail(B200COMP_EINVAL, "fill_gradient: bad argument");
+    if (!aligned4(dst, (int64_t)pitch)) return fail(B200COMP_EINVAL, "fill_gradient: buffer must be 4-byte aligned");
+    cudaStream_t st = S(stream);
+    const int n = horizontal ? W : H;
+    uint32_t *lut = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)&lut, (size_t)n * 4, st));
+    gradient_lut_kernel<<<(n + 255) / 256, 256, 0, st>>>(lut, n, c1[0], c1[1], c1[2], c2[0], c2[1], c2[2]);
+    dim3 grd((unsigned)std::min(16, (W + 255) / 256), (unsigned)H);
+    gradient_fill_kernel<<<grd, 256, 0, st>>>(dst, W, H, (int64_t)pitch, lut, horizontal ? 1 : 0);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(lut, st);
+    if (e != cudaSuccess) return fail(B200COMP_ECUDA, cudaGetErrorString(e));
+    return 0;
+}
+
+int b200comp_masked_median_rgb(const uint8_t *img, int W, int H, size_t pitch, int x0, int y0, int x1, int y1,
+                               int32_t out_rgb[3], void *stream) {
+    if (!img || !out_rgb || W < 1 || H < 1) return fail(B200COMP_EINVAL, "median: bad argument");
+    if (x0 < 0 || y0 < 0 || x1 > W || y1 > H || x0 >= x1 || y0 >= y1)
+        return fail(B200COMP_EINVAL, "median: rectangle outside the image or empty");
+    if (!aligned4(img, (int64_t)pitch)) return fail(B200COMP_EINVAL, "median: buffer must be 4-byte aligned");
+    cudaStream_t st = S(stream);
+    unsigned long long *d = nullptr;  // [2*3*256] hist + [2] counts + 3 int32 result
+    const size_t bytes = (2 * 3 * 256 + 2) * sizeof(unsigned long long) + 4 * sizeof(int32_t);
+    CUDA_TRY(cudaMallocAsync((void **)&d, bytes, st));
+    cudaError_t e = cudaMemsetAsync(d, 0, bytes, st);
+    const int64_t total = (int64_t)(x1 - x0) * (y1 - y0);
+    const int64_t n_runs = (total + 7) / 8;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_runs + 255) / 256, 148 * 8));
+    int32_t *d_out = reinterpret_cast<int32_t *>(d + 2 * 3 * 256 + 2);
+    if (e == cudaSuccess) {
+        hist_rgb_kernel<<<blocks, 256, 0, st>>>(img, (int64_t)pitch, x0, y0, x1, y1, d, d + 2 * 3 * 256);
+        median_from_hist_kernel<<<1, 32, 0, st>>>(d, d + 2 * 3 * 256, d_out);
+        e = cudaGetLastError();
+    }
+    int32_t h_out[3] = {0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, d_out, sizeof h_out, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFreeAsync(d, st);
+    if (e != cudaSuccess) return fail(B200COMP_ECUDA, std::string("median: ") + cudaGetErrorString(e));
+    out_rgb[0] = h_out[0];
+    out_rgb[1] = h_out[1];
+    out_rgb[2] = h_out[2];
+    return 0;
+}
+
+// -------------------------------------------------------------------------------- plan
+int b200comp_plan_destroy(b200comp_plan *plan) {
+    if (!plan) return 0;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != plan->device) cudaSetDevice(plan->device);
+    for (void *p : plan->owned) cudaFreeAsync(p, plan->create_stream);
+    if (cur != plan->device) cudaSetDevice(cur);
+    delete plan;
+    return 0;
+}
+
+int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const b200comp_placement *placements,
+                         int n_placements, int n_host_threads, void *stream, b200comp_plan **out_plan) {
+    if (!out_plan) return fail(B200COMP_EINVAL, "plan_create: null plan pointer");
+    *out_plan = nullptr;
+    if (n_canvases < 1 || !canvases || n_placements < 0 || (n_placements > 0 && !placements))
+        return fail(B200COMP_EINVAL, "plan_create: empty batch or null arrays");
+    cudaStream_t st = S(stream);
+    b200comp_plan *plan = new b200comp_plan();
+    struct Guard {
+        b200comp_plan *p;
+        ~Guard() { if (p) b200comp_plan_destroy(p); }
+    } guard{plan};
+    CUDA_TRY(cudaGetDevice(&plan->device));
+    plan->create_stream = st;
+    plan->n_canvases = n_canvases;
+
+    // ---- validate, classify placements, collect tables ----
+    TableSet ts;
+    std::vector<DevPlacement> hp((size_t)std::max(1, n_placements));
+    std::vector<std::pair<TableRef, TableRef>> tref((size_t)std::max(1, n_placements));
+    std::vector<int> pre_index((size_t)std::max(1, n_placements), -1);
+    int max_patch = 16, max_inter = 16;
+    int64_t n_fused = 0, n_ident = 0;
+    for (int i = 0; i < n_placements; ++i) {
+        const b200comp_placement &p = placements[i];
+        if (!p.src || p.sw < 1 || p.sh < 1 || p.w < 1 || p.h < 1)
+            return fail(B200COMP_EINVAL, "plan_create: placement " + std::to_string(i) + " has a null source or empty size");
+        if (!aligned4(p.src, p.src_pitch) || p.src_pitch < (int64_t)p.sw * 4 || p.src_pitch > INT32_MAX)
+            return fail(B200COMP_EINVAL, "plan_create: placement " + std::to_string(i) + " source misaligned or bad pitch");
+        DevPlacement &d = hp[i];
+        std::memset(&d, 0, sizeof d);
+        d.src = p.src;
+        d.src_pitch = (int32_t)p.src_pitch;
+        d.sw = p.sw; d.sh = p.sh;
+        d.x = p.x; d.y = p.y; d.w = p.w; d.h = p.h;
+        if (p.w == p.sw && p.h == p.sh) {
+            d.mode = 0;
+            ++n_ident;
+            continue;
+        }
+        const bool need_h = p.w != p.sw, need_v = p.h != p.sh;
+        const int ksx = need_h ? lanczos_ksize(p.sw, p.w) : 1;
+        const int ksy = need_v ? lanczos_ksize(p.sh, p.h) : 1;
+        const int nc = extent_bound(p.sw, p.w, kTileW), nr = extent_bound(p.sh, p.h, kTileH);
+        const int64_t patch = (int64_t)nr * (nc | 1) + ksx;
+        const int64_t inter = (int64_t)(nr + ksy) * kInterPitch;
+        const size_t need = ((size_t)kTileH * kCtPitch + patch + inter) * 4;
+        const bool vertical_first = (p.flags & B200COMP_VERTICAL_FIRST) && need_h && need_v;
+        if (!vertical_first && ksx <= kFusedMaxKs && ksy <= kFusedMaxKs && need <= kMaxSmemBytes) {
+            d.mode = 1;
+            tref[i].first = ts.want(p.sw, p.w, !need_h);
+            tref[i].second = ts.want(p.sh, p.h, !need_v);
+            d.ksx = tref[i].first.ks;
+            d.ksy = tref[i].second.ks;
+            max_patch = std::max<int>(max_patch, (int)patch);
+            max_inter = std::max<int>(max_inter, (int)inter);
+            ++n_fused;
+        } else {
+            // pre-resample with the generic kernels; the tile kernel then sees an identity-size overlay
+            b200comp_plan::Pre pr;
+            pr.src = p.src; pr.sp = p.src_pitch; pr.sw = p.sw; pr.sh = p.sh; pr.w = p.w; pr.h = p.h;
+            pr.flags = vertical_first ? B200COMP_VERTICAL_FIRST : 0;
+            if (need_h) pr.tx = ts.want(p.sw, p.w, false);
+            if (need_v) pr.ty = ts.want(p.sh, p.h, false);
+            pr.dst = nullptr; pr.scratch = nullptr;
+            pre_index[i] = (int)plan->pre.size();
+            plan->pre.push_back(pr);
+            d.mode = 0;
+            d.sw = p.w; d.sh = p.h;
+            d.src_pitch = p.w * 4;
+        }
+    }
+
+    // ---- canvases / tiles ----
+    std::vector<DevCanvas> hc((size_t)n_canvases);
+    int64_t tiles = 0, algo = 0;
+    for (int c = 0; c < n_canvases; ++c) {
+        const b200comp_canvas &cv = canvases[c];
+        if (!cv.out || cv.W < 1 || cv.H < 1) return fail(B200COMP_EINVAL, "plan_create: canvas " + std::to_string(c) + " has no output or empty size");
+        if (!aligned4(cv.out, cv.out_pitch) || cv.out_pitch < (int64_t)cv.W * 4 || (cv.bg && (!aligned4(cv.bg, cv.bg_pitch) || cv.bg_pitch < (int64_t)cv.W * 4)))
+            return fail(B200COMP_EINVAL, "plan_create: canvas " + std::to_string(c) + " misaligned or bad pitch");
+        if (cv.n_placements < 0 || cv.first_placement < 0 || (int64_t)cv.first_placement + cv.n_placements > n_placements)
+            return fail(B200COMP_EINVAL, "plan_create: canvas " + std::to_string(c) + " placement range out of bounds");
+        DevCanvas &d = hc[c];
+        std::memset(&d, 0, sizeof d);
+        d.out = cv.out; d.bg = cv.bg; d.out_pitch = cv.out_pitch; d.bg_pitch = cv.bg_pitch;
+        d.solid = cv.solid_rgba; d.W = cv.W; d.H = cv.H;
+        d.first = cv.first_placement; d.count = cv.n_placements;
+        d.tiles_x = (cv.W + kTileW - 1) / kTileW;
+        d.tiles_y = (cv.H + kTileH - 1) / kTileH;
+        d.tile_base = tiles;
+        tiles += (int64_t)d.tiles_x * d.tiles_y;
+        algo += (int64_t)cv.W * cv.H * 4 * (cv.bg ? 2 : 1);
+        for (int i = 0; i < cv.n_placements; ++i) {
+            const b200comp_placement &p = placements[cv.first_placement + i];
+            algo += (int64_t)p.sw * p.sh * 4;
+        }
+    }
+    if (tiles > INT32_MAX) return fail(B200COMP_EINVAL, "plan_create: too many tiles for one launch; split the batch");
+    plan->n_tiles = tiles;
+
+    // ---- build tables on the host threads, upload everything ----
+    ts.build(n_host_threads);
+    const size_t tbytes = ts.host.size() * sizeof(int32_t);
+    auto dev_alloc = [&](void **p, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMallocAsync(p, std::max<size_t>(bytes, 16), st);
+        if (e == cudaSuccess) plan->owned.push_back(*p);
+        return e;
+    };
+    CUDA_TRY(dev_alloc((void **)&plan->d_tables, tbytes));
+    CUDA_TRY(dev_alloc((void **)&plan->d_placements, hp.size() * sizeof(DevPlacement)));
+    CUDA_TRY(dev_alloc((void **)&plan->d_canvases, hc.size() * sizeof(DevCanvas)));
+    CUDA_TRY(dev_alloc((void **)&plan->d_status, sizeof(int)));
+    for (auto &pr : plan->pre) {
+        CUDA_TRY(dev_alloc((void **)&pr.dst, (size_t)pr.w * pr.h * 4));
+        if (pr.w != pr.sw && pr.h != pr.sh)
+            CUDA_TRY(dev_alloc((void **)&pr.scratch, (size_t)std::max((int64_t)pr.sh * pr.w, (int64_t)pr.h * pr.sw) * 4));
+    }
+    for (int i = 0; i < n_placements; ++i) {
+        DevPlacement &d = hp[i];
+        if (d.mode == 1) {
+            d.kx = plan->d_tables + tref[i].first.k_off;
+            d.bx = plan->d_tables + tref[i].first.b_off;
+            d.ky = plan->d_tables + tref[i].second.k_off;
+            d.by = plan->d_tables + tref[i].second.b_off;
+        } else if (pre_index[i] >= 0) {
+            d.src = plan->pre[(size_t)pre_index[i]].dst;
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(plan->d_tables, ts.host.data(), tbytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(plan->d_placements, hp.data(), hp.size() * sizeof(DevPlacement), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(plan->d_canvases, hc.data(), hc.size() * sizeof(DevCanvas), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(plan->d_status, 0, sizeof(int), st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // host staging vectors die with this scope
+
+    plan->patch_words = max_patch;
+    plan->inter_words = max_inter;
+    plan->smem_bytes = ((size_t)kTileH * kCtPitch + max_patch + max_inter) * 4;
+    CUDA_TRY(cudaFuncSetAttribute(composite_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemBytes));
+
+    plan->info[B200COMP_INFO_ALGORITHMIC_BYTES] = algo;
+    plan->info[B200COMP_INFO_LAUNCHES_PER_RUN] = 1;
+    for (auto &pr : plan->pre) plan->info[B200COMP_INFO_LAUNCHES_PER_RUN] += (pr.w != pr.sw && pr.h != pr.sh) ? 2 : 1;
+    plan->info[B200COMP_INFO_FUSED_PLACEMENTS] = n_fused;
+    plan->info[B200COMP_INFO_IDENTITY_PLACEMENTS] = n_ident;
+    plan->info[B200COMP_INFO_PRERESAMPLED_PLACEMENTS] = (int64_t)plan->pre.size();
+    plan->info[B200COMP_INFO_COEFF_BYTES] = (int64_t)tbytes;
+    plan->info[B200COMP_INFO_SMEM_BYTES] = (int64_t)plan->smem_bytes;
+    plan->info[B200COMP_INFO_TILES] = tiles;
+
+    guard.p = nullptr;
+    *out_plan = plan;
+    return 0;
+}
+
+int b200comp_plan_run(b200comp_plan *plan, void *stream) {
+    if (!plan) return fail(B200COMP_EINVAL, "plan_run: null plan");
+    cudaStream_t st = S(stream);
+    for (auto &pr : plan->pre) {
+        const int32_t *t = plan->d_tables;
+        int rc = resample_two_pass(pr.src, pr.sw, pr.sh, pr.sp, pr.dst, pr.w, pr.h, (int64_t)pr.w * 4, t + pr.tx.k_off,
+                                   t + pr.tx.b_off, pr.tx.ks, t + pr.ty.k_off, t + pr.ty.b_off, pr.ty.ks, pr.scratch,
+                                   pr.flags, st);
+        if (rc) return rc;
+    }
+    composite_tiles_kernel<<<(unsigned)plan->n_tiles, kThreads, plan->smem_bytes, st>>>(
+        plan->d_canvases, plan->n_canvases, plan->d_placements, plan->patch_words, plan->inter_words, plan->d_status);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int b200comp_plan_info(const b200comp_plan *plan, int64_t *info) {
+    if (!plan || !info) return fail(B200COMP_EINVAL, "plan_info: null argument");
+    std::memcpy(info, plan->info, sizeof plan->info);
+    return 0;
+}
+
+// Reads the device status word (shared-memory sizing violations); synchronises the stream.
+int b200comp_plan_check(b200comp_plan *plan, void *stream) {
+    if (!plan) return fail(B200COMP_EINVAL, "plan_check: null plan");
+    int h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, plan->d_status, sizeof h, cudaMemcpyDeviceToHost, S(stream)));
+    CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    if (h != 0) return fail(B200COMP_EINTERNAL, "tile kernel reported a shared-memory sizing violation (status " + std::to_string(h) + ")");
+    return 0;
+}
+
+int b200comp_composite_batch(const b200comp_canvas *canvases, int n_canvases, const b200comp_placement *placements,
+                             int n_placements, void *stream) {
+    b200comp_plan *plan = nullptr;
+    int rc = b200comp_plan_create(canvases, n_canvases, placements, n_placements, 0, stream, &plan);
+    if (rc) return rc;
+    rc = b200comp_plan_run(plan, stream);
+    if (!rc) rc = b200comp_plan_check(plan, stream);
+    b200comp_plan_destroy(plan);
+    return rc;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

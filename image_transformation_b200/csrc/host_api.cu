@@ -1,0 +1,304 @@
+// Host-buffer entry points of libb200comp.so: what a ctypes / cffi binding of the reference's
+// composite() / fill_solid() / fill_gradient() calls with plain host arrays.  They only use the
+// device-level C ABI declared in include/b200comp.h plus CUDA runtime copies.
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <thread>
+#include <tuple>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/b200comp.h"
+
+namespace {
+
+thread_local std::string g_host_err;
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int b200comp_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return B200COMP_EINVAL;
+    return cudaHostAlloc(ptr, std::max<size_t>(bytes, 1), cudaHostAllocDefault) == cudaSuccess ? 0 : B200COMP_ENOMEM;
+}
+
+int b200comp_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? 0 : B200COMP_ECUDA; }
+
+// internal: set the message returned by b200comp_last_error() (defined in b200comp.cu)
+int b200comp_set_error_(int code, const char *msg);
+
+int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvases,
+                                  const b200comp_placement *placements, int n_placements, int n_host_threads,
+                                  int chunk_canvases, int n_streams) {
+    if (n_canvases < 1 || !canvases || n_placements < 0 || (n_placements > 0 && !placements))
+        return b200comp_set_error_(B200COMP_EINVAL, "composite_batch_host: empty batch or null arrays");
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, "no CUDA device");
+    if (n_host_threads <= 0) n_host_threads = std::max(1u, std::thread::hardware_concurrency());
+    if (chunk_canvases <= 0) chunk_canvases = 8;
+    if (n_streams <= 0) n_streams = 3;
+    const int n_chunks = (n_canvases + chunk_canvases - 1) / chunk_canvases;
+    n_streams = std::min(n_streams, n_chunks);
+
+    // ---- cutouts: upload each distinct host cutout once, 16-byte aligned pitch ----
+    typedef std::tuple<const uint8_t *, int, int, int64_t> SrcKey;
+    std::map<SrcKey, size_t> src_off;
+    std::vector<SrcKey> src_order;
+    size_t pool_bytes = 0;
+    for (int i = 0; i < n_placements; ++i) {
+        const b200comp_placement &p = placements[i];
+        if (!p.src || p.sw < 1 || p.sh < 1 || p.w < 1 || p.h < 1 || p.src_pitch < (int64_t)p.sw * 4)
+            return b200comp_set_error_(B200COMP_EINVAL, "composite_batch_host: bad placement");
+        SrcKey k(p.src, p.sw, p.sh, p.src_pitch);
+        if (src_off.find(k) == src_off.end()) {
+            src_off[k] = pool_bytes;
+            src_order.push_back(k);
+            pool_bytes += align_up((size_t)p.sw * 4, 16) * p.sh;
+            pool_bytes = align_up(pool_bytes, 256);
+        }
+    }
+    DevBuf pool;
+    if (pool.alloc(pool_bytes) != cudaSuccess) return b200comp_set_error_(B200COMP_ENOMEM, "cutout pool allocation failed");
+    cudaStream_t s0;
+    if (cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking) != cudaSuccess)
+        return b200comp_set_error_(B200COMP_ECUDA, "stream creation failed");
+    for (const SrcKey &k : src_order) {
+        const int sw = std::get<1>(k), sh = std::get<2>(k);
+        cudaMemcpy2DAsync((uint8_t *)pool.p + src_off[k], align_up((size_t)sw * 4, 16), std::get<0>(k),
+                          (size_t)std::get<3>(k), (size_t)sw * 4, sh, cudaMemcpyHostToDevice, s0);
+    }
+    cudaError_t e0 = cudaStreamSynchronize(s0);
+    cudaStreamDestroy(s0);
+    if (e0 != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, cudaGetErrorString(e0));
+
+    // ---- per-stream worker: chunks of canvases, bg H2D -> fused kernel -> out D2H ----
+    size_t max_canvas_bytes = 0;
+    for (int c = 0; c < n_canvases; ++c) {
+        if (!canvases[c].out || canvases[c].W < 1 || canvases[c].H < 1)
+            return b200comp_set_error_(B200COMP_EINVAL, "composite_batch_host: bad canvas");
+        max_canvas_bytes = std::max(max_canvas_bytes, align_up((size_t)canvases[c].W * 4, 16) * canvases[c].H);
+    }
+    max_canvas_bytes = align_up(max_canvas_bytes, 256);
+    std::atomic<int> next_chunk(0);
+    std::atomic<int> first_rc(0);
+    std::vector<std::string> errs((size_t)n_streams);
+    const int builder_threads = std::max(1, n_host_threads / n_streams);
+
+    auto worker = [&](int tid) {
+        auto bail = [&](int rc, const std::string &m) {
+            int expected = 0;
+            if (first_rc.compare_exchange_strong(expected, rc)) errs[(size_t)tid] = m;
+        };
+        if (cudaSetDevice(device) != cudaSuccess) return bail(B200COMP_ECUDA, "cudaSetDevice failed");
+        cudaStream_t st;
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return bail(B200COMP_ECUDA, "stream creation failed");
+        DevBuf d_out, d_bg;
+        bool any_bg = false;
+        for (int c = 0; c < n_canvases; ++c) any_bg |= canvases[c].bg != nullptr;
+        if (d_out.alloc(max_canvas_bytes * chunk_canvases) != cudaSuccess ||
+            (any_bg && d_bg.alloc(max_canvas_bytes * chunk_canvases) != cudaSuccess)) {
+            cudaStreamDestroy(st);
+            return bail(B200COMP_ENOMEM, "canvas staging allocation failed");
+        }
+        std::vector<b200comp_canvas> cc;
+        std::vector<b200comp_placement> pp;
+        for (;;) {
+            const int chunk = next_chunk.fetch_add(1);
+            if (chunk >= n_chunks || first_rc.load() != 0) break;
+            const int c_lo = chunk * chunk_canvases, c_hi = std::min(n_canvases, c_lo + chunk_canvases);
+            cc.clear();
+            pp.clear();
+            for (int c = c_lo; c < c_hi; ++c) {
+                b200comp_canvas cv = canvases[c];
+                const size_t dp = align_up((size_t)cv.W * 4, 16);
+                uint8_t *o = (uint8_t *)d_out.p + (size_t)(c - c_lo) * max_canvas_bytes;
+                if (cv.bg) {
+                    uint8_t *b = (uint8_t *)d_bg.p + (size_t)(c - c_lo) * max_canvas_bytes;
+                    cudaMemcpy2DAsync(b, dp, cv.bg, (size_t)cv.bg_pitch, (size_t)cv.W * 4, cv.H, cudaMemcpyHostToDevice, st);
+                    cv.bg = b;
+                    cv.bg_pitch = (int64_t)dp;
+                }
+                cv.out = o;
+                cv.out_pitch = (int64_t)dp;
+                if (cv.n_placements < 0 || cv.first_placement < 0 || (int64_t)cv.first_placement + cv.n_placements > n_placements) {
+                    bail(B200COMP_EINVAL, "composite_batch_host: placement range out of bounds");
+                    break;
+                }
+                const int first = (int)pp.size();
+                for (int i = 0; i < cv.n_placements; ++i) {
+                    b200comp_placement p = placements[cv.first_placement + i];
+                    SrcKey k(p.src, p.sw, p.sh, p.src_pitch);
+                    p.src = (const uint8_t *)pool.p + src_off[k];
+                    p.src_pitch = (int64_t)align_up((size_t)p.sw * 4, 16);
+                    pp.push_back(p);
+                }
+                cv.first_placement = first;
+                cc.push_back(cv);
+            }
+            if (first_rc.load() != 0) break;
+            b200comp_plan *plan = nullptr;
+            int rc = b200comp_plan_create(cc.data(), (int)cc.size(), pp.data(), (int)pp.size(), builder_threads, st, &plan);
+            if (!rc) rc = b200comp_plan_run(plan, st);
+            if (!rc) {
+                for (int c = c_lo; c < c_hi; ++c) {
+                    const b200comp_canvas &cv = canvases[c];
+                    cudaMemcpy2DAsync(cv.out, (size_t)cv.out_pitch, cc[(size_t)(c - c_lo)].out,
+                                      (size_t)cc[(size_t)(c - c_lo)].out_pitch, (size_t)cv.W * 4, cv.H,
+                                      cudaMemcpyDeviceToHost, st);
+                }
+                rc = b200comp_plan_check(plan, st);  // synchronises the stream
+            }
+            if (rc) bail(rc, b200comp_last_error());
+            if (plan) b200comp_plan_destroy(plan);
+            if (rc) break;
+        }
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) bail(B200COMP_ECUDA, cudaGetErrorString(e));
+        cudaStreamDestroy(st);
+    };
+
+    if (n_streams == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_streams; ++t) th.emplace_back(worker, t);
+        for (auto &t : th) t.join();
+    }
+    cudaSetDevice(device);
+    if (first_rc.load() != 0) {
+        for (auto &m : errs)
+            if (!m.empty()) return b200comp_set_error_(first_rc.load(), m.c_str());
+        return b200comp_set_error_(first_rc.load(), "composite_batch_host failed");
+    }
+    return 0;
+}
+
+int b200comp_composite_host(const uint8_t *bg, int W, int H, size_t bg_pitch, uint8_t *out, size_t out_pitch,
+                            const b200comp_placement *placements, int n_placements) {
+    if (!bg || !out) return b200comp_set_error_(B200COMP_EINVAL, "composite_host: null canvas");
+    b200comp_canvas cv;
+    std::memset(&cv, 0, sizeof cv);
+    cv.out = out;
+    cv.out_pitch = (int64_t)out_pitch;
+    cv.bg = bg;
+    cv.bg_pitch = (int64_t)bg_pitch;
+    cv.W = W;
+    cv.H = H;
+    cv.first_placement = 0;
+    cv.n_placements = n_placements;
+    return b200comp_composite_batch_host(&cv, 1, placements, n_placements, 8, 1, 1);
+}
+
+// decoded image (HOST) -> tightly packed device copy
+static int upload_image(const uint8_t *img, int W, int H, size_t pitch, DevBuf &d, const char *who) {
+    if (!img || W < 1 || H < 1 || pitch < (size_t)W * 4)
+        return b200comp_set_error_(B200COMP_EINVAL, (std::string(who) + ": bad image argument").c_str());
+    if (d.alloc((size_t)W * 4 * H) != cudaSuccess)
+        return b200comp_set_error_(B200COMP_ENOMEM, (std::string(who) + ": device allocation failed").c_str());
+    cudaError_t e = cudaMemcpy2D(d.p, (size_t)W * 4, img, pitch, (size_t)W * 4, H, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, cudaGetErrorString(e));
+    return 0;
+}
+
+// _edge_strip_median_colors (background_resizing.py:36-55): left, right, top, bottom strips
+static int edge_medians_dev(const uint8_t *d_img, int W, int H, int strip_px, int32_t edges[12]) {
+    const int rects[4][4] = {{0, 0, std::min(strip_px, W), H},
+                             {std::max(0, W - strip_px), 0, W, H},
+                             {0, 0, W, std::min(strip_px, H)},
+                             {0, std::max(0, H - strip_px), W, H}};
+    for (int i = 0; i < 4; ++i) {
+        int rc = b200comp_masked_median_rgb(d_img, W, H, (size_t)W * 4, rects[i][0], rects[i][1], rects[i][2],
+                                            rects[i][3], edges + 3 * i, nullptr);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int b200comp_masked_median_rgb_host(const uint8_t *img, int W, int H, size_t pitch, int x0, int y0, int x1, int y1,
+                                    int32_t out_rgb[3]) {
+    DevBuf d;
+    int rc = upload_image(img, W, H, pitch, d, "masked_median_rgb_host");
+    if (rc) return rc;
+    return b200comp_masked_median_rgb((const uint8_t *)d.p, W, H, (size_t)W * 4, x0, y0, x1, y1, out_rgb, nullptr);
+}
+
+int b200comp_edge_strip_medians_host(const uint8_t *img, int W, int H, size_t pitch, int strip_px,
+                                     int32_t out_edges[12]) {
+    if (strip_px < 1 || !out_edges) return b200comp_set_error_(B200COMP_EINVAL, "edge_strip_medians_host: bad argument");
+    DevBuf d;
+    int rc = upload_image(img, W, H, pitch, d, "edge_strip_medians_host");
+    if (rc) return rc;
+    return edge_medians_dev((const uint8_t *)d.p, W, H, strip_px, out_edges);
+}
+
+int b200comp_fill_solid_host(const uint8_t *bg, int Wb, int Hb, size_t bg_pitch, uint8_t *out, int W, int H,
+                             size_t out_pitch, int32_t out_rgb[3]) {
+    if (!out || W < 1 || H < 1 || out_pitch < (size_t)W * 4)
+        return b200comp_set_error_(B200COMP_EINVAL, "fill_solid_host: bad canvas argument");
+    DevBuf d_bg, d_out;
+    int rc = upload_image(bg, Wb, Hb, bg_pitch, d_bg, "fill_solid_host");
+    if (rc) return rc;
+    if (d_out.alloc((size_t)W * 4 * H) != cudaSuccess)
+        return b200comp_set_error_(B200COMP_ENOMEM, "fill_solid_host: device allocation failed");
+    int32_t rgb[3];
+    rc = b200comp_masked_median_rgb((const uint8_t *)d_bg.p, Wb, Hb, (size_t)Wb * 4, 0, 0, Wb, Hb, rgb, nullptr);
+    if (rc) return rc;
+    const uint32_t rgba = (uint32_t)rgb[0] | ((uint32_t)rgb[1] << 8) | ((uint32_t)rgb[2] << 16) | 0xff000000u;
+    rc = b200comp_fill_rgba((uint8_t *)d_out.p, W, H, (size_t)W * 4, rgba, nullptr);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpy2D(out, out_pitch, d_out.p, (size_t)W * 4, (size_t)W * 4, H, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, cudaGetErrorString(e));
+    if (out_rgb) std::memcpy(out_rgb, rgb, sizeof rgb);
+    return 0;
+}
+
+int b200comp_fill_gradient_host(const uint8_t *bg, int Wb, int Hb, size_t bg_pitch, uint8_t *out, int W, int H,
+                                size_t out_pitch, int strip_px, int32_t out_edges[12], int *out_horizontal) {
+    if (!out || W < 1 || H < 1 || strip_px < 1 || out_pitch < (size_t)W * 4)
+        return b200comp_set_error_(B200COMP_EINVAL, "fill_gradient_host: bad argument");
+    DevBuf d_bg, d_out;
+    int rc = upload_image(bg, Wb, Hb, bg_pitch, d_bg, "fill_gradient_host");
+    if (rc) return rc;
+    if (d_out.alloc((size_t)W * 4 * H) != cudaSuccess)
+        return b200comp_set_error_(B200COMP_ENOMEM, "fill_gradient_host: device allocation failed");
+    int32_t edges[12];
+    rc = edge_medians_dev((const uint8_t *)d_bg.p, Wb, Hb, strip_px, edges);
+    if (rc) return rc;
+    // _axis_variance (:58-60) and the direction choice (:69-80): squared colour distance, ties -> horizontal
+    auto dist = [&](int a, int b) {
+        double s = 0;
+        for (int c = 0; c < 3; ++c) {
+            const double d = (double)edges[3 * a + c] - (double)edges[3 * b + c];
+            s += d * d;
+        }
+        return s;
+    };
+    const int horizontal = dist(0, 1) <= dist(2, 3) ? 1 : 0;
+    const int32_t *c1 = horizontal ? edges : edges + 6;
+    const int32_t *c2 = horizontal ? edges + 3 : edges + 9;
+    rc = b200comp_fill_gradient((uint8_t *)d_out.p, W, H, (size_t)W * 4, horizontal, c1, c2, nullptr);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpy2D(out, out_pitch, d_out.p, (size_t)W * 4, (size_t)W * 4, H, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, cudaGetErrorString(e));
+    if (out_edges) std::memcpy(out_edges, edges, sizeof edges);
+    if (out_horizontal) *out_horizontal = horizontal;
+    return 0;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

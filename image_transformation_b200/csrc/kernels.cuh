@@ -1,0 +1,120 @@
+// Device code of the B200 compositor hot path (sm_100a).  Integer-exact restatement of
+// the Pillow arithmetic reached from /root/reference/compositor.py:20-21 and
+// /root/reference/background_resizing.py:11-33,74-97; see DESIGN.md for the layout.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200comp {
+
+// ------------------------------------------------------------------ descriptors
+struct DevPlacement {
+    const uint8_t *src;  // cutout (identity) or pre-resampled temp
+    const int32_t *kx;   // [w][ksx] 22-bit fixed point, zero padded
+    const int32_t *bx;   // [w][2]   (xmin, xmax)
+    const int32_t *ky;   // [h][ksy]
+    const int32_t *by;   // [h][2]
+    int32_t src_pitch;   // bytes
+    int32_t sw, sh;
+    int32_t x, y, w, h;  // destination box (top-left, resampled size)
+    int32_t ksx, ksy;    // taps per output sample (1 = pass skipped: identity table)
+    int32_t mode;        // 0 = plain over of src (w x h), 1 = resample in the tile kernel
+    int32_t pad_[3];
+};
+static_assert(sizeof(DevPlacement) == 96, "DevPlacement layout");
+
+struct DevCanvas {
+    uint8_t *out;
+    const uint8_t *bg;  // may be null -> solid
+    int64_t out_pitch;
+    int64_t bg_pitch;
+    int64_t tile_base;  // first tile index of this canvas in the launch
+    uint32_t solid;
+    int32_t W, H;
+    int32_t first, count;  // placement range
+    int32_t tiles_x, tiles_y;
+    int32_t pad_;
+};
+static_assert(sizeof(DevCanvas) == 72, "DevCanvas layout");
+
+constexpr int kTileW = 64;
+constexpr int kTileH = 32;
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kCtPitch = kTileW + 1;  // odd pitch: row-per-lane accesses hit distinct banks
+constexpr int kInterPitch = kTileW + 1;
+constexpr int kPrecisionBits = 22;
+
+enum : int { kStatusPatchOverflow = 1, kStatusInterOverflow = 2 };
+
+// ------------------------------------------------------------------ pixel arithmetic
+// ImagingUtils.h MULDIV255
+__device__ __forceinline__ uint32_t muldiv255(uint32_t a, uint32_t b) {
+    uint32_t t = a * b + 128u;
+    return ((t >> 8) + t) >> 8;
+}
+__device__ __forceinline__ uint32_t shiftfordiv255(uint32_t a) { return ((a >> 8) + a) >> 8; }
+
+// Convert.c rgbA2rgba: RGBA -> RGBa
+__device__ __forceinline__ uint32_t premultiply_px(uint32_t p) {
+    const uint32_t a = p >> 24;
+    if (a == 255u) return p;
+    if (a == 0u) return 0u;
+    const uint32_t r = muldiv255(p & 0xffu, a);
+    const uint32_t g = muldiv255((p >> 8) & 0xffu, a);
+    const uint32_t b = muldiv255((p >> 16) & 0xffu, a);
+    return r | (g << 8) | (b << 16) | (a << 24);
+}
+
+// Convert.c rgba2rgbA: RGBa -> RGBA, truncating divide, clip
+__device__ __forceinline__ uint32_t unpremultiply_px(uint32_t p) {
+    const uint32_t a = p >> 24;
+    if (a == 255u || a == 0u) return p;
+    const uint32_t r = min(255u, (255u * (p & 0xffu)) / a);
+    const uint32_t g = min(255u, (255u * ((p >> 8) & 0xffu)) / a);
+    const uint32_t b = min(255u, (255u * ((p >> 16) & 0xffu)) / a);
+    return r | (g << 8) | (b << 16) | (a << 24);
+}
+
+// AlphaComposite.c ImagingAlphaComposite, one pixel: src over dst
+__device__ __forceinline__ uint32_t over_px(uint32_t d, uint32_t s) {
+    const uint32_t sa = s >> 24;
+    if (sa == 0u) return d;
+    if (sa == 255u) return s;  // coef2 == 0 and the rounding is exact: the source pixel itself
+    const uint32_t da = d >> 24;
+    uint32_t coef1, outa;
+    if (da == 255u) {  // opaque canvas: outa255 == 255*255, division-free
+        coef1 = sa * 128u;
+        outa = 255u;
+    } else {
+        const uint32_t blend = da * (255u - sa);
+        const uint32_t outa255 = sa * 255u + blend;
+        coef1 = sa * 255u * 255u * 128u / outa255;
+        outa = shiftfordiv255(outa255 + 0x80u);
+    }
+    const uint32_t coef2 = 255u * 128u - coef1;
+    const uint32_t r = shiftfordiv255((s & 0xffu) * coef1 + (d & 0xffu) * coef2 + (0x80u << 7)) >> 7;
+    const uint32_t g = shiftfordiv255(((s >> 8) & 0xffu) * coef1 + ((d >> 8) & 0xffu) * coef2 + (0x80u << 7)) >> 7;
+    const uint32_t b = shiftfordiv255(((s >> 16) & 0xffu) * coef1 + ((d >> 16) & 0xffu) * coef2 + (0x80u << 7)) >> 7;
+    return r | (g << 8) | (b << 16) | (outa << 24);
+}
+
+// Resample.c clip8: arithmetic shift then clamp
+__device__ __forceinline__ uint32_t clip8(int32_t v) { return (uint32_t)min(255, max(0, v >> kPrecisionBits)); }
+
+__device__ __forceinline__ uint32_t pack_clip(int32_t a0, int32_t a1, int32_t a2, int32_t a3) {
+    return clip8(a0) | (clip8(a1) << 8) | (clip8(a2) << 16) | (clip8(a3) << 24);
+}
+
+__device__ __forceinline__ void mac_px(int32_t &a0, int32_t &a1, int32_t &a2, int32_t &a3, uint32_t p, int32_t k) {
+    a0 += (int32_t)(p & 0xffu) * k;
+    a1 += (int32_t)((p >> 8) & 0xffu) * k;
+    a2 += (int32_t)((p >> 16) & 0xffu) * k;
+    a3 += (int32_t)(p >> 24) * k;
+}
+
+__device__ __forceinline__ uint32_t ld_px(const uint8_t *base, int64_t off) {
+    return __ldg(reinterpret_cast<const uint32_t *>(base + off));
+}
+
+}  // namespace b200comp

@@ -1,0 +1,364 @@
+"""GPU parity tests (run on the B200 with `-m gpu`): every CUDA entry point, called through the
+C ABI, against the CPU oracle and the committed golden vectors -- bit-exact."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import golden_io as G
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def B():
+    from image_transformation_b200 import batch
+
+    return batch
+
+
+def dev(a: np.ndarray):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t) -> np.ndarray:
+    return t.cpu().numpy()
+
+
+def assert_same(got: np.ndarray, exp: np.ndarray, what=""):
+    if not np.array_equal(got, exp):
+        d = np.abs(got.astype(int) - exp.astype(int))
+        bad = np.argwhere(d.any(axis=-1))
+        raise AssertionError(f"{what}: {len(bad)} pixels differ (max {d.max()}), first at {bad[:5].tolist()}")
+
+
+# ------------------------------------------------------------------------------ stage kernels
+@pytest.mark.parametrize("entry", G.manifest()["stage"]["resize"], ids=lambda e: e["key"])
+def test_resize_golden(B, entry):
+    src = G.stage(entry["key"] + "/src")
+    exp = G.stage(entry["key"] + "/out")
+    sw, sh = entry["src"]
+    w, h = entry["dst"]
+    vf = sh > 100 * sw and h < sh
+    out = host(B.resize_rgba_lanczos(dev(src), (w, h), vertical_first=vf))
+    assert_same(out, exp, entry["key"])
+
+
+def test_resize_random_sweep_vs_oracle(B):
+    rng = np.random.default_rng(21)
+    for _ in range(40):
+        sw, sh = (int(v) for v in rng.integers(1, 300, 2))
+        w, h = (int(v) for v in rng.integers(1, 300, 2))
+        src = rng.integers(0, 256, (sh, sw, 4), dtype=np.uint8)
+        if rng.random() < 0.5:
+            src[..., 3] = np.where(rng.random((sh, sw)) < 0.3, 0, np.where(rng.random((sh, sw)) < 0.7, 255, src[..., 3]))
+        exp = oracle.resize_rgba_lanczos(src, (w, h), vertical_first_rule=False)
+        assert_same(host(B.resize_rgba_lanczos(dev(src), (w, h))), exp, f"{sw}x{sh}->{w}x{h}")
+
+
+def test_resize_with_pitch(B):
+    rng = np.random.default_rng(22)
+    big = rng.integers(0, 256, (90, 160, 4), dtype=np.uint8)
+    view = dev(big)[7:80, 12:131]  # non-contiguous rows: pitch != width*4
+    exp = oracle.resize_rgba_lanczos(big[7:80, 12:131], (61, 50))
+    assert_same(host(B.resize_rgba_lanczos(view, (61, 50))), exp)
+
+
+@pytest.mark.parametrize("entry", G.manifest()["stage"]["over"], ids=lambda e: e["key"])
+def test_alpha_over_golden(B, entry):
+    key = entry["key"]
+    exp = G.stage(key + "/out")
+    if "grid" in key:
+        sa, da = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8))
+        s = np.zeros((256, 256, 4), np.uint8)
+        d = np.zeros((256, 256, 4), np.uint8)
+        s[..., :3] = entry["src_rgb"]
+        d[..., :3] = entry["dst_rgb"]
+        s[..., 3] = sa
+        d[..., 3] = da
+    else:
+        s, d = G.stage(key + "/src"), G.stage(key + "/dst")
+    canvas = dev(d)
+    B.alpha_over_(canvas, dev(s), (0, 0))
+    assert_same(host(canvas), exp, key)
+
+
+def test_alpha_over_clipping(B):
+    rng = np.random.default_rng(23)
+    d = rng.integers(0, 256, (40, 50, 4), dtype=np.uint8)
+    s = rng.integers(0, 256, (30, 35, 4), dtype=np.uint8)
+    for dest in [(-10, -5), (30, 25), (-40, 0), (60, 60), (0, 39), (49, 0)]:
+        exp = d.copy()
+        oracle.alpha_over_inplace(exp, s, dest)
+        canvas = dev(d)
+        B.alpha_over_(canvas, dev(s), dest)
+        assert_same(host(canvas), exp, str(dest))
+
+
+def test_premultiply_roundtrip_exhaustive_through_resize(B):
+    # every (colour, alpha) pair goes through premultiply -> 1-tap-equivalent V pass -> un-premultiply
+    grid = G.stage("premul/in")
+    exp = oracle.resize_rgba_lanczos(grid, (256, 255))
+    assert_same(host(B.resize_rgba_lanczos(dev(grid), (256, 255))), exp)
+
+
+@pytest.mark.parametrize("entry", G.manifest()["stage"]["median"], ids=lambda e: e["key"])
+def test_median_golden(B, entry):
+    a = G.stage(entry["key"] + "/in")
+    assert list(B.masked_median_rgb(dev(a))) == entry["median"]
+
+
+def test_median_large_and_strips(B):
+    from image_transformation_b200 import synth
+
+    a = synth.synthetic_background(1543, 877)
+    t = dev(a)
+    assert B.masked_median_rgb(t) == oracle.masked_median_rgb(a)
+    for rect in [(0, 0, 8, 877), (1535, 0, 1543, 877), (0, 0, 1543, 8), (0, 869, 1543, 877), (100, 50, 101, 51)]:
+        assert B.masked_median_rgb(t, rect) == oracle.masked_median_rgb(a, rect), rect
+    flat = np.zeros((512, 2048, 4), np.uint8)
+    flat[...] = (9, 200, 77, 255)
+    flat[100:110, :, 3] = 0
+    assert B.masked_median_rgb(dev(flat)) == (9, 200, 77)
+
+
+def test_fill_and_gradient(B):
+    for (W, H) in [(1, 1), (5, 3), (640, 360), (1001, 37)]:
+        t = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+        B.fill_rgba_(t, (220, 238, 245, 255))
+        assert (host(t) == np.array([220, 238, 245, 255], np.uint8)).all()
+        padded = torch.zeros((H, W + 3, 4), dtype=torch.uint8, device="cuda")
+        B.fill_rgba_(padded[:, 1:W + 1], (1, 2, 3, 4))
+        hp = host(padded)
+        assert (hp[:, 1:W + 1] == np.array([1, 2, 3, 4], np.uint8)).all() and (hp[:, 0] == 0).all() and (hp[:, W + 1:] == 0).all()
+    n = 0
+    for f in G.manifest()["stage"]["fill"]:
+        if "synthetic" not in f:
+            continue
+        w, h = f["size"]
+        key = f"gradient/synth{f['synthetic']}/{w}x{h}"
+        src = G.stage(key + "/in")
+        left, right, top, bottom = oracle.edge_strip_median_colors(src)
+        horizontal = f["synthetic"] == 0
+        t = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+        B.fill_gradient_(t, horizontal, left if horizontal else top, right if horizontal else bottom)
+        assert_same(host(t), G.stage(key + "/out"), key)
+        n += 1
+    assert n == 6
+
+
+# ------------------------------------------------------------------------------ drop-in API
+def pil(a):
+    from PIL import Image
+
+    return Image.fromarray(np.ascontiguousarray(a))
+
+
+@pytest.mark.parametrize("name", G.case_names())
+def test_composite_dropin_golden(name):
+    from image_transformation_b200.compositor import composite
+
+    bg, objs, pl, exp = G.case(name)
+    bg_img = pil(bg)
+    out = composite(bg_img, {k: pil(v) for k, v in objs.items()}, pl)
+    assert out.mode == "RGBA" and out.size == (bg.shape[1], bg.shape[0])
+    assert_same(np.array(out), exp, name)
+    assert_same(np.array(bg_img), bg, "background mutated")
+    assert_same(oracle.composite(bg, objs, pl), exp, "oracle drifted from golden")
+
+
+def test_reference_unit_test_through_dropin():
+    # /root/reference/tests/test_compositor.py:5-11, verbatim semantics
+    from PIL import Image
+    from image_transformation_b200.compositor import composite
+
+    bg = Image.new("RGBA", (10, 10), (255, 0, 0, 255))
+    obj = Image.new("RGBA", (2, 2), (0, 255, 0, 255))
+    out = composite(bg, {1: obj}, [{"object_id": 1, "box": [4, 4, 6, 6]}])
+    assert out.getpixel((4, 4))[:3] == (0, 255, 0)
+    out.putpixel((0, 0), (1, 2, 3, 4))  # result is a real, mutable image
+
+
+def test_dropin_error_conventions():
+    from PIL import Image
+    from image_transformation_b200.compositor import composite
+
+    bg = Image.new("RGBA", (10, 10), (255, 0, 0, 255))
+    obj = Image.new("RGBA", (2, 2), (0, 255, 0, 255))
+    with pytest.raises(ValueError, match="wrong mode"):
+        composite(bg.convert("RGB"), {1: obj}, [{"object_id": 1, "box": [0, 0, 2, 2]}])
+    with pytest.raises(ValueError, match="do not match"):
+        composite(bg, {1: obj.convert("RGB")}, [{"object_id": 1, "box": [0, 0, 2, 2]}])
+    with pytest.raises(KeyError):
+        composite(bg, {1: obj}, [{"object_id": 1}])
+    with pytest.raises(ValueError):
+        composite(bg, {1: obj}, [{"object_id": "a", "box": [0, 0, 2, 2]}])
+    out = composite(bg, {1: obj}, [{"object_id": 5, "box": [0, 0, 2, 2]}])  # unknown id: silently skipped
+    assert np.array_equal(np.array(out), np.array(bg))
+
+
+def test_background_resizing_dropin(tmp_path):
+    from PIL import Image
+    from image_transformation_b200 import background_resizing as br
+
+    for name in ("squarespace", "audio_book"):
+        bg, _ = G.bundle(name)
+        path = str(tmp_path / f"{name}.png")
+        Image.fromarray(bg).save(path)
+        info = G.manifest()["bundles"][name]
+        img = br._load_background_rgba(path)
+        assert list(br._median_color_nontransparent(img)) == info["median_color"]
+        assert [list(c) for c in br._edge_strip_median_colors(img)] == info["edge_strip_medians"]
+        for f in G.manifest()["stage"]["fill"]:
+            if f.get("bundle") != name:
+                continue
+            size = tuple(f["size"])
+            solid = br.fill_solid(path, size)
+            assert solid.mode == "RGBA" and solid.size == size
+            assert G.sha(np.array(solid)) == f["solid_sha256"], ("solid", name, size)
+            grad = br.fill_gradient(path, size)
+            assert G.sha(np.array(grad)) == f["gradient_sha256"], ("gradient", name, size)
+    assert br._axis_variance((1, 2, 3), (4, 6, 8)) == 50.0
+
+
+# ------------------------------------------------------------------------------ batched device API
+def run_batch(B, pool_arrays, sizes, placements, bgs=None, solid=None):
+    pool = B.CutoutPool(pool_arrays)
+    bg_t = None if bgs is None else [None if b is None else dev(b) for b in bgs]
+    cb = B.CompositeBatch(pool, sizes, placements, backgrounds=bg_t, solid=solid)
+    cb.run()
+    cb.check()
+    outs = [host(o) for o in cb.outputs()]
+    info = cb.info
+    cb.close()
+    return outs, info
+
+
+def test_batch_matches_golden_cases(B):
+    # all bundle cases of one bundle in ONE launch (different canvas sizes in the same batch)
+    names = [c["name"] for c in G.manifest()["cases"] if c.get("bundle") == "audio_book"]
+    _, objs = G.bundle("audio_book")
+    cases = [G.case(n) for n in names]
+    outs, info = run_batch(B, objs, [(c[0].shape[1], c[0].shape[0]) for c in cases], [c[2] for c in cases],
+                           bgs=[c[0] for c in cases])
+    for n, c, o in zip(names, cases, outs):
+        assert_same(o, c[3], n)
+    assert info["launches_per_run"] == 1 and info["tiles"] > 0
+
+
+def test_batch_random_vs_oracle_mixed_scales(B):
+    from image_transformation_b200 import synth
+
+    rng = np.random.default_rng(31)
+    pool = synth.make_pool(10, 40, 400, seed=5)
+    sizes_by_id = {k: (v.shape[1], v.shape[0]) for k, v in pool.items()}
+    canvases, placements, bgs, solids = [], [], [], []
+    for ci in range(6):
+        W, H = int(rng.integers(200, 1300)), int(rng.integers(150, 900))
+        canvases.append((W, H))
+        pl = []
+        for _ in range(12):
+            oid = int(rng.integers(1, 11))
+            sw, sh = sizes_by_id[oid]
+            mode = rng.random()
+            if mode < 0.15:
+                w, h = sw, sh
+            elif mode < 0.3:
+                w, h = sw, max(1, int(sh * rng.uniform(0.3, 2.0)))  # single axis
+            elif mode < 0.4:
+                w, h = max(1, int(sw * rng.uniform(0.05, 0.3))), max(1, int(sh * rng.uniform(0.05, 0.3)))  # heavy downscale
+            else:
+                w, h = max(1, int(sw * rng.uniform(0.4, 2.5))), max(1, int(sh * rng.uniform(0.4, 2.5)))
+            x, y = int(rng.integers(-w // 2, W)), int(rng.integers(-h // 2, H))
+            pl.append({"object_id": oid, "box": [x, y, x + w, y + h]})
+        placements.append(pl)
+        if ci % 2 == 0:
+            bg = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+            if ci % 4 == 0:
+                bg[..., 3] = 255
+            bgs.append(bg)
+            solids.append((0, 0, 0, 0))
+        else:
+            bgs.append(None)
+            solids.append((int(rng.integers(0, 256)), 238, 245, 255))
+    outs, info = run_batch(B, pool, canvases, placements, bgs=bgs, solid=solids)
+    for ci, o in enumerate(outs):
+        W, H = canvases[ci]
+        bg = bgs[ci]
+        if bg is None:
+            bg = np.zeros((H, W, 4), np.uint8)
+            bg[...] = solids[ci]
+        assert_same(o, oracle.composite(bg, pool, placements[ci]), f"canvas {ci}")
+    assert info["fused_placements"] > 0 and info["identity_placements"] > 0
+
+
+def test_batch_extreme_scales_use_preresample_path(B):
+    rng = np.random.default_rng(32)
+    pool = {1: rng.integers(0, 256, (900, 1200, 4), dtype=np.uint8), 2: rng.integers(0, 256, (400, 3, 4), dtype=np.uint8),
+            3: rng.integers(0, 256, (1, 1, 4), dtype=np.uint8)}
+    pl = [{"object_id": 1, "box": [5, 5, 45, 35]},      # 30x downscale: ksize 181 -> generic kernels
+          {"object_id": 2, "box": [60, 2, 69, 4]},      # Pillow-12 vertical-first
+          {"object_id": 3, "box": [10, 50, 200, 140]},  # 1x1 upscaled
+          {"object_id": 1, "box": [100, 20, 700, 470]}]  # 2x downscale, fused
+    bg = rng.integers(0, 256, (480, 720, 4), dtype=np.uint8)
+    bg[..., 3] = 255
+    outs, info = run_batch(B, pool, [(720, 480)], [pl], bgs=[bg])
+    assert_same(outs[0], oracle.composite(bg, pool, pl))
+    assert info["preresampled_placements"] == 2 and info["launches_per_run"] > 1
+
+
+def test_batch_c3_canvas_full_size_vs_oracle(B):
+    # one real C3 canvas (3840x2160, 20 objects, pool cutouts 256..1536 px, scale 0.5..1) bit-exact vs the oracle
+    from image_transformation_b200 import synth
+
+    pool = synth.make_pool(12, 256, 1536, seed=1234)
+    sizes_by_id = {k: (v.shape[1], v.shape[0]) for k, v in pool.items()}
+    idx = [0, 3]
+    pls = [synth.canvas_placements(sizes_by_id, (3840, 2160), i) for i in idx]
+    outs, info = run_batch(B, pool, [(3840, 2160)] * len(idx), pls, solid=(220, 238, 245, 255))
+    for i, o, pl in zip(idx, outs, pls):
+        bg = np.empty((2160, 3840, 4), np.uint8)
+        bg[...] = (220, 238, 245, 255)
+        assert_same(o, oracle.composite(bg, pool, pl), f"C3 canvas {i}")
+    assert info["preresampled_placements"] == 0 and info["launches_per_run"] == 1
+
+
+def test_batch_properties_at_scale(B):
+    """Size-independent properties on a larger batch: determinism, batch == single-canvas
+    launches, transparent overlays are the identity, opaque identity overlay replaces pixels."""
+    from image_transformation_b200 import synth
+
+    pool = synth.make_pool(8, 256, 1024, seed=77)
+    sizes_by_id = {k: (v.shape[1], v.shape[0]) for k, v in pool.items()}
+    n = 12
+    pls = [synth.canvas_placements(sizes_by_id, (3840, 2160), i, n_objects=20) for i in range(n)]
+    o1, _ = run_batch(B, pool, [(3840, 2160)] * n, pls, solid=(10, 20, 30, 255))
+    o2, _ = run_batch(B, pool, [(3840, 2160)] * n, pls, solid=(10, 20, 30, 255))
+    for a, b in zip(o1, o2):
+        assert np.array_equal(a, b)
+    for i in (0, n - 1):
+        single, _ = run_batch(B, pool, [(3840, 2160)], [pls[i]], solid=(10, 20, 30, 255))
+        assert np.array_equal(single[0], o1[i])
+    clear = {k: np.zeros_like(v) for k, v in pool.items()}  # alpha 0 everywhere -> canvas unchanged
+    oc, _ = run_batch(B, clear, [(3840, 2160)], [pls[0]], solid=(10, 20, 30, 255))
+    assert (oc[0] == np.array([10, 20, 30, 255], np.uint8)).all()
+    opaque = pool[1].copy()
+    opaque[..., 3] = 255
+    sw, sh = sizes_by_id[1]
+    oo, _ = run_batch(B, {1: opaque}, [(3840, 2160)], [[{"object_id": 1, "box": [100, 50, 100 + sw, 50 + sh]}]],
+                      solid=(10, 20, 30, 255))
+    assert np.array_equal(oo[0][50:50 + sh, 100:100 + sw], opaque)
+
+
+def test_batch_rejects_bad_arguments(B):
+    pool = B.CutoutPool({1: np.zeros((4, 4, 4), np.uint8)})
+    with pytest.raises(ValueError):
+        B.CompositeBatch(pool, [(10, 10)], [])
+    with pytest.raises(ValueError):
+        B.CompositeBatch(pool, [(0, 10)], [[]])
+    with pytest.raises(ValueError):
+        B.CutoutPool({1: np.zeros((4, 4, 3), np.uint8)})

@@ -1,0 +1,106 @@
+"""CPU-only tests: host-side mirror of the reference interface, the C-ABI library's exports,
+and the host coefficient builder (the one part of the product that is not a kernel)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from image_transformation_b200 import _native, synth
+from image_transformation_b200.compositor import resolve_placements
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "b200comp.h")).read()
+    declared = set(re.findall(r"\b(b200comp_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes parsed"
+    assert declared == set(_native.EXPORTED)
+    L = _native.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert L.b200comp_abi_version() == 1
+    assert L.b200comp_device_count() >= 0
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_native.Placement) == 48
+    assert ctypes.sizeof(_native.Canvas) == 56
+
+
+def test_no_gpu_fails_loudly():
+    if _native.lib().b200comp_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    from PIL import Image
+    from image_transformation_b200.compositor import composite
+
+    bg = Image.new("RGBA", (10, 10), (255, 0, 0, 255))
+    obj = Image.new("RGBA", (2, 2), (0, 255, 0, 255))
+    with pytest.raises(_native.B200CompError):
+        composite(bg, {1: obj}, [{"object_id": 1, "box": [4, 4, 6, 6]}])
+
+
+@pytest.mark.parametrize("pair", [(64, 32), (33, 64), (1536, 1), (100, 99), (7, 7), (256, 255), (1024, 513),
+                                  (1365, 1024), (3, 400), (400, 3), (1, 1), (2, 1), (1, 2), (977, 611)])
+def test_coefficient_builder_matches_oracle(pair):
+    in_size, out_size = pair
+    L = _native.lib()
+    ks = L.b200comp_ksize(in_size, out_size)
+    k = np.full((out_size, ks), 12345, np.int32)
+    b = np.zeros((out_size, 2), np.int32)
+    got = ctypes.c_int(0)
+    assert L.b200comp_build_coeffs(in_size, out_size, k.ctypes.data, b.ctypes.data, ctypes.byref(got)) == 0
+    ko, bo, kso = oracle.coeffs(in_size, out_size)
+    assert got.value == ks == kso
+    assert np.array_equal(k, ko) and np.array_equal(b, bo)
+
+
+def test_coefficient_builder_rejects_bad_sizes():
+    L = _native.lib()
+    assert L.b200comp_ksize(0, 5) == -1
+    assert "positive" in _native.last_error()
+    assert L.b200comp_build_coeffs(4, 4, None, None, None) == -1
+
+
+def test_resolve_placements_reference_semantics():
+    sizes = {1: (10, 20), 2: (3, 400)}
+    pl = [
+        {"object_id": "1", "box": [1.9, -2.9, 11.2, 17.5]},   # str id, float box -> int() truncation toward 0
+        {"object_id": 7, "box": "not even looked at"},        # unknown id skipped before the box is read
+        {"object_id": 1, "box": [5, 5, 5, 2]},                # degenerate -> 1x1
+        {"object_id": 2, "box": [0, 0, 9, 2]},                # tall image, shrinking height -> vertical first
+        {"object_id": True, "box": [0, 0, 1, 1]},             # bool is an int: key 1
+    ]
+    r = resolve_placements(pl, sizes)
+    assert r[0] == (1, 1, -2, 10, 19, 0)
+    assert r[1] == (1, 5, 5, 1, 1, 0)
+    assert r[2] == (2, 0, 0, 9, 2, _native.VERTICAL_FIRST)
+    assert r[3][0] is True or r[3][0] == 1
+    with pytest.raises(KeyError):
+        resolve_placements([{"object_id": 1}], sizes)
+    with pytest.raises(KeyError):
+        resolve_placements([{"box": [0, 0, 1, 1]}], sizes)
+    with pytest.raises(ValueError):
+        resolve_placements([{"object_id": "a", "box": [0, 0, 1, 1]}], sizes)
+    with pytest.raises(ValueError):
+        resolve_placements([{"object_id": 1, "box": [0, 0, 1]}], sizes)
+    with pytest.raises((ValueError, TypeError)):
+        resolve_placements([{"object_id": 1, "box": [0, 0, 1, None]}], sizes)
+
+
+def test_synthetic_workload_is_deterministic_and_in_spec():
+    sizes = {i: (300 + 7 * i, 900 - 5 * i) for i in range(1, 9)}
+    a = synth.canvas_placements(sizes, (3840, 2160), 5)
+    b = synth.canvas_placements(sizes, (3840, 2160), 5)
+    assert a == b and len(a) == 20
+    for p in a:
+        x1, y1, x2, y2 = p["box"]
+        sw, sh = sizes[p["object_id"]]
+        assert 0.49 <= (x2 - x1) / sw <= 1.01 and x1 >= 0 and y1 >= 0
+    u = synth.canvas_placements(sizes, (7680, 4320), 0, n_objects=64, layout="uniform")
+    assert len(u) == 64
+    st = synth.alpha_stats(synth.make_pool(4, 64, 128))
+    assert 0.2 < st["transparent"] < 0.4 and 0.5 < st["opaque"] < 0.75
