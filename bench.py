@@ -1,0 +1,444 @@
+#!/usr/bin/env python3
+"""Benchmark of the compositor hot path (BASELINE.json metric: composited megapixels/s and
+canvases/s at 4K, HBM GB/s vs peak, 1/2/4/8 GPUs).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU port of the reference path
+
+A "step" is one pass of the fused resample + alpha-over kernel over one batch of synthetic
+canvases (workload c3_4k_20obj = BASELINE.json configs[2]: 3840x2160 canvases, 20 RGBA cutouts
+each, scale 0.5..1.0, random flex layouts).  Canvases are independent: every rank owns `--batch`
+canvases (weak scaling), there is no collective on the data path.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "composited_canvas_megapixels_per_s"
+UNIT = "MP/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3_4k_20obj")
+    ap.add_argument("--batch", type=int, default=0, help="canvases per GPU per step (0: workload default, capped by HBM)")
+    ap.add_argument("--e2e-batch", type=int, default=64, help="canvases per end-to-end (host buffer) step")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="canvases in the CPU baseline sample (0: auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--solid-bg", action="store_true", help="synthesise the solid background in-kernel (no bg read)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------ helpers
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, torch copy read+write)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def traffic_ratio():
+    """dram bytes / algorithmic bytes of the fused kernel from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_per_launch"]) / float(d["algorithmic_bytes_per_launch"]), d.get("source", path)
+    except Exception:
+        return None, None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+                power.append(float(p[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def build_inputs(workload: str, lo: int, hi: int):
+    from image_transformation_b200 import synth
+
+    pool = synth.workload_pool(workload)
+    sizes = {k: (v.shape[1], v.shape[0]) for k, v in pool.items()}
+    canvases = [synth.workload_canvas_size(workload, i) for i in range(lo, hi)]
+    placements = [synth.workload_placements(workload, sizes, i) for i in range(lo, hi)]
+    return pool, canvases, placements
+
+
+def bg_colour(i: int):
+    # one solid colour per canvas (what fill_solid hands to composite()); varied so buffers differ
+    return ((37 * i + 220) % 256, (91 * i + 238) % 256, (53 * i + 245) % 256, 255)
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_port_throughput(pool, canvases, placements, n_threads: int, repeats: int = 1):
+    """Oracle port (oracle/compositor_oracle.c) of the reference composite(), one canvas per
+    task on `n_threads` host threads (ctypes releases the GIL)."""
+    import oracle
+
+    oracle.lib()
+    bgs = []
+    for i, (W, H) in enumerate(canvases):
+        b = np.empty((H, W, 4), np.uint8)
+        b[...] = bg_colour(i)
+        bgs.append(b)
+
+    def one(i):
+        oracle.composite(bgs[i], pool, placements[i])
+        return canvases[i][0] * canvases[i][1]
+
+    best = None
+    with ThreadPoolExecutor(n_threads) as ex:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            px = sum(ex.map(one, range(len(canvases))))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return px / 1e6 / best, len(canvases) / best, best
+
+
+def pillow_throughput(pool, canvases, placements, n_threads: int):
+    """Same sample through Pillow itself (the library the reference calls), for information."""
+    try:
+        from PIL import Image
+    except Exception:
+        return None
+    ims = {k: Image.fromarray(v) for k, v in pool.items()}
+
+    def one(i):
+        W, H = canvases[i]
+        c = Image.new("RGBA", (W, H), bg_colour(i))
+        for p in placements[i]:
+            x1, y1, x2, y2 = (int(v) for v in p["box"])
+            r = ims[p["object_id"]].resize((max(1, x2 - x1), max(1, y2 - y1)), Image.LANCZOS)
+            c.alpha_composite(r, dest=(x1, y1))
+        return W * H
+
+    with ThreadPoolExecutor(n_threads) as ex:
+        t0 = time.perf_counter()
+        px = sum(ex.map(one, range(len(canvases))))
+        dt = time.perf_counter() - t0
+    return px / 1e6 / dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 alone
+    cores = host_cores()
+    sample = args.cpu_sample or max(8, min(cores, 64))
+    pool, canvases, placements = build_inputs(args.workload, 0, sample)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_port_throughput(pool, canvases[: max(1, min(sample, cores))], placements, cores)
+    times = []
+    px = sum(w * h for w, h in canvases)
+    for _ in range(max(1, args.steps)):
+        _, _, dt = cpu_port_throughput(pool, canvases, placements, cores)
+        times.append(dt)
+        if sum(times) > 150:  # keep the whole run within a few minutes
+            break
+    dt = float(np.mean(times))
+    value = px / 1e6 / dt
+    W, H = canvases[0]
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload, "canvas": [W, H], "objects_per_canvas": len(placements[0]),
+                   "canvases_per_step": sample, "canvases_per_s": sample / dt},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} canvases of {args.workload} per step, one canvas per task on {cores} threads "
+                                   "(oracle/compositor_oracle.c; the reference path is Python over Pillow, not compilable)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from image_transformation_b200 import _native
+    from image_transformation_b200 import batch as B
+    from image_transformation_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the compositor has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    wl = synth.WORKLOADS[args.workload]
+    batch = args.batch or wl["batch"]
+    W0, H0 = synth.workload_canvas_size(args.workload, 0)
+    free_b, _ = torch.cuda.mem_get_info()
+    per_canvas = W0 * H0 * 4 * (1 if args.solid_bg else 2)
+    batch = max(1, min(batch, int(free_b * 0.8) // per_canvas))
+    lo = rank * batch
+    t_setup = time.perf_counter()
+    pool, canvases, placements = build_inputs(args.workload, lo, lo + batch)
+    dpool = B.CutoutPool(pool, dev)
+    bgs = None
+    solids = [bg_colour(lo + i) for i in range(batch)]
+    if not args.solid_bg:
+        bgs = [torch.empty((h, w, 4), dtype=torch.uint8, device=dev) for (w, h) in canvases]
+        for i, t in enumerate(bgs):
+            B.fill_rgba_(t, solids[i])
+    t_plan = time.perf_counter()
+    cb = B.CompositeBatch(dpool, canvases, placements, backgrounds=bgs, solid=solids, host_threads=host_cores())
+    torch.cuda.synchronize()
+    plan_s = time.perf_counter() - t_plan
+    setup_s = time.perf_counter() - t_setup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        cb.run()
+    cb.check()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        cb.run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    barrier()
+    cb.check()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    px_step_rank = sum(w * h for w, h in canvases)
+    value = world * px_step_rank / 1e6 / (ms_step / 1e3)
+    algo = cb.algorithmic_bytes
+    info = dict(cb.info)
+    achieved = algo / 1e9 / (ms_step / 1e3)
+    peak, peak_src = measured_peak()
+    ratio, ratio_src = traffic_ratio()
+
+    # ---- end to end: host buffers through the C ABI (H2D cutouts + backgrounds, D2H canvases) ----
+    e2e = None
+    if not args.no_e2e:
+        cb.close()
+        del cb, bgs
+        torch.cuda.empty_cache()
+        nb = max(1, min(args.e2e_batch, batch))
+        L = _native.lib()
+        import ctypes
+
+        host_bg = None if args.solid_bg else torch.empty((nb, H0 * W0 * 4), dtype=torch.uint8, pin_memory=True)
+        host_out = torch.empty((nb, H0 * W0 * 4), dtype=torch.uint8, pin_memory=True)
+        uniform = all(c == (W0, H0) for c in canvases[:nb])
+        if not uniform:
+            raise SystemExit("e2e leg expects uniform canvases; use --no-e2e for mixed-size workloads")
+        host_pool = {}
+        pool_bytes = 0
+        for k, v in pool.items():
+            tp = torch.empty(v.shape, dtype=torch.uint8, pin_memory=True)
+            tp.numpy()[...] = v
+            host_pool[k] = tp
+            pool_bytes += v.nbytes
+        if host_bg is not None:
+            for i in range(nb):
+                host_bg[i].view(H0, W0, 4).numpy()[...] = solids[i]
+        sizes = {k: (v.shape[1], v.shape[0]) for k, v in pool.items()}
+        from image_transformation_b200.compositor import resolve_placements
+
+        cvs = (_native.Canvas * nb)()
+        recs = []
+        for i in range(nb):
+            res = resolve_placements(placements[i], sizes)
+            r, g, b_, a = solids[i]
+            cvs[i] = _native.Canvas(host_out[i].data_ptr(), W0 * 4, host_bg[i].data_ptr() if host_bg is not None else None,
+                                    W0 * 4 if host_bg is not None else 0, r | (g << 8) | (b_ << 16) | (a << 24),
+                                    W0, H0, len(recs), len(res), 0)
+            recs.extend(res)
+        pls = (_native.Placement * len(recs))()
+        used_pool = set()
+        for j, (oid, x, y, w, h, fl) in enumerate(recs):
+            tp = host_pool[oid]
+            used_pool.add(oid)
+            pls[j] = _native.Placement(tp.data_ptr(), tp.shape[1] * 4, tp.shape[1], tp.shape[0], x, y, w, h, fl, 0)
+
+        def e2e_step():
+            rc = L.b200comp_composite_batch_host(cvs, nb, pls, len(recs), host_cores(), 8, 3)
+            _native.check(rc, "composite_batch_host")
+
+        e2e_step()  # warm-up (also pages the pinned buffers in)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d = sum(pool[k].nbytes for k in used_pool) + (nb * W0 * H0 * 4 if host_bg is not None else 0)
+        e2e = {"value": world * nb * W0 * H0 / 1e6 / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(nb * W0 * H0 * 4), "canvases_per_step": nb, "ms_per_step": dt * 1e3,
+               "canvases_per_s": world * nb / dt,
+               "api": "b200comp_composite_batch_host (pinned host buffers; coefficient tables rebuilt every step)"}
+        # spot-check one e2e canvas against the device-resident result path's oracle
+        if rank == 0:
+            import oracle
+
+            bg0 = np.empty((H0, W0, 4), np.uint8)
+            bg0[...] = solids[0]
+            exp = oracle.composite(bg0, pool, placements[0])
+            if not np.array_equal(host_out[0].view(H0, W0, 4).numpy(), exp):
+                raise SystemExit("bench.py: e2e canvas 0 differs from the oracle -- refusing to report a number")
+
+    # ---- CPU baseline (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        sample = args.cpu_sample or max(8, min(cores, 64))
+        sample = min(sample, batch)
+        v, cps, dt = cpu_port_throughput(pool, canvases[:sample], placements[:sample], cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "canvases_per_s": cps,
+               "sample": f"{sample} canvases of {args.workload} (same placements/pool), one canvas per task on {cores} "
+                         f"threads, {dt:.1f} s of wall time; oracle/compositor_oracle.c"}
+        pv = pillow_throughput(pool, canvases[:sample], placements[:sample], cores)
+        if pv is not None:
+            cpu["pillow_same_sample"] = pv
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "canvas": [W0, H0], "objects_per_canvas": wl["n_objects"],
+                       "canvases_per_gpu_per_step": batch, "canvases_per_s": world * batch / (ms_step / 1e3),
+                       "background": "solid colour synthesised in-kernel" if args.solid_bg else "per-canvas RGBA buffer read from HBM",
+                       "l2": f"inputs+outputs {algo / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
+                       "parallelism": f"canvas-sharded x{world}, no collective",
+                       "fused_placements": info["fused_placements"], "identity_placements": info["identity_placements"],
+                       "preresampled_placements": info["preresampled_placements"], "smem_bytes_per_cta": info["smem_bytes"],
+                       "coeff_table_bytes": info["coeff_bytes"], "plan_create_s": plan_s, "setup_s": setup_s,
+                       "host_cores": host_cores()},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (ratio * algo if ratio else None), "peak_source": peak_src,
+                         "traffic_source": ratio_src, "algorithmic_bytes_per_launch": algo,
+                         "kernel": "composite_tiles_kernel (1 launch per step)"},
+            "gpu_launches": int(world * args.steps * info["launches_per_run"]),
+            "clocks": clocks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1 and "RANK" not in os.environ:
+        # convenience: `python bench.py --gpus N` re-launches itself under torchrun
+        port = 29500 + os.getpid() % 2000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

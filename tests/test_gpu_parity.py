@@ -143,7 +143,9 @@ def test_fill_and_gradient(B):
         key = f"gradient/synth{f['synthetic']}/{w}x{h}"
         src = G.stage(key + "/in")
         left, right, top, bottom = oracle.edge_strip_median_colors(src)
-        horizontal = f["synthetic"] == 0
+        hv = sum((a - b) ** 2 for a, b in zip(left, right))
+        vv = sum((a - b) ** 2 for a, b in zip(top, bottom))
+        horizontal = hv <= vv  # background_resizing.py:69-80: the axis with the LOWER colour distance
         t = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
         B.fill_gradient_(t, horizontal, left if horizontal else top, right if horizontal else bottom)
         assert_same(host(t), G.stage(key + "/out"), key)
