@@ -9,6 +9,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -224,191 +225,11 @@ __global__ void median_from_hist_kernel(const unsigned long long *__restrict__ h
     out[c] = (lo + hi) / 2;
 }
 
-// ---- fused resample + alpha-over tile kernel ---------------------------------------------
-// One CTA per 64x32 output tile.  The canvas tile stays in shared memory while the CTA walks
-// the canvas' placements in z-order; for each placement that touches the tile it stages the
-// needed source patch (premultiplied) in shared memory, runs the horizontal pass into a
-// uint8 intermediate (rounded, as Pillow's two-pass resampler does), then the vertical pass,
-// un-premultiplies and composites onto the resident tile.  The tile is written once.
+}  // namespace b200comp
 
-// Horizontal pass: lane <-> output column (coefficients in registers), loop over patch rows.
-template <int KS>
-__device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int PP, uint32_t *__restrict__ I, int NR,
-                                           int c0, int ox0, int two, const int32_t *__restrict__ kx,
-                                           const int32_t *__restrict__ bx, int ksx) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ncg = (two + 31) >> 5;  // column groups of 32 (1 or 2)
-    const int cg = warp % ncg;
-    const int rstep = kWarps / ncg;
-    const int jj = cg * 32 + lane;  // column inside the tile part
-    if (jj >= two) return;
-    const int j = ox0 + jj;
-    const int base = __ldg(bx + 2 * j) - c0;
-    if (KS > 0) {
-        int32_t kreg[KS > 0 ? KS : 1];
-#pragma unroll
-        for (int t = 0; t < KS; ++t) kreg[t] = __ldg(kx + (int64_t)j * KS + t);
-        for (int r = warp / ncg; r < NR; r += rstep) {
-            const uint32_t *row = P + r * PP + base;
-            int32_t a0, a1, a2, a3;
-            a0 = a1 = a2 = a3 = 1 << (kPrecisionBits - 1);
-#pragma unroll
-            for (int t = 0; t < KS; ++t) mac_px(a0, a1, a2, a3, row[t], kreg[t]);
-            I[r * kInterPitch + jj] = pack_clip(a0, a1, a2, a3);
-        }
-    } else {
-        const int n = __ldg(bx + 2 * j + 1);
-        const int32_t *kk = kx + (int64_t)j * ksx;
-        for (int r = warp / ncg; r < NR; r += rstep) {
-            const uint32_t *row = P + r * PP + base;
-            int32_t a0, a1, a2, a3;
-            a0 = a1 = a2 = a3 = 1 << (kPrecisionBits - 1);
-            for (int t = 0; t < n; ++t) mac_px(a0, a1, a2, a3, row[t], __ldg(kk + t));
-            I[r * kInterPitch + jj] = pack_clip(a0, a1, a2, a3);
-        }
-    }
-}
+#include "tile_kernel.cuh"
 
-// Vertical pass + un-premultiply + over: lane <-> output row, loop over tile columns.
-template <int KS>
-__device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, uint32_t *__restrict__ ctile, int r0,
-                                                int oy0, int tho, int two, int tile_dx, int tile_dy,
-                                                const int32_t *__restrict__ ky, const int32_t *__restrict__ by,
-                                                int ksy) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane >= tho) return;
-    const int y = oy0 + lane;
-    const int base = __ldg(by + 2 * y) - r0;
-    uint32_t *crow = ctile + (tile_dy + lane) * kCtPitch + tile_dx;
-    if (KS > 0) {
-        int32_t kreg[KS > 0 ? KS : 1];
-#pragma unroll
-        for (int t = 0; t < KS; ++t) kreg[t] = __ldg(ky + (int64_t)y * KS + t);
-        for (int x = warp; x < two; x += kWarps) {
-            const uint32_t *col = I + base * kInterPitch + x;
-            int32_t a0, a1, a2, a3;
-            a0 = a1 = a2 = a3 = 1 << (kPrecisionBits - 1);
-#pragma unroll
-            for (int t = 0; t < KS; ++t) mac_px(a0, a1, a2, a3, col[t * kInterPitch], kreg[t]);
-            const uint32_t s = unpremultiply_px(pack_clip(a0, a1, a2, a3));
-            crow[x] = over_px(crow[x], s);
-        }
-    } else {
-        const int n = __ldg(by + 2 * y + 1);
-        const int32_t *kk = ky + (int64_t)y * ksy;
-        for (int x = warp; x < two; x += kWarps) {
-            const uint32_t *col = I + base * kInterPitch + x;
-            int32_t a0, a1, a2, a3;
-            a0 = a1 = a2 = a3 = 1 << (kPrecisionBits - 1);
-            for (int t = 0; t < n; ++t) mac_px(a0, a1, a2, a3, col[t * kInterPitch], __ldg(kk + t));
-            const uint32_t s = unpremultiply_px(pack_clip(a0, a1, a2, a3));
-            crow[x] = over_px(crow[x], s);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kThreads) composite_tiles_kernel(const DevCanvas *__restrict__ canvases,
-                                                                    int n_canvases,
-                                                                    const DevPlacement *__restrict__ placements,
-                                                                    int patch_words, int inter_words,
-                                                                    int *__restrict__ status) {
-    extern __shared__ uint32_t smem[];
-    uint32_t *ctile = smem;                    // kTileH * kCtPitch
-    uint32_t *P = ctile + kTileH * kCtPitch;   // patch_words (premultiplied source patch)
-    uint32_t *I = P + patch_words;             // inter_words (H-pass result, uint8x4)
-
-    // ---- which canvas / tile ----
-    const int64_t tile = blockIdx.x;
-    int lo = 0, hi = n_canvases - 1;
-    while (lo < hi) {  // last canvas with tile_base <= tile
-        const int mid = (lo + hi + 1) >> 1;
-        if (__ldg(&canvases[mid].tile_base) <= tile) lo = mid; else hi = mid - 1;
-    }
-    const DevCanvas cv = canvases[lo];
-    const int local = (int)(tile - cv.tile_base);
-    const int ty = local / cv.tiles_x, tx = local - ty * cv.tiles_x;
-    const int tx0 = tx * kTileW, ty0 = ty * kTileH;
-    const int tx1 = min(cv.W, tx0 + kTileW), ty1 = min(cv.H, ty0 + kTileH);
-    const int tw = tx1 - tx0, th = ty1 - ty0;
-
-    // ---- load the canvas tile (background or solid colour) ----
-    for (int i = threadIdx.x; i < kTileW * kTileH; i += kThreads) {
-        const int yy = i / kTileW, xx = i - yy * kTileW;
-        if (yy < th && xx < tw) {
-            ctile[yy * kCtPitch + xx] =
-                cv.bg ? ld_px(cv.bg, (int64_t)(ty0 + yy) * cv.bg_pitch + (int64_t)(tx0 + xx) * 4) : cv.solid;
-        }
-    }
-    __syncthreads();
-
-    // ---- z-order walk ----
-    for (int pi = 0; pi < cv.count; ++pi) {
-        const DevPlacement *pp = placements + cv.first + pi;
-        const int px = __ldg(&pp->x), py = __ldg(&pp->y), pw = __ldg(&pp->w), ph = __ldg(&pp->h);
-        const int ix0 = max(tx0, px), iy0 = max(ty0, py);
-        const int ix1 = min(tx1, px + pw), iy1 = min(ty1, py + ph);
-        if (ix0 >= ix1 || iy0 >= iy1) continue;  // uniform across the CTA
-        const int two = ix1 - ix0, tho = iy1 - iy0;
-        const uint8_t *src = pp->src;
-        const int spitch = __ldg(&pp->src_pitch);
-        if (__ldg(&pp->mode) == 0) {
-            // identity-size placement: plain over straight from the cutout
-            for (int i = threadIdx.x; i < two * tho; i += kThreads) {
-                const int yy = i / two, xx = i - yy * two;
-                const uint32_t s = ld_px(src, (int64_t)(iy0 + yy - py) * spitch + (int64_t)(ix0 + xx - px) * 4);
-                uint32_t *d = ctile + (iy0 + yy - ty0) * kCtPitch + (ix0 + xx - tx0);
-                *d = over_px(*d, s);
-            }
-            __syncthreads();
-            continue;
-        }
-        const int32_t *kx = pp->kx, *bx = pp->bx, *ky = pp->ky, *by = pp->by;
-        const int ksx = __ldg(&pp->ksx), ksy = __ldg(&pp->ksy);
-        const int ox0 = ix0 - px, ox1 = ix1 - px, oy0 = iy0 - py, oy1 = iy1 - py;
-        const int c0 = __ldg(bx + 2 * ox0);
-        const int c1 = __ldg(bx + 2 * (ox1 - 1)) + __ldg(bx + 2 * (ox1 - 1) + 1);
-        const int r0 = __ldg(by + 2 * oy0);
-        const int r1 = __ldg(by + 2 * (oy1 - 1)) + __ldg(by + 2 * (oy1 - 1) + 1);
-        const int NC = c1 - c0, NR = r1 - r0;
-        const int PP = NC | 1;
-        if (NR * PP + ksx > patch_words || (NR + ksy) * kInterPitch > inter_words) {
-            if (threadIdx.x == 0) atomicOr(status, NR * PP + ksx > patch_words ? kStatusPatchOverflow : kStatusInterOverflow);
-            continue;  // host sizing bug: flagged, never silently wrong
-        }
-        // stage the premultiplied source patch
-        for (int i = threadIdx.x; i < NR * NC; i += kThreads) {
-            const int rr = i / NC, cc = i - rr * NC;
-            P[rr * PP + cc] = premultiply_px(ld_px(src, (int64_t)(r0 + rr) * spitch + (int64_t)(c0 + cc) * 4));
-        }
-        __syncthreads();
-        switch (ksx) {
-            case 1: tile_hpass<1>(P, PP, I, NR, c0, ox0, two, kx, bx, ksx); break;
-            case 7: tile_hpass<7>(P, PP, I, NR, c0, ox0, two, kx, bx, ksx); break;
-            case 9: tile_hpass<9>(P, PP, I, NR, c0, ox0, two, kx, bx, ksx); break;
-            case 11: tile_hpass<11>(P, PP, I, NR, c0, ox0, two, kx, bx, ksx); break;
-            case 13: tile_hpass<13>(P, PP, I, NR, c0, ox0, two, kx, bx, ksx); break;
-            default: tile_hpass<0>(P, PP, I, NR, c0, ox0, two, kx, bx, ksx); break;
-        }
-        __syncthreads();
-        switch (ksy) {
-            case 1: tile_vpass_over<1>(I, ctile, r0, oy0, tho, two, ix0 - tx0, iy0 - ty0, ky, by, ksy); break;
-            case 7: tile_vpass_over<7>(I, ctile, r0, oy0, tho, two, ix0 - tx0, iy0 - ty0, ky, by, ksy); break;
-            case 9: tile_vpass_over<9>(I, ctile, r0, oy0, tho, two, ix0 - tx0, iy0 - ty0, ky, by, ksy); break;
-            case 11: tile_vpass_over<11>(I, ctile, r0, oy0, tho, two, ix0 - tx0, iy0 - ty0, ky, by, ksy); break;
-            case 13: tile_vpass_over<13>(I, ctile, r0, oy0, tho, two, ix0 - tx0, iy0 - ty0, ky, by, ksy); break;
-            default: tile_vpass_over<0>(I, ctile, r0, oy0, tho, two, ix0 - tx0, iy0 - ty0, ky, by, ksy); break;
-        }
-        __syncthreads();
-    }
-
-    // ---- write the tile once ----
-    for (int i = threadIdx.x; i < kTileW * kTileH; i += kThreads) {
-        const int yy = i / kTileW, xx = i - yy * kTileW;
-        if (yy < th && xx < tw)
-            *reinterpret_cast<uint32_t *>(cv.out + (int64_t)(ty0 + yy) * cv.out_pitch + (int64_t)(tx0 + xx) * 4) =
-                ctile[yy * kCtPitch + xx];
-    }
-}
+namespace b200comp {
 
 // =====================================================================================
 // Host side
@@ -441,15 +262,6 @@ static void identity_table(int n, int32_t *k, int32_t *b) {
         b[2 * i] = i;
         b[2 * i + 1] = 1;
     }
-}
-
-// Upper bound of the source extent needed by `n_out` consecutive output samples.
-static int extent_bound(int in_size, int out_size, int n_out) {
-    if (in_size == out_size) return n_out;
-    const double scale = (double)in_size / out_size;
-    const double support = 3.0 * std::max(1.0, scale);
-    const double e = (std::min(n_out, out_size) - 1) * scale + 2.0 * support + 1.0;
-    return std::min(in_size, (int)std::floor(e) + 2);
 }
 
 static int launch_axis(const uint8_t *in, int64_t in_pitch, int in_w, int in_h, uint8_t *out, int64_t out_pitch,
@@ -492,34 +304,78 @@ static int resample_two_pass(const uint8_t *src, int sw, int sh, int64_t sp, uin
     return launch_axis(src, sp, sw, sh, dst, dp, w, h, ky, by, ksy, 1, 1, 1, st);
 }
 
-// ---- coefficient table cache for one plan / call ----------------------------------------
+// ---- coefficient tables of one plan / call ------------------------------------------------
+// Two device formats share one int32 buffer:
+//   legacy : k[out][ks] int32 + bounds[out][2]              (generic one-axis kernels)
+//   packed : w0[out] + planes[3*nw][out] (byte planes, SoA)  (fused tile kernel, dp4a)
 struct TableRef {
-    int64_t k_off = 0;  // offsets in int32 units into the table buffer
-    int64_t b_off = 0;
-    int ks = 0;
+    int64_t k_off = 0;  // legacy: k      | packed: w0
+    int64_t b_off = 0;  // legacy: bounds | packed: planes
+    int ks = 0;         // legacy: taps   | packed: words per output sample (nw)
 };
 
+// words per output sample needed by a table with `ks` taps, bucketed to the kernel's variants
+static int packed_words(int ks) {
+    const int nw = (3 + ks + 3) >> 2;
+    if (nw <= 3) return 3;
+    if (nw <= 4) return 4;
+    if (nw <= 5) return 5;
+    return 0;  // more than 17 taps (downscale beyond 2.66x): generic kernels
+}
+
 struct TableSet {
-    // key: (in, out); out == -in marks the identity table of a skipped pass
-    std::map<std::pair<int, int>, TableRef> refs;
-    std::vector<std::pair<int, int>> order;
+    struct Key {
+        int in_size, out_size, kind;  // kind 0 legacy, 1 packed, 2 packed identity (skipped pass)
+        bool operator<(const Key &o) const {
+            return std::tie(in_size, out_size, kind) < std::tie(o.in_size, o.out_size, o.kind);
+        }
+    };
+    std::map<Key, TableRef> refs;
+    std::vector<Key> order;
     std::vector<int32_t> host;
     int64_t total = 0;
 
-    TableRef &want(int in_size, int out_size, bool identity) {
-        std::pair<int, int> key(in_size, identity ? -in_size : out_size);
+    TableRef &want(const Key &key) {
         auto it = refs.find(key);
         if (it != refs.end()) return it->second;
         TableRef r;
-        r.ks = identity ? 1 : lanczos_ksize(in_size, out_size);
-        const int n = identity ? in_size : out_size;
-        r.k_off = total;
-        total += (int64_t)n * r.ks;
-        r.b_off = total;
-        total += (int64_t)n * 2;
+        const int n = key.out_size;
+        if (key.kind == 0) {
+            r.ks = lanczos_ksize(key.in_size, key.out_size);
+            r.k_off = total;
+            total += (int64_t)n * r.ks;
+            r.b_off = total;
+            total += (int64_t)n * 2;
+        } else {
+            r.ks = key.kind == 2 ? 3 : packed_words(lanczos_ksize(key.in_size, key.out_size));
+            r.k_off = total;
+            total += n;
+            r.b_off = total;
+            total += (int64_t)3 * r.ks * n;
+        }
         total = (total + 3) & ~(int64_t)3;  // keep every table 16-byte aligned
         order.push_back(key);
         return refs.emplace(key, r).first->second;
+    }
+    TableRef &want_legacy(int in_size, int out_size) { return want(Key{in_size, out_size, 0}); }
+    TableRef &want_packed(int in_size, int out_size, bool identity) {
+        return want(Key{in_size, out_size, identity ? 2 : 1});
+    }
+
+    // split Pillow's 22-bit taps into byte planes placed at their position inside 4-sample words
+    static void pack(int n_out, int ks, const int32_t *k, const int32_t *bounds, int nw, int32_t *w0, int32_t *planes) {
+        uint32_t *pl = reinterpret_cast<uint32_t *>(planes);
+        for (int j = 0; j < n_out; ++j) {
+            const int lo = bounds[2 * j], n = bounds[2 * j + 1];
+            w0[j] = lo >> 2;
+            for (int t = 0; t < n; ++t) {
+                const int pos = (lo & 3) + t, word = pos >> 2, sh = 8 * (pos & 3);
+                const int32_t kv = k[(size_t)j * ks + t];
+                pl[(size_t)(0 * nw + word) * n_out + j] |= (uint32_t)(kv & 0xff) << sh;
+                pl[(size_t)(1 * nw + word) * n_out + j] |= (uint32_t)((kv >> 8) & 0xff) << sh;
+                pl[(size_t)(2 * nw + word) * n_out + j] |= (uint32_t)((kv >> 16) & 0xff) << sh;  // signed top byte
+            }
+        }
     }
 
     void build(int n_threads) {
@@ -527,13 +383,29 @@ struct TableSet {
         if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
         n_threads = std::max(1, std::min<int>(n_threads, (int)order.size()));
         auto work = [&](int tid) {
+            std::vector<int32_t> k, b;
             for (size_t i = tid; i < order.size(); i += n_threads) {
-                const auto &key = order[i];
+                const Key &key = order[i];
                 const TableRef &r = refs[key];
-                if (key.second < 0)
-                    identity_table(key.first, host.data() + r.k_off, host.data() + r.b_off);
-                else
-                    build_lanczos_table(key.first, key.second, host.data() + r.k_off, host.data() + r.b_off);
+                int32_t *h = host.data();
+                if (key.kind == 0) {
+                    build_lanczos_table(key.in_size, key.out_size, h + r.k_off, h + r.b_off);
+                    continue;
+                }
+                const int n = key.out_size;
+                int ks;
+                if (key.kind == 2) {
+                    ks = 1;
+                    k.assign((size_t)n, 0);
+                    b.assign((size_t)2 * n, 0);
+                    identity_table(n, k.data(), b.data());
+                } else {
+                    ks = lanczos_ksize(key.in_size, key.out_size);
+                    k.assign((size_t)n * ks, 0);
+                    b.assign((size_t)2 * n, 0);
+                    build_lanczos_table(key.in_size, key.out_size, k.data(), b.data());
+                }
+                pack(n, ks, k.data(), b.data(), r.ks, h + r.k_off, h + r.b_off);
             }
         };
         if (n_threads == 1) {
@@ -545,6 +417,13 @@ struct TableSet {
         }
     }
 };
+
+// Upper bound of the 4-sample words one tile needs along an axis (see tile_kernel.cuh: cw1 - cw0).
+static int words_bound(int in_size, int out_size, int n_out, int nw) {
+    const double scale = (double)in_size / out_size;
+    const double span = (std::min(n_out, out_size) - 1) * scale + 1.0;
+    return (int)std::floor(span / 4.0) + 2 + nw;
+}
 
 }  // namespace b200comp
 
@@ -558,8 +437,9 @@ struct b200comp_plan {
     cudaStream_t create_stream = nullptr;
     int n_canvases = 0;
     int64_t n_tiles = 0;
+    int max_tiles = 1;
     int32_t *d_tables = nullptr;
-    DevPlacement *d_placements = nullptr;
+    DevPlacementT *d_placements = nullptr;
     DevCanvas *d_canvases = nullptr;
     int *d_status = nullptr;
     int patch_words = 0, inter_words = 0;
@@ -578,8 +458,9 @@ struct b200comp_plan {
     std::vector<void *> owned;  // device allocations freed with the plan
 };
 
-static const size_t kMaxSmemBytes = 200 * 1024;  // per-CTA budget for the tile kernel
-static const int kFusedMaxKs = 61;               // up to 10x downscale inside the tile kernel
+static const size_t kMaxSmemBytes = 200 * 1024;    // opt-in dynamic shared memory limit we request
+static const size_t kFusedSmemCap = 112 * 1024;    // placements needing more go through the generic kernels
+static_assert(sizeof(b200comp_placement) == 48 && sizeof(b200comp_canvas) == 56, "public struct layout");
 
 #pragma GCC visibility push(default)
 extern "C" {
@@ -634,8 +515,8 @@ int b200comp_resize_rgba_lanczos(const uint8_t *src, int sw, int sh, size_t src_
                                  nullptr, nullptr, 0, nullptr, flags, st);
     TableSet ts;
     TableRef tx, ty;
-    if (w != sw) tx = ts.want(sw, w, false);
-    if (h != sh) ty = ts.want(sh, h, false);
+    if (w != sw) tx = ts.want_legacy(sw, w);
+    if (h != sh) ty = ts.want_legacy(sh, h);
     ts.build(1);
     const size_t tbytes = ts.host.size() * sizeof(int32_t);
     const size_t sbytes = (size_t)std::max((int64_t)sh * w, (int64_t)h * sw) * 4;
@@ -766,7 +647,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
 
     // ---- validate, classify placements, collect tables ----
     TableSet ts;
-    std::vector<DevPlacement> hp((size_t)std::max(1, n_placements));
+    std::vector<DevPlacementT> hp((size_t)std::max(1, n_placements));
     std::vector<std::pair<TableRef, TableRef>> tref((size_t)std::max(1, n_placements));
     std::vector<int> pre_index((size_t)std::max(1, n_placements), -1);
     int max_patch = 16, max_inter = 16;
@@ -777,31 +658,36 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             return fail(B200COMP_EINVAL, "plan_create: placement " + std::to_string(i) + " has a null source or empty size");
         if (!aligned4(p.src, p.src_pitch) || p.src_pitch < (int64_t)p.sw * 4 || p.src_pitch > INT32_MAX)
             return fail(B200COMP_EINVAL, "plan_create: placement " + std::to_string(i) + " source misaligned or bad pitch");
-        DevPlacement &d = hp[i];
+        DevPlacementT &d = hp[i];
         std::memset(&d, 0, sizeof d);
         d.src = p.src;
         d.src_pitch = (int32_t)p.src_pitch;
         d.sw = p.sw; d.sh = p.sh;
         d.x = p.x; d.y = p.y; d.w = p.w; d.h = p.h;
+        d.vec_ok = ((reinterpret_cast<uintptr_t>(p.src) & 15u) == 0 && (p.src_pitch & 15) == 0) ? 1 : 0;
         if (p.w == p.sw && p.h == p.sh) {
             d.mode = 0;
             ++n_ident;
             continue;
         }
         const bool need_h = p.w != p.sw, need_v = p.h != p.sh;
-        const int ksx = need_h ? lanczos_ksize(p.sw, p.w) : 1;
-        const int ksy = need_v ? lanczos_ksize(p.sh, p.h) : 1;
-        const int nc = extent_bound(p.sw, p.w, kTileW), nr = extent_bound(p.sh, p.h, kTileH);
-        const int64_t patch = (int64_t)nr * (nc | 1) + ksx;
-        const int64_t inter = (int64_t)(nr + ksy) * kInterPitch;
-        const size_t need = ((size_t)kTileH * kCtPitch + patch + inter) * 4;
+        const int nwx = need_h ? packed_words(lanczos_ksize(p.sw, p.w)) : 3;
+        const int nwy = need_v ? packed_words(lanczos_ksize(p.sh, p.h)) : 3;
         const bool vertical_first = (p.flags & B200COMP_VERTICAL_FIRST) && need_h && need_v;
-        if (!vertical_first && ksx <= kFusedMaxKs && ksy <= kFusedMaxKs && need <= kMaxSmemBytes) {
+        bool fused = !vertical_first && nwx > 0 && nwy > 0;
+        int64_t patch = 0, inter = 0;
+        if (fused) {
+            const int ncw = words_bound(p.sw, p.w, kTileW, nwx), nrq = words_bound(p.sh, p.h, kTileH, nwy);
+            patch = (int64_t)4 * (4 * nrq) * ncw;          // 4 channel planes x rows x words
+            inter = (int64_t)4 * kTileW * (nrq | 1);       // 4 channel planes x columns x row-quads
+            fused = ((size_t)kTileH * kCtPitch + patch + inter) * 4 <= kFusedSmemCap;
+        }
+        if (fused) {
             d.mode = 1;
-            tref[i].first = ts.want(p.sw, p.w, !need_h);
-            tref[i].second = ts.want(p.sh, p.h, !need_v);
-            d.ksx = tref[i].first.ks;
-            d.ksy = tref[i].second.ks;
+            tref[i].first = ts.want_packed(p.sw, p.w, !need_h);
+            tref[i].second = ts.want_packed(p.sh, p.h, !need_v);
+            d.nwx = tref[i].first.ks;
+            d.nwy = tref[i].second.ks;
             max_patch = std::max<int>(max_patch, (int)patch);
             max_inter = std::max<int>(max_inter, (int)inter);
             ++n_fused;
@@ -810,14 +696,15 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             b200comp_plan::Pre pr;
             pr.src = p.src; pr.sp = p.src_pitch; pr.sw = p.sw; pr.sh = p.sh; pr.w = p.w; pr.h = p.h;
             pr.flags = vertical_first ? B200COMP_VERTICAL_FIRST : 0;
-            if (need_h) pr.tx = ts.want(p.sw, p.w, false);
-            if (need_v) pr.ty = ts.want(p.sh, p.h, false);
+            if (need_h) pr.tx = ts.want_legacy(p.sw, p.w);
+            if (need_v) pr.ty = ts.want_legacy(p.sh, p.h);
             pr.dst = nullptr; pr.scratch = nullptr;
             pre_index[i] = (int)plan->pre.size();
             plan->pre.push_back(pr);
             d.mode = 0;
             d.sw = p.w; d.sh = p.h;
             d.src_pitch = p.w * 4;
+            d.vec_ok = 0;
         }
     }
 
@@ -840,13 +727,14 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         d.tiles_y = (cv.H + kTileH - 1) / kTileH;
         d.tile_base = tiles;
         tiles += (int64_t)d.tiles_x * d.tiles_y;
+        if ((int64_t)d.tiles_x * d.tiles_y > INT32_MAX) return fail(B200COMP_EINVAL, "plan_create: canvas too large");
+        plan->max_tiles = std::max(plan->max_tiles, d.tiles_x * d.tiles_y);
         algo += (int64_t)cv.W * cv.H * 4 * (cv.bg ? 2 : 1);
         for (int i = 0; i < cv.n_placements; ++i) {
             const b200comp_placement &p = placements[cv.first_placement + i];
             algo += (int64_t)p.sw * p.sh * 4;
         }
     }
-    if (tiles > INT32_MAX) return fail(B200COMP_EINVAL, "plan_create: too many tiles for one launch; split the batch");
     plan->n_tiles = tiles;
 
     // ---- build tables on the host threads, upload everything ----
@@ -858,7 +746,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         return e;
     };
     CUDA_TRY(dev_alloc((void **)&plan->d_tables, tbytes));
-    CUDA_TRY(dev_alloc((void **)&plan->d_placements, hp.size() * sizeof(DevPlacement)));
+    CUDA_TRY(dev_alloc((void **)&plan->d_placements, hp.size() * sizeof(DevPlacementT)));
     CUDA_TRY(dev_alloc((void **)&plan->d_canvases, hc.size() * sizeof(DevCanvas)));
     CUDA_TRY(dev_alloc((void **)&plan->d_status, sizeof(int)));
     for (auto &pr : plan->pre) {
@@ -867,18 +755,18 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             CUDA_TRY(dev_alloc((void **)&pr.scratch, (size_t)std::max((int64_t)pr.sh * pr.w, (int64_t)pr.h * pr.sw) * 4));
     }
     for (int i = 0; i < n_placements; ++i) {
-        DevPlacement &d = hp[i];
+        DevPlacementT &d = hp[i];
         if (d.mode == 1) {
-            d.kx = plan->d_tables + tref[i].first.k_off;
-            d.bx = plan->d_tables + tref[i].first.b_off;
-            d.ky = plan->d_tables + tref[i].second.k_off;
-            d.by = plan->d_tables + tref[i].second.b_off;
+            d.w0x = plan->d_tables + tref[i].first.k_off;
+            d.plx = reinterpret_cast<const uint32_t *>(plan->d_tables + tref[i].first.b_off);
+            d.w0y = plan->d_tables + tref[i].second.k_off;
+            d.ply = reinterpret_cast<const uint32_t *>(plan->d_tables + tref[i].second.b_off);
         } else if (pre_index[i] >= 0) {
             d.src = plan->pre[(size_t)pre_index[i]].dst;
         }
     }
     CUDA_TRY(cudaMemcpyAsync(plan->d_tables, ts.host.data(), tbytes, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(plan->d_placements, hp.data(), hp.size() * sizeof(DevPlacement), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(plan->d_placements, hp.data(), hp.size() * sizeof(DevPlacementT), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(plan->d_canvases, hc.data(), hc.size() * sizeof(DevCanvas), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(plan->d_status, 0, sizeof(int), st));
     CUDA_TRY(cudaStreamSynchronize(st));  // host staging vectors die with this scope
@@ -913,8 +801,12 @@ int b200comp_plan_run(b200comp_plan *plan, void *stream) {
                                    pr.flags, st);
         if (rc) return rc;
     }
-    composite_tiles_kernel<<<(unsigned)plan->n_tiles, kThreads, plan->smem_bytes, st>>>(
-        plan->d_canvases, plan->n_canvases, plan->d_placements, plan->patch_words, plan->inter_words, plan->d_status);
+    // grid.y is limited to 65535 canvases per launch
+    for (int c0 = 0; c0 < plan->n_canvases; c0 += 65535) {
+        const int nc = std::min(65535, plan->n_canvases - c0);
+        composite_tiles_kernel<<<dim3((unsigned)plan->max_tiles, (unsigned)nc), kThreads, plan->smem_bytes, st>>>(
+            plan->d_canvases + c0, plan->d_placements, plan->patch_words, plan->inter_words, plan->d_status);
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -8,21 +8,6 @@
 namespace b200comp {
 
 // ------------------------------------------------------------------ descriptors
-struct DevPlacement {
-    const uint8_t *src;  // cutout (identity) or pre-resampled temp
-    const int32_t *kx;   // [w][ksx] 22-bit fixed point, zero padded
-    const int32_t *bx;   // [w][2]   (xmin, xmax)
-    const int32_t *ky;   // [h][ksy]
-    const int32_t *by;   // [h][2]
-    int32_t src_pitch;   // bytes
-    int32_t sw, sh;
-    int32_t x, y, w, h;  // destination box (top-left, resampled size)
-    int32_t ksx, ksy;    // taps per output sample (1 = pass skipped: identity table)
-    int32_t mode;        // 0 = plain over of src (w x h), 1 = resample in the tile kernel
-    int32_t pad_[3];
-};
-static_assert(sizeof(DevPlacement) == 96, "DevPlacement layout");
-
 struct DevCanvas {
     uint8_t *out;
     const uint8_t *bg;  // may be null -> solid
@@ -42,7 +27,6 @@ constexpr int kTileH = 32;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kCtPitch = kTileW + 1;  // odd pitch: row-per-lane accesses hit distinct banks
-constexpr int kInterPitch = kTileW + 1;
 constexpr int kPrecisionBits = 22;
 
 enum : int { kStatusPatchOverflow = 1, kStatusInterOverflow = 2 };

@@ -1,0 +1,344 @@
+// Fused resample + alpha-over tile kernel (sm_100a), the hot kernel of the path.
+//
+// One CTA owns one 64x32 tile of one output canvas.  The tile lives in shared memory while the
+// CTA walks the canvas' placements in z-order (compositor.py:12-21).  For every placement that
+// touches the tile:
+//   1. stage   the needed source patch: 128-bit loads of RGBA pixels, premultiply (Convert.c
+//              rgbA2rgba), byte-transpose into four channel planes (4 consecutive pixels of one
+//              channel per 32-bit word)
+//   2. H pass  lane <-> output column; Pillow's 22-bit fixed-point taps are held as three byte
+//              planes (k = b0 + 256*b1 + 65536*b2, b2 signed) so four taps cost three dp4a and no
+//              byte unpacking; result rounded + clipped to uint8 (ImagingResampleHorizontal_8bpc)
+//              and written transposed (4 consecutive ROWS of one channel per word)
+//   3. V pass  lane <-> output row, same dp4a scheme (ImagingResampleVertical_8bpc), then
+//              un-premultiply (rgba2rgbA) and alpha-over (AlphaComposite.c) onto the resident tile
+// The tile is written to HBM once.  Arithmetic is integer-exact: dp4a partial sums wrap modulo
+// 2^32 and the true accumulator fits in int32, exactly as Pillow's int accumulator.
+#pragma once
+#include "kernels.cuh"
+
+namespace b200comp {
+
+__device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
+__device__ __forceinline__ int32_t dp4a_us(uint32_t a, uint32_t b, int32_t c) {
+    int32_t d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// 4 RGBA pixels -> 4 channel words (byte k of each word = pixel k)
+__device__ __forceinline__ void transpose4(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t &r, uint32_t &g,
+                                           uint32_t &b, uint32_t &a) {
+    const uint32_t t01 = __byte_perm(p0, p1, 0x5140);  // p0.b0 p1.b0 p0.b1 p1.b1
+    const uint32_t t23 = __byte_perm(p2, p3, 0x5140);
+    const uint32_t u01 = __byte_perm(p0, p1, 0x7362);  // p0.b2 p1.b2 p0.b3 p1.b3
+    const uint32_t u23 = __byte_perm(p2, p3, 0x7362);
+    r = __byte_perm(t01, t23, 0x5410);
+    g = __byte_perm(t01, t23, 0x7632);
+    b = __byte_perm(u01, u23, 0x5410);
+    a = __byte_perm(u01, u23, 0x7632);
+}
+
+__device__ __forceinline__ uint32_t clip8i(int32_t v) { return (uint32_t)min(255, max(0, v >> kPrecisionBits)); }
+
+// ---- stage: global RGBA -> premultiplied planar patch -----------------------------------------
+// P[c][r][wx]: plane c at P + c*plane_stride, row pitch NCW words; source pixel 4*(cw0+wx)+k of
+// source row 4*rw0+r sits in byte k.  Rows / columns outside the cutout are left untouched: every
+// tap that could read them has a zero coefficient.  Loads are issued four at a time per thread
+// (memory-level parallelism) before any of them is consumed.
+__device__ __forceinline__ void stage_store(uint32_t *__restrict__ d, int plane_stride, uint32_t p0, uint32_t p1,
+                                            uint32_t p2, uint32_t p3) {
+    uint32_t R, G, B, A;
+    transpose4(p0, p1, p2, p3, R, G, B, A);
+    if (((A ^ (A >> 1)) & 0x7f7f7f7fu) == 0u) {
+        // every alpha is 0 or 255: MULDIV255(c, a) is c or 0 -> mask the colours with the alpha bytes
+        R &= A; G &= A; B &= A;
+    } else {
+        transpose4(premultiply_px(p0), premultiply_px(p1), premultiply_px(p2), premultiply_px(p3), R, G, B, A);
+    }
+    d[0] = R;
+    d[plane_stride] = G;
+    d[2 * plane_stride] = B;
+    d[3 * plane_stride] = A;
+}
+
+__device__ __forceinline__ void stage_patch(uint32_t *__restrict__ P, int plane_stride, int NR, int NCW,
+                                            const uint8_t *__restrict__ src, int spitch, int sw, int sh, int rw0,
+                                            int cw0, bool vec_ok) {
+    const uint32_t rcp = 0xFFFFFFFFu / (uint32_t)NCW + 1u;  // exact i / NCW for i*NCW < 2^32
+    const int total = NR * NCW;
+    constexpr int U = 4;
+    for (int base = threadIdx.x; base < total; base += U * kThreads) {
+        uint4 v[U];
+        int off[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * kThreads;
+            const int r = (int)__umulhi((uint32_t)i, rcp);
+            const int wx = i - r * NCW;
+            const int gy = 4 * rw0 + r, gx = 4 * (cw0 + wx);
+            off[u] = -1;
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < total && gy < sh && gx < sw) {
+                off[u] = r * NCW + wx;
+                const uint8_t *rowp = src + (int64_t)gy * spitch + (int64_t)gx * 4;
+                if (vec_ok && gx + 3 < sw) {
+                    v[u] = __ldg(reinterpret_cast<const uint4 *>(rowp));
+                } else {
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(rowp);
+                    v[u].x = __ldg(q);
+                    if (gx + 1 < sw) v[u].y = __ldg(q + 1);
+                    if (gx + 2 < sw) v[u].z = __ldg(q + 2);
+                    if (gx + 3 < sw) v[u].w = __ldg(q + 3);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (off[u] >= 0) stage_store(P + off[u], plane_stride, v[u].x, v[u].y, v[u].z, v[u].w);
+    }
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// pull the coefficient rows this lane will need into L1 while the patch is being staged
+__device__ __forceinline__ void prefetch_coeffs(const int32_t *__restrict__ w0, const uint32_t *__restrict__ pl, int nw,
+                                                int n_out, int idx) {
+    prefetch_l1(w0 + idx);
+    for (int q = 0; q < 3 * nw; ++q) prefetch_l1(pl + (int64_t)q * n_out + idx);
+}
+
+// ---- H pass ---------------------------------------------------------------------------------
+// I[c][jj][rq]: plane c at I + c*iplane_stride, column pitch IPW words (odd), byte k of word rq =
+// intermediate row 4*rq+k (relative to source row 4*rw0).
+template <int NW>
+__device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int plane_stride, int NCW,
+                                           uint32_t *__restrict__ I, int iplane_stride, int IPW, int NRQ, int cw0,
+                                           int ox0, int two, const int32_t *__restrict__ w0x,
+                                           const uint32_t *__restrict__ plx, int n_out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ncg = (two + 31) >> 5;  // 1 or 2 column groups of 32
+    const int cg = warp % ncg;
+    const int rstep = kWarps / ncg;
+    const int jj = cg * 32 + lane;
+    if (jj >= two) return;
+    const int j = ox0 + jj;
+    const int wbase = __ldg(w0x + j) - cw0;
+    uint32_t k0[NW], k1[NW], k2[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        k0[i] = __ldg(plx + (int64_t)(0 * NW + i) * n_out + j);
+        k1[i] = __ldg(plx + (int64_t)(1 * NW + i) * n_out + j);
+        k2[i] = __ldg(plx + (int64_t)(2 * NW + i) * n_out + j);
+    }
+    for (int rq = warp / ncg; rq < NRQ; rq += rstep) {
+        uint32_t o[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const uint32_t *row = P + (rq * 4 + rr) * NCW + wbase;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t a0 = 0u, a1 = 0u;
+                int32_t a2 = 0;
+#pragma unroll
+                for (int i = 0; i < NW; ++i) {
+                    const uint32_t wd = row[c * plane_stride + i];
+                    a0 = dp4a_uu(wd, k0[i], a0);
+                    a1 = dp4a_uu(wd, k1[i], a1);
+                    a2 = dp4a_us(wd, k2[i], a2);
+                }
+                const int32_t v = (int32_t)(a0 + (a1 << 8) + ((uint32_t)a2 << 16) + (1u << (kPrecisionBits - 1)));
+                o[c] |= clip8i(v) << (8 * rr);
+            }
+        }
+        uint32_t *d = I + jj * IPW + rq;
+        d[0] = o[0];
+        d[iplane_stride] = o[1];
+        d[2 * iplane_stride] = o[2];
+        d[3 * iplane_stride] = o[3];
+    }
+}
+
+// ---- V pass + un-premultiply + over -------------------------------------------------------------
+template <int NW>
+__device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, int iplane_stride, int IPW,
+                                                uint32_t *__restrict__ ctile, int rw0, int oy0, int tho, int two,
+                                                int tile_dx, int tile_dy, const int32_t *__restrict__ w0y,
+                                                const uint32_t *__restrict__ ply, int n_out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane >= tho) return;
+    const int y = oy0 + lane;
+    const int wbase = __ldg(w0y + y) - rw0;
+    uint32_t k0[NW], k1[NW], k2[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        k0[i] = __ldg(ply + (int64_t)(0 * NW + i) * n_out + y);
+        k1[i] = __ldg(ply + (int64_t)(1 * NW + i) * n_out + y);
+        k2[i] = __ldg(ply + (int64_t)(2 * NW + i) * n_out + y);
+    }
+    uint32_t *crow = ctile + (tile_dy + lane) * kCtPitch + tile_dx;
+    for (int x = warp; x < two; x += kWarps) {
+        const uint32_t *col = I + x * IPW + wbase;
+        uint32_t ch[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t a0 = 0u, a1 = 0u;
+            int32_t a2 = 0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                const uint32_t wd = col[c * iplane_stride + i];
+                a0 = dp4a_uu(wd, k0[i], a0);
+                a1 = dp4a_uu(wd, k1[i], a1);
+                a2 = dp4a_us(wd, k2[i], a2);
+            }
+            ch[c] = clip8i((int32_t)(a0 + (a1 << 8) + ((uint32_t)a2 << 16) + (1u << (kPrecisionBits - 1))));
+        }
+        if (ch[3] == 0u) continue;  // transparent: canvas pixel unchanged
+        const uint32_t s = ch[0] | (ch[1] << 8) | (ch[2] << 16) | (ch[3] << 24);
+        crow[x] = ch[3] == 255u ? s : over_px(crow[x], unpremultiply_px(s));
+    }
+}
+
+struct DevPlacementT {
+    const uint8_t *src;   // cutout (mode 1) or w x h overlay to composite as is (mode 0)
+    const int32_t *w0x;   // [w]  first source word (4 px) of output column j
+    const uint32_t *plx;  // [3*nwx][w] coefficient byte planes
+    const int32_t *w0y;   // [h]
+    const uint32_t *ply;  // [3*nwy][h]
+    int32_t src_pitch;    // bytes
+    int32_t sw, sh;
+    int32_t x, y, w, h;   // destination box
+    int32_t nwx, nwy;     // words per output sample (3, 4 or 5)
+    int32_t mode;         // 0 = plain over, 1 = resample in the tile kernel
+    int32_t vec_ok;       // src 16-byte aligned with pitch % 16 == 0
+    int32_t pad_[2];
+};
+static_assert(sizeof(DevPlacementT) == 96, "DevPlacementT layout");
+
+constexpr int kDescCache = 64;  // placement descriptors cached in shared memory per CTA
+constexpr int kDescWords = sizeof(DevPlacementT) / 4;
+
+// grid = (max tiles per canvas, n canvases): blockIdx.y is the canvas, blockIdx.x its tile.
+__global__ void __launch_bounds__(kThreads, 2)
+composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__restrict__ placements,
+                       int patch_words, int inter_words, int *__restrict__ status) {
+    extern __shared__ uint32_t smem[];
+    uint32_t *ctile = smem;                   // kTileH * kCtPitch
+    uint32_t *P = ctile + kTileH * kCtPitch;  // patch_words
+    uint32_t *I = P + patch_words;            // inter_words
+    __shared__ __align__(16) uint32_t desc_words[kDescCache * kDescWords];
+    __shared__ uint32_t hit_mask[kDescCache / 32];
+
+    const DevCanvas cv = canvases[blockIdx.y];
+    const int local = blockIdx.x;
+    if (local >= cv.tiles_x * cv.tiles_y) return;  // canvases of different sizes share one grid
+    const int ty = local / cv.tiles_x, tx = local - ty * cv.tiles_x;
+    const int tx0 = tx * kTileW, ty0 = ty * kTileH;
+    const int tx1 = min(cv.W, tx0 + kTileW), ty1 = min(cv.H, ty0 + kTileH);
+    const int tw = tx1 - tx0, th = ty1 - ty0;
+
+    // ---- placement descriptors -> shared memory (one coalesced pass), canvas tile -> shared memory ----
+    const int n_cached = min(cv.count, kDescCache);
+    {
+        const uint32_t *g = reinterpret_cast<const uint32_t *>(placements + cv.first);
+        for (int i = threadIdx.x; i < n_cached * kDescWords; i += kThreads) desc_words[i] = __ldg(g + i);
+    }
+    for (int i = threadIdx.x; i < kTileW * kTileH; i += kThreads) {
+        const int yy = i / kTileW, xx = i - yy * kTileW;
+        if (yy < th && xx < tw)
+            ctile[yy * kCtPitch + xx] =
+                cv.bg ? ld_px(cv.bg, (int64_t)(ty0 + yy) * cv.bg_pitch + (int64_t)(tx0 + xx) * 4) : cv.solid;
+    }
+    __syncthreads();
+    const DevPlacementT *desc = reinterpret_cast<const DevPlacementT *>(desc_words);
+    // which cached placements touch this tile: one ballot per warp of 32 descriptors
+    if (threadIdx.x < kDescCache) {
+        bool hit = false;
+        if ((int)threadIdx.x < n_cached) {
+            const DevPlacementT &d = desc[threadIdx.x];
+            hit = max(tx0, d.x) < min(tx1, d.x + d.w) && max(ty0, d.y) < min(ty1, d.y + d.h);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if ((threadIdx.x & 31) == 0) hit_mask[threadIdx.x >> 5] = m;
+    }
+    __syncthreads();
+
+    // ---- z-order walk over the placements that touch the tile ----
+    for (int pi = 0; pi < cv.count; ++pi) {
+        const DevPlacementT *pp;
+        if (pi < kDescCache) {
+            const uint32_t m = hit_mask[pi >> 5] >> (pi & 31);
+            if (m == 0u) {  // nothing left in this group of 32
+                pi |= 31;
+                continue;
+            }
+            pi += __ffs((int)m) - 1;
+            pp = desc + pi;
+        } else {
+            pp = placements + cv.first + pi;  // beyond the cache: straight from global memory
+        }
+        const int px = pp->x, py = pp->y, pw = pp->w, ph = pp->h;
+        const int ix0 = max(tx0, px), iy0 = max(ty0, py);
+        const int ix1 = min(tx1, px + pw), iy1 = min(ty1, py + ph);
+        if (ix0 >= ix1 || iy0 >= iy1) continue;  // uniform across the CTA
+        const int two = ix1 - ix0, tho = iy1 - iy0;
+        const uint8_t *src = pp->src;
+        const int spitch = pp->src_pitch;
+        if (pp->mode == 0) {
+            // identity-size placement: plain over straight from the cutout
+            for (int i = threadIdx.x; i < two * tho; i += kThreads) {
+                const int yy = i / two, xx = i - yy * two;
+                const uint32_t s = ld_px(src, (int64_t)(iy0 + yy - py) * spitch + (int64_t)(ix0 + xx - px) * 4);
+                uint32_t *d = ctile + (iy0 + yy - ty0) * kCtPitch + (ix0 + xx - tx0);
+                *d = over_px(*d, s);
+            }
+            __syncthreads();
+            continue;
+        }
+        const int32_t *w0x = pp->w0x, *w0y = pp->w0y;
+        const uint32_t *plx = pp->plx, *ply = pp->ply;
+        const int nwx = pp->nwx, nwy = pp->nwy;
+        const int ox0 = ix0 - px, ox1 = ix1 - px, oy0 = iy0 - py, oy1 = iy1 - py;
+        const int cw0 = __ldg(w0x + ox0), cw1 = __ldg(w0x + ox1 - 1) + nwx;
+        const int rw0 = __ldg(w0y + oy0), rw1 = __ldg(w0y + oy1 - 1) + nwy;
+        {   // coefficient rows -> L1 while the patch is staged
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            if (warp < 2 && warp * 32 + lane < two) prefetch_coeffs(w0x, plx, nwx, pw, ox0 + warp * 32 + lane);
+            if (warp == 2 && lane < tho) prefetch_coeffs(w0y, ply, nwy, ph, oy0 + lane);
+        }
+        const int NCW = cw1 - cw0, NRQ = rw1 - rw0, NR = 4 * NRQ;
+        const int IPW = NRQ | 1;
+        const int plane_stride = NR * NCW, iplane_stride = kTileW * IPW;
+        if (4 * plane_stride > patch_words || 4 * iplane_stride > inter_words) {
+            if (threadIdx.x == 0)
+                atomicOr(status, 4 * plane_stride > patch_words ? kStatusPatchOverflow : kStatusInterOverflow);
+            continue;  // host sizing bug: flagged, never silently wrong
+        }
+        stage_patch(P, plane_stride, NR, NCW, src, spitch, pp->sw, pp->sh, rw0, cw0, pp->vec_ok != 0);
+        __syncthreads();
+        if (nwx == 3)
+            tile_hpass<3>(P, plane_stride, NCW, I, iplane_stride, IPW, NRQ, cw0, ox0, two, w0x, plx, pw);
+        else if (nwx == 4)
+            tile_hpass<4>(P, plane_stride, NCW, I, iplane_stride, IPW, NRQ, cw0, ox0, two, w0x, plx, pw);
+        else
+            tile_hpass<5>(P, plane_stride, NCW, I, iplane_stride, IPW, NRQ, cw0, ox0, two, w0x, plx, pw);
+        __syncthreads();
+        if (nwy == 3)
+            tile_vpass_over<3>(I, iplane_stride, IPW, ctile, rw0, oy0, tho, two, ix0 - tx0, iy0 - ty0, w0y, ply, ph);
+        else if (nwy == 4)
+            tile_vpass_over<4>(I, iplane_stride, IPW, ctile, rw0, oy0, tho, two, ix0 - tx0, iy0 - ty0, w0y, ply, ph);
+        else
+            tile_vpass_over<5>(I, iplane_stride, IPW, ctile, rw0, oy0, tho, two, ix0 - tx0, iy0 - ty0, w0y, ply, ph);
+        __syncthreads();
+    }
+
+    // ---- write the tile once ----
+    for (int i = threadIdx.x; i < kTileW * kTileH; i += kThreads) {
+        const int yy = i / kTileW, xx = i - yy * kTileW;
+        if (yy < th && xx < tw)
+            *reinterpret_cast<uint32_t *>(cv.out + (int64_t)(ty0 + yy) * cv.out_pitch + (int64_t)(tx0 + xx) * 4) =
+                ctile[yy * kCtPitch + xx];
+    }
+}
+
+}  // namespace b200comp
