@@ -20,7 +20,8 @@ INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 
 CUDA_SOURCES = ["b200comp.cu", "host_api.cu"]
 CXX_SOURCES = ["coeffs.cpp"]
-HEADERS = [os.path.join(CSRC, h) for h in ("kernels.cuh", "coeffs.h")] + [os.path.join(INCLUDE, "b200comp.h")]
+HEADERS = sorted(os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".h"))) + [
+    os.path.join(INCLUDE, "b200comp.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -307,7 +307,7 @@ static int resample_two_pass(const uint8_t *src, int sw, int sh, int64_t sp, uin
 // ---- coefficient tables of one plan / call ------------------------------------------------
 // Two device formats share one int32 buffer:
 //   legacy : k[out][ks] int32 + bounds[out][2]              (generic one-axis kernels)
-//   packed : w0[out] + planes[3*nw][out] (byte planes, SoA)  (fused tile kernel, dp4a)
+//   packed : planes[3*nw][out] (byte planes, SoA)            (fused tile kernel, dp4a)
 struct TableRef {
     int64_t k_off = 0;  // legacy: k      | packed: w0
     int64_t b_off = 0;  // legacy: bounds | packed: planes
@@ -349,7 +349,6 @@ struct TableSet {
         } else {
             r.ks = key.kind == 2 ? 3 : packed_words(lanczos_ksize(key.in_size, key.out_size));
             r.k_off = total;
-            total += n;
             r.b_off = total;
             total += (int64_t)3 * r.ks * n;
         }
@@ -363,11 +362,10 @@ struct TableSet {
     }
 
     // split Pillow's 22-bit taps into byte planes placed at their position inside 4-sample words
-    static void pack(int n_out, int ks, const int32_t *k, const int32_t *bounds, int nw, int32_t *w0, int32_t *planes) {
+    static void pack(int n_out, int ks, const int32_t *k, const int32_t *bounds, int nw, int32_t *planes) {
         uint32_t *pl = reinterpret_cast<uint32_t *>(planes);
         for (int j = 0; j < n_out; ++j) {
             const int lo = bounds[2 * j], n = bounds[2 * j + 1];
-            w0[j] = lo >> 2;
             for (int t = 0; t < n; ++t) {
                 const int pos = (lo & 3) + t, word = pos >> 2, sh = 8 * (pos & 3);
                 const int32_t kv = k[(size_t)j * ks + t];
@@ -405,7 +403,7 @@ struct TableSet {
                     b.assign((size_t)2 * n, 0);
                     build_lanczos_table(key.in_size, key.out_size, k.data(), b.data());
                 }
-                pack(n, ks, k.data(), b.data(), r.ks, h + r.k_off, h + r.b_off);
+                pack(n, ks, k.data(), b.data(), r.ks, h + r.b_off);
             }
         };
         if (n_threads == 1) {
@@ -688,6 +686,12 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             tref[i].second = ts.want_packed(p.sh, p.h, !need_v);
             d.nwx = tref[i].first.ks;
             d.nwy = tref[i].second.ks;
+            // the kernel recomputes each window start from these doubles exactly as the table builder does;
+            // a skipped pass is the 1-tap identity: scale 1, support 1 -> first tap = the sample itself
+            d.scale_x = need_h ? (double)p.sw / p.w : 1.0;
+            d.support_x = need_h ? 3.0 * std::max(d.scale_x, 1.0) : 1.0;
+            d.scale_y = need_v ? (double)p.sh / p.h : 1.0;
+            d.support_y = need_v ? 3.0 * std::max(d.scale_y, 1.0) : 1.0;
             max_patch = std::max<int>(max_patch, (int)patch);
             max_inter = std::max<int>(max_inter, (int)inter);
             ++n_fused;
@@ -757,9 +761,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     for (int i = 0; i < n_placements; ++i) {
         DevPlacementT &d = hp[i];
         if (d.mode == 1) {
-            d.w0x = plan->d_tables + tref[i].first.k_off;
             d.plx = reinterpret_cast<const uint32_t *>(plan->d_tables + tref[i].first.b_off);
-            d.w0y = plan->d_tables + tref[i].second.k_off;
             d.ply = reinterpret_cast<const uint32_t *>(plan->d_tables + tref[i].second.b_off);
         } else if (pre_index[i] >= 0) {
             d.src = plan->pre[(size_t)pre_index[i]].dst;

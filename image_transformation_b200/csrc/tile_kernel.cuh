@@ -39,7 +39,21 @@ __device__ __forceinline__ void transpose4(uint32_t p0, uint32_t p1, uint32_t p2
     a = __byte_perm(u01, u23, 0x7632);
 }
 
-__device__ __forceinline__ uint32_t clip8i(int32_t v) { return (uint32_t)min(255, max(0, v >> kPrecisionBits)); }
+// Resample.c clip8: arithmetic shift, clamp to [0, 255] (one shift + one min-with-relu)
+__device__ __forceinline__ uint32_t clip8i(int32_t v) { return (uint32_t)__vimin_s32_relu(v >> kPrecisionBits, 255); }
+// First source sample of output sample `o` (Resample.c precompute_coeffs: xmin), recomputed with the
+// same IEEE double operations as the host table builder (no contraction), so no table lookup is needed.
+__device__ __forceinline__ int first_tap(int o, double scale, double support) {
+    const double center = __dmul_rn((double)o + 0.5, scale);
+    const int lo = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+    return max(lo, 0);
+}
+
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---- stage: global RGBA -> premultiplied planar patch -----------------------------------------
 // P[c][r][wx]: plane c at P + c*plane_stride, row pitch NCW words; source pixel 4*(cw0+wx)+k of
@@ -102,9 +116,7 @@ __device__ __forceinline__ void stage_patch(uint32_t *__restrict__ P, int plane_
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // pull the coefficient rows this lane will need into L1 while the patch is being staged
-__device__ __forceinline__ void prefetch_coeffs(const int32_t *__restrict__ w0, const uint32_t *__restrict__ pl, int nw,
-                                                int n_out, int idx) {
-    prefetch_l1(w0 + idx);
+__device__ __forceinline__ void prefetch_coeffs(const uint32_t *__restrict__ pl, int nw, int n_out, int idx) {
     for (int q = 0; q < 3 * nw; ++q) prefetch_l1(pl + (int64_t)q * n_out + idx);
 }
 
@@ -114,7 +126,7 @@ __device__ __forceinline__ void prefetch_coeffs(const int32_t *__restrict__ w0, 
 template <int NW>
 __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int plane_stride, int NCW,
                                            uint32_t *__restrict__ I, int iplane_stride, int IPW, int NRQ, int cw0,
-                                           int ox0, int two, const int32_t *__restrict__ w0x,
+                                           int ox0, int two, double scale, double support,
                                            const uint32_t *__restrict__ plx, int n_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ncg = (two + 31) >> 5;  // 1 or 2 column groups of 32
@@ -123,7 +135,7 @@ __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int p
     const int jj = cg * 32 + lane;
     if (jj >= two) return;
     const int j = ox0 + jj;
-    const int wbase = __ldg(w0x + j) - cw0;
+    const int wbase = (first_tap(j, scale, support) >> 2) - cw0;
     uint32_t k0[NW], k1[NW], k2[NW];
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
@@ -132,13 +144,13 @@ __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int p
         k2[i] = __ldg(plx + (int64_t)(2 * NW + i) * n_out + j);
     }
     for (int rq = warp / ncg; rq < NRQ; rq += rstep) {
-        uint32_t o[4] = {0u, 0u, 0u, 0u};
+        uint32_t o[4];
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
             const uint32_t *row = P + (rq * 4 + rr) * NCW + wbase;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                uint32_t a0 = 0u, a1 = 0u;
+                uint32_t a0 = 1u << (kPrecisionBits - 1), a1 = 0u;  // rounding term rides in the low plane
                 int32_t a2 = 0;
 #pragma unroll
                 for (int i = 0; i < NW; ++i) {
@@ -147,8 +159,11 @@ __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int p
                     a1 = dp4a_uu(wd, k1[i], a1);
                     a2 = dp4a_us(wd, k2[i], a2);
                 }
-                const int32_t v = (int32_t)(a0 + (a1 << 8) + ((uint32_t)a2 << 16) + (1u << (kPrecisionBits - 1)));
-                o[c] |= clip8i(v) << (8 * rr);
+                const uint32_t v = clip8i((int32_t)(a0 + (a1 << 8) + ((uint32_t)a2 << 16)));
+                if (rr == 0) o[c] = v;
+                else if (rr == 1) o[c] = __byte_perm(o[c], v, 0x3240);
+                else if (rr == 2) o[c] = __byte_perm(o[c], v, 0x3410);
+                else o[c] = __byte_perm(o[c], v, 0x4210);
             }
         }
         uint32_t *d = I + jj * IPW + rq;
@@ -163,12 +178,12 @@ __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int p
 template <int NW>
 __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, int iplane_stride, int IPW,
                                                 uint32_t *__restrict__ ctile, int rw0, int oy0, int tho, int two,
-                                                int tile_dx, int tile_dy, const int32_t *__restrict__ w0y,
+                                                int tile_dx, int tile_dy, double scale, double support,
                                                 const uint32_t *__restrict__ ply, int n_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane >= tho) return;
     const int y = oy0 + lane;
-    const int wbase = __ldg(w0y + y) - rw0;
+    const int wbase = (first_tap(y, scale, support) >> 2) - rw0;
     uint32_t k0[NW], k1[NW], k2[NW];
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
@@ -179,10 +194,10 @@ __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, 
     uint32_t *crow = ctile + (tile_dy + lane) * kCtPitch + tile_dx;
     for (int x = warp; x < two; x += kWarps) {
         const uint32_t *col = I + x * IPW + wbase;
-        uint32_t ch[4];
+        int32_t acc[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            uint32_t a0 = 0u, a1 = 0u;
+            uint32_t a0 = 1u << (kPrecisionBits - 1), a1 = 0u;
             int32_t a2 = 0;
 #pragma unroll
             for (int i = 0; i < NW; ++i) {
@@ -191,29 +206,33 @@ __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, 
                 a1 = dp4a_uu(wd, k1[i], a1);
                 a2 = dp4a_us(wd, k2[i], a2);
             }
-            ch[c] = clip8i((int32_t)(a0 + (a1 << 8) + ((uint32_t)a2 << 16) + (1u << (kPrecisionBits - 1))));
+            acc[c] = (int32_t)(a0 + (a1 << 8) + ((uint32_t)a2 << 16));
         }
-        if (ch[3] == 0u) continue;  // transparent: canvas pixel unchanged
-        const uint32_t s = ch[0] | (ch[1] << 8) | (ch[2] << 16) | (ch[3] << 24);
-        crow[x] = ch[3] == 255u ? s : over_px(crow[x], unpremultiply_px(s));
+        // Alpha tests on the raw accumulator (clip8(acc) == 0 / == 255).  Do NOT test the clamped value:
+        // CUDA 12.9 ptxas folds `clamp(x) == 255` into VIMNMX.RELU's predicate output with the wrong
+        // sense on sm_100a (partially transparent pixels took the opaque branch).
+        if (acc[3] < (1 << kPrecisionBits)) continue;  // transparent: canvas pixel unchanged
+        const bool opaque = acc[3] >= (255 << kPrecisionBits);
+        const uint32_t s = clip8i(acc[0]) | (clip8i(acc[1]) << 8) | (clip8i(acc[2]) << 16) | (clip8i(acc[3]) << 24);
+        crow[x] = opaque ? s : over_px(crow[x], unpremultiply_px(s));
     }
 }
 
 struct DevPlacementT {
-    const uint8_t *src;   // cutout (mode 1) or w x h overlay to composite as is (mode 0)
-    const int32_t *w0x;   // [w]  first source word (4 px) of output column j
-    const uint32_t *plx;  // [3*nwx][w] coefficient byte planes
-    const int32_t *w0y;   // [h]
-    const uint32_t *ply;  // [3*nwy][h]
-    int32_t src_pitch;    // bytes
+    const uint8_t *src;    // cutout (mode 1) or w x h overlay to composite as is (mode 0)
+    const uint32_t *plx;   // [3*nwx][w] coefficient byte planes of the horizontal pass
+    const uint32_t *ply;   // [3*nwy][h] vertical pass
+    double scale_x, support_x;  // sw / w and 3 * max(1, scale): exactly the host builder's doubles
+    double scale_y, support_y;
+    int32_t src_pitch;     // bytes
     int32_t sw, sh;
-    int32_t x, y, w, h;   // destination box
-    int32_t nwx, nwy;     // words per output sample (3, 4 or 5)
-    int32_t mode;         // 0 = plain over, 1 = resample in the tile kernel
-    int32_t vec_ok;       // src 16-byte aligned with pitch % 16 == 0
-    int32_t pad_[2];
+    int32_t x, y, w, h;    // destination box
+    int32_t nwx, nwy;      // words per output sample (3, 4 or 5)
+    int32_t mode;          // 0 = plain over, 1 = resample in the tile kernel
+    int32_t vec_ok;        // src 16-byte aligned with pitch % 16 == 0
+    int32_t pad_[3];
 };
-static_assert(sizeof(DevPlacementT) == 96, "DevPlacementT layout");
+static_assert(sizeof(DevPlacementT) == 112, "DevPlacementT layout");
 
 constexpr int kDescCache = 64;  // placement descriptors cached in shared memory per CTA
 constexpr int kDescWords = sizeof(DevPlacementT) / 4;
@@ -243,11 +262,17 @@ composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacemen
         const uint32_t *g = reinterpret_cast<const uint32_t *>(placements + cv.first);
         for (int i = threadIdx.x; i < n_cached * kDescWords; i += kThreads) desc_words[i] = __ldg(g + i);
     }
-    for (int i = threadIdx.x; i < kTileW * kTileH; i += kThreads) {
+    // the background tile streams in asynchronously (cp.async); it is first needed by an over step
+#pragma unroll
+    for (int k = 0; k < kTileW * kTileH / kThreads; ++k) {
+        const int i = threadIdx.x + k * kThreads;
         const int yy = i / kTileW, xx = i - yy * kTileW;
-        if (yy < th && xx < tw)
-            ctile[yy * kCtPitch + xx] =
-                cv.bg ? ld_px(cv.bg, (int64_t)(ty0 + yy) * cv.bg_pitch + (int64_t)(tx0 + xx) * 4) : cv.solid;
+        if (yy < th && xx < tw) {
+            if (cv.bg)
+                cp_async4(ctile + yy * kCtPitch + xx, cv.bg + (int64_t)(ty0 + yy) * cv.bg_pitch + (int64_t)(tx0 + xx) * 4);
+            else
+                ctile[yy * kCtPitch + xx] = cv.solid;
+        }
     }
     __syncthreads();
     const DevPlacementT *desc = reinterpret_cast<const DevPlacementT *>(desc_words);
@@ -286,6 +311,8 @@ composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacemen
         const int spitch = pp->src_pitch;
         if (pp->mode == 0) {
             // identity-size placement: plain over straight from the cutout
+            cp_async_wait_all();
+            __syncthreads();
             for (int i = threadIdx.x; i < two * tho; i += kThreads) {
                 const int yy = i / two, xx = i - yy * two;
                 const uint32_t s = ld_px(src, (int64_t)(iy0 + yy - py) * spitch + (int64_t)(ix0 + xx - px) * 4);
@@ -295,16 +322,16 @@ composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacemen
             __syncthreads();
             continue;
         }
-        const int32_t *w0x = pp->w0x, *w0y = pp->w0y;
         const uint32_t *plx = pp->plx, *ply = pp->ply;
         const int nwx = pp->nwx, nwy = pp->nwy;
+        const double scx = pp->scale_x, spx = pp->support_x, scy = pp->scale_y, spy = pp->support_y;
         const int ox0 = ix0 - px, ox1 = ix1 - px, oy0 = iy0 - py, oy1 = iy1 - py;
-        const int cw0 = __ldg(w0x + ox0), cw1 = __ldg(w0x + ox1 - 1) + nwx;
-        const int rw0 = __ldg(w0y + oy0), rw1 = __ldg(w0y + oy1 - 1) + nwy;
+        const int cw0 = first_tap(ox0, scx, spx) >> 2, cw1 = (first_tap(ox1 - 1, scx, spx) >> 2) + nwx;
+        const int rw0 = first_tap(oy0, scy, spy) >> 2, rw1 = (first_tap(oy1 - 1, scy, spy) >> 2) + nwy;
         {   // coefficient rows -> L1 while the patch is staged
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-            if (warp < 2 && warp * 32 + lane < two) prefetch_coeffs(w0x, plx, nwx, pw, ox0 + warp * 32 + lane);
-            if (warp == 2 && lane < tho) prefetch_coeffs(w0y, ply, nwy, ph, oy0 + lane);
+            if (warp < 2 && warp * 32 + lane < two) prefetch_coeffs(plx, nwx, pw, ox0 + warp * 32 + lane);
+            if (warp == 2 && lane < tho) prefetch_coeffs(ply, nwy, ph, oy0 + lane);
         }
         const int NCW = cw1 - cw0, NRQ = rw1 - rw0, NR = 4 * NRQ;
         const int IPW = NRQ | 1;
@@ -317,22 +344,25 @@ composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacemen
         stage_patch(P, plane_stride, NR, NCW, src, spitch, pp->sw, pp->sh, rw0, cw0, pp->vec_ok != 0);
         __syncthreads();
         if (nwx == 3)
-            tile_hpass<3>(P, plane_stride, NCW, I, iplane_stride, IPW, NRQ, cw0, ox0, two, w0x, plx, pw);
+            tile_hpass<3>(P, plane_stride, NCW, I, iplane_stride, IPW, NRQ, cw0, ox0, two, scx, spx, plx, pw);
         else if (nwx == 4)
-            tile_hpass<4>(P, plane_stride, NCW, I, iplane_stride, IPW, NRQ, cw0, ox0, two, w0x, plx, pw);
+            tile_hpass<4>(P, plane_stride, NCW, I, iplane_stride, IPW, NRQ, cw0, ox0, two, scx, spx, plx, pw);
         else
-            tile_hpass<5>(P, plane_stride, NCW, I, iplane_stride, IPW, NRQ, cw0, ox0, two, w0x, plx, pw);
+            tile_hpass<5>(P, plane_stride, NCW, I, iplane_stride, IPW, NRQ, cw0, ox0, two, scx, spx, plx, pw);
+        cp_async_wait_all();  // background tile (no-op after the first placement)
         __syncthreads();
         if (nwy == 3)
-            tile_vpass_over<3>(I, iplane_stride, IPW, ctile, rw0, oy0, tho, two, ix0 - tx0, iy0 - ty0, w0y, ply, ph);
+            tile_vpass_over<3>(I, iplane_stride, IPW, ctile, rw0, oy0, tho, two, ix0 - tx0, iy0 - ty0, scy, spy, ply, ph);
         else if (nwy == 4)
-            tile_vpass_over<4>(I, iplane_stride, IPW, ctile, rw0, oy0, tho, two, ix0 - tx0, iy0 - ty0, w0y, ply, ph);
+            tile_vpass_over<4>(I, iplane_stride, IPW, ctile, rw0, oy0, tho, two, ix0 - tx0, iy0 - ty0, scy, spy, ply, ph);
         else
-            tile_vpass_over<5>(I, iplane_stride, IPW, ctile, rw0, oy0, tho, two, ix0 - tx0, iy0 - ty0, w0y, ply, ph);
+            tile_vpass_over<5>(I, iplane_stride, IPW, ctile, rw0, oy0, tho, two, ix0 - tx0, iy0 - ty0, scy, spy, ply, ph);
         __syncthreads();
     }
 
     // ---- write the tile once ----
+    cp_async_wait_all();
+    __syncthreads();
     for (int i = threadIdx.x; i < kTileW * kTileH; i += kThreads) {
         const int yy = i / kTileW, xx = i - yy * kTileW;
         if (yy < th && xx < tw)
