@@ -14,6 +14,7 @@
 #include <utility>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "../../include/b200comp.h"
@@ -255,6 +256,23 @@ static bool aligned4(const void *p, int64_t pitch) {
     return (reinterpret_cast<uintptr_t>(p) & 3u) == 0 && (pitch & 3) == 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
 // identity table for a skipped pass: one tap of 1.0 at the same index
 static void identity_table(int n, int32_t *k, int32_t *b) {
     for (int i = 0; i < n; ++i) {
@@ -453,6 +471,9 @@ struct b200comp_plan {
         uint8_t *scratch;  // intermediate
     };
     std::vector<Pre> pre;
+    PrepDesc *d_prep = nullptr;  // distinct cutouts the tile kernel resamples (prepared every run)
+    int n_prep = 0;
+    int prep_blocks_x = 1;
     std::vector<void *> owned;  // device allocations freed with the plan
 };
 
@@ -662,7 +683,6 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         d.src_pitch = (int32_t)p.src_pitch;
         d.sw = p.sw; d.sh = p.sh;
         d.x = p.x; d.y = p.y; d.w = p.w; d.h = p.h;
-        d.vec_ok = ((reinterpret_cast<uintptr_t>(p.src) & 15u) == 0 && (p.src_pitch & 15) == 0) ? 1 : 0;
         if (p.w == p.sw && p.h == p.sh) {
             d.mode = 0;
             ++n_ident;
@@ -674,11 +694,13 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         const bool vertical_first = (p.flags & B200COMP_VERTICAL_FIRST) && need_h && need_v;
         bool fused = !vertical_first && nwx > 0 && nwy > 0;
         int64_t patch = 0, inter = 0;
+        int ncw = 0, nrq = 0;
         if (fused) {
-            const int ncw = words_bound(p.sw, p.w, kTileW, nwx), nrq = words_bound(p.sh, p.h, kTileH, nwy);
-            patch = (int64_t)4 * (4 * nrq) * ncw;          // 4 channel planes x rows x words
+            ncw = words_bound(p.sw, p.w, kTileW, nwx);
+            nrq = words_bound(p.sh, p.h, kTileH, nwy);
+            patch = (int64_t)4 * (4 * nrq) * ncw;          // TMA box: rows x (words x 4 channels)
             inter = (int64_t)4 * kTileW * (nrq | 1);       // 4 channel planes x columns x row-quads
-            fused = ((size_t)kTileH * kCtPitch + patch + inter) * 4 <= kFusedSmemCap;
+            fused = ((size_t)kTileH * kCtPitch + patch + inter) * 4 <= kFusedSmemCap && 4 * ncw <= 256 && 4 * nrq <= 256;
         }
         if (fused) {
             d.mode = 1;
@@ -686,6 +708,8 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             tref[i].second = ts.want_packed(p.sh, p.h, !need_v);
             d.nwx = tref[i].first.ks;
             d.nwy = tref[i].second.ks;
+            d.pbw = 4 * ncw;
+            d.nrbox = 4 * nrq;
             // the kernel recomputes each window start from these doubles exactly as the table builder does;
             // a skipped pass is the 1-tap identity: scale 1, support 1 -> first tap = the sample itself
             d.scale_x = need_h ? (double)p.sw / p.w : 1.0;
@@ -708,7 +732,6 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             d.mode = 0;
             d.sw = p.w; d.sh = p.h;
             d.src_pitch = p.w * 4;
-            d.vec_ok = 0;
         }
     }
 
@@ -767,6 +790,62 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             d.src = plan->pre[(size_t)pre_index[i]].dst;
         }
     }
+    // ---- prepared cutouts (premultiplied, planar) + one TMA descriptor per resampled placement ----
+    {
+        typedef std::tuple<const uint8_t *, int, int, int64_t> SrcKey;
+        std::map<SrcKey, int> prep_index;
+        std::vector<PrepDesc> hprep;
+        std::vector<CUtensorMap> hmaps;
+        std::vector<int> map_of((size_t)std::max(1, n_placements), -1);
+        int64_t max_words = 1;
+        for (int i = 0; i < n_placements; ++i) {
+            if (hp[i].mode != 1) continue;
+            const b200comp_placement &p = placements[i];
+            SrcKey key(p.src, p.sw, p.sh, p.src_pitch);
+            auto it = prep_index.find(key);
+            if (it == prep_index.end()) {
+                PrepDesc pd;
+                std::memset(&pd, 0, sizeof pd);
+                pd.src = p.src;
+                pd.src_pitch = p.src_pitch;
+                pd.sw = p.sw;
+                pd.sh = p.sh;
+                pd.w4 = (p.sw + 3) / 4;
+                pd.vec_ok = ((reinterpret_cast<uintptr_t>(p.src) & 15u) == 0 && (p.src_pitch & 15) == 0) ? 1 : 0;
+                CUDA_TRY(dev_alloc((void **)&pd.dst, (size_t)pd.w4 * 16 * p.sh));
+                max_words = std::max<int64_t>(max_words, (int64_t)pd.w4 * p.sh);
+                it = prep_index.emplace(key, (int)hprep.size()).first;
+                hprep.push_back(pd);
+            }
+            const PrepDesc &pd = hprep[(size_t)it->second];
+            EncodeTiledFn enc = encode_tiled_fn();
+            if (!enc) return fail(B200COMP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+            CUtensorMap tm;
+            const cuuint64_t gdim[2] = {(cuuint64_t)pd.w4 * 4, (cuuint64_t)pd.sh};
+            const cuuint64_t gstride[1] = {(cuuint64_t)pd.w4 * 16};
+            const cuuint32_t box[2] = {(cuuint32_t)hp[i].pbw, (cuuint32_t)hp[i].nrbox};
+            const cuuint32_t estride[2] = {1, 1};
+            const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, pd.dst, gdim, gstride, box, estride,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS)
+                return fail(B200COMP_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for placement " + std::to_string(i));
+            map_of[i] = (int)hmaps.size();
+            hmaps.push_back(tm);
+        }
+        if (!hprep.empty()) {
+            CUtensorMap *d_maps = nullptr;
+            CUDA_TRY(dev_alloc((void **)&d_maps, hmaps.size() * sizeof(CUtensorMap)));
+            CUDA_TRY(dev_alloc((void **)&plan->d_prep, hprep.size() * sizeof(PrepDesc)));
+            CUDA_TRY(cudaMemcpyAsync(d_maps, hmaps.data(), hmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(plan->d_prep, hprep.data(), hprep.size() * sizeof(PrepDesc), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));  // hmaps / hprep are locals
+            plan->n_prep = (int)hprep.size();
+            plan->prep_blocks_x = (int)std::max<int64_t>(1, std::min<int64_t>((max_words + 255) / 256, 64));
+            for (int i = 0; i < n_placements; ++i)
+                if (map_of[i] >= 0) hp[i].tmap = d_maps + map_of[i];
+        }
+    }
     CUDA_TRY(cudaMemcpyAsync(plan->d_tables, ts.host.data(), tbytes, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(plan->d_placements, hp.data(), hp.size() * sizeof(DevPlacementT), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(plan->d_canvases, hc.data(), hc.size() * sizeof(DevCanvas), cudaMemcpyHostToDevice, st));
@@ -779,7 +858,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     CUDA_TRY(cudaFuncSetAttribute(composite_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemBytes));
 
     plan->info[B200COMP_INFO_ALGORITHMIC_BYTES] = algo;
-    plan->info[B200COMP_INFO_LAUNCHES_PER_RUN] = 1;
+    plan->info[B200COMP_INFO_LAUNCHES_PER_RUN] = 1 + (plan->n_prep > 0 ? 1 : 0);
     for (auto &pr : plan->pre) plan->info[B200COMP_INFO_LAUNCHES_PER_RUN] += (pr.w != pr.sw && pr.h != pr.sh) ? 2 : 1;
     plan->info[B200COMP_INFO_FUSED_PLACEMENTS] = n_fused;
     plan->info[B200COMP_INFO_IDENTITY_PLACEMENTS] = n_ident;
@@ -802,6 +881,15 @@ int b200comp_plan_run(b200comp_plan *plan, void *stream) {
                                    t + pr.tx.b_off, pr.tx.ks, t + pr.ty.k_off, t + pr.ty.b_off, pr.ty.ks, pr.scratch,
                                    pr.flags, st);
         if (rc) return rc;
+    }
+    if (plan->n_prep > 0) {
+        // premultiplied planar copies of the cutouts the tile kernel resamples (re-made every run, so
+        // the plan never shows stale pixels if the caller rewrites a cutout between runs)
+        for (int p0 = 0; p0 < plan->n_prep; p0 += 65535) {
+            const int np = std::min(65535, plan->n_prep - p0);
+            prepare_cutouts_kernel<<<dim3((unsigned)plan->prep_blocks_x, (unsigned)np), 256, 0, st>>>(plan->d_prep + p0);
+        }
+        CUDA_TRY(cudaGetLastError());
     }
     // grid.y is limited to 65535 canvases per launch
     for (int c0 = 0; c0 < plan->n_canvases; c0 += 65535) {

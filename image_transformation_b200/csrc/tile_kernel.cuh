@@ -55,62 +55,77 @@ __device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const void *gsrc) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// ---- stage: global RGBA -> premultiplied planar patch -----------------------------------------
-// P[c][r][wx]: plane c at P + c*plane_stride, row pitch NCW words; source pixel 4*(cw0+wx)+k of
-// source row 4*rw0+r sits in byte k.  Rows / columns outside the cutout are left untouched: every
-// tap that could read them has a zero coefficient.  Loads are issued four at a time per thread
-// (memory-level parallelism) before any of them is consumed.
-__device__ __forceinline__ void stage_store(uint32_t *__restrict__ d, int plane_stride, uint32_t p0, uint32_t p1,
-                                            uint32_t p2, uint32_t p3) {
-    uint32_t R, G, B, A;
-    transpose4(p0, p1, p2, p3, R, G, B, A);
-    if (((A ^ (A >> 1)) & 0x7f7f7f7fu) == 0u) {
-        // every alpha is 0 or 255: MULDIV255(c, a) is c or 0 -> mask the colours with the alpha bytes
-        R &= A; G &= A; B &= A;
-    } else {
-        transpose4(premultiply_px(p0), premultiply_px(p1), premultiply_px(p2), premultiply_px(p3), R, G, B, A);
+// ---- prepare: RGBA cutout -> premultiplied, channel-planar words --------------------------------
+// One launch per plan run converts every distinct cutout the tile kernel resamples into the layout
+// its dp4a passes consume: for each row, for each group of 4 pixels, 16 bytes = (R4, G4, B4, A4)
+// with byte k of each word = pixel 4*g+k, colours premultiplied (Convert.c rgbA2rgba).  The tile
+// kernel then fetches source patches with TMA (cp.async.bulk.tensor) and does no per-pixel work
+// before the horizontal pass.  Pixels past the row end are zero.
+struct PrepDesc {
+    const uint8_t *src;
+    uint4 *dst;
+    int64_t src_pitch;
+    int32_t sw, sh;
+    int32_t w4;      // 4-pixel groups per row
+    int32_t vec_ok;  // src 16-byte aligned with pitch % 16 == 0
+};
+
+__global__ void __launch_bounds__(256) prepare_cutouts_kernel(const PrepDesc *__restrict__ descs) {
+    const PrepDesc d = descs[blockIdx.y];
+    const int64_t total = (int64_t)d.sh * d.w4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / d.w4), g = (int)(i - (int64_t)r * d.w4);
+        const int gx = 4 * g;
+        const uint8_t *rowp = d.src + (int64_t)r * d.src_pitch + (int64_t)gx * 4;
+        uint32_t p0, p1 = 0u, p2 = 0u, p3 = 0u;
+        if (d.vec_ok && gx + 3 < d.sw) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(rowp));
+            p0 = v.x; p1 = v.y; p2 = v.z; p3 = v.w;
+        } else {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(rowp);
+            p0 = __ldg(q);
+            if (gx + 1 < d.sw) p1 = __ldg(q + 1);
+            if (gx + 2 < d.sw) p2 = __ldg(q + 2);
+            if (gx + 3 < d.sw) p3 = __ldg(q + 3);
+        }
+        uint32_t R, G, B, A;
+        transpose4(p0, p1, p2, p3, R, G, B, A);
+        if (((A ^ (A >> 1)) & 0x7f7f7f7fu) == 0u) {
+            // every alpha is 0 or 255: MULDIV255(c, a) is c or 0 -> mask the colours with the alpha bytes
+            R &= A; G &= A; B &= A;
+        } else {
+            transpose4(premultiply_px(p0), premultiply_px(p1), premultiply_px(p2), premultiply_px(p3), R, G, B, A);
+        }
+        d.dst[i] = make_uint4(R, G, B, A);
     }
-    d[0] = R;
-    d[plane_stride] = G;
-    d[2 * plane_stride] = B;
-    d[3 * plane_stride] = A;
 }
 
-__device__ __forceinline__ void stage_patch(uint32_t *__restrict__ P, int plane_stride, int NR, int NCW,
-                                            const uint8_t *__restrict__ src, int spitch, int sw, int sh, int rw0,
-                                            int cw0, bool vec_ok) {
-    const uint32_t rcp = 0xFFFFFFFFu / (uint32_t)NCW + 1u;  // exact i / NCW for i*NCW < 2^32
-    const int total = NR * NCW;
-    constexpr int U = 4;
-    for (int base = threadIdx.x; base < total; base += U * kThreads) {
-        uint4 v[U];
-        int off[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = base + u * kThreads;
-            const int r = (int)__umulhi((uint32_t)i, rcp);
-            const int wx = i - r * NCW;
-            const int gy = 4 * rw0 + r, gx = 4 * (cw0 + wx);
-            off[u] = -1;
-            v[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (i < total && gy < sh && gx < sw) {
-                off[u] = r * NCW + wx;
-                const uint8_t *rowp = src + (int64_t)gy * spitch + (int64_t)gx * 4;
-                if (vec_ok && gx + 3 < sw) {
-                    v[u] = __ldg(reinterpret_cast<const uint4 *>(rowp));
-                } else {
-                    const uint32_t *q = reinterpret_cast<const uint32_t *>(rowp);
-                    v[u].x = __ldg(q);
-                    if (gx + 1 < sw) v[u].y = __ldg(q + 1);
-                    if (gx + 2 < sw) v[u].z = __ldg(q + 2);
-                    if (gx + 3 < sw) v[u].w = __ldg(q + 3);
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (off[u] >= 0) stage_store(P + off[u], plane_stride, v[u].x, v[u].y, v[u].z, v[u].w);
-    }
+// ---- TMA / mbarrier helpers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 2-D tile of the prepared cutout -> shared memory; completion is signalled on `bar`
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tmap, int x, int y, uint64_t *bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the buffer are done
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -123,8 +138,9 @@ __device__ __forceinline__ void prefetch_coeffs(const uint32_t *__restrict__ pl,
 // ---- H pass ---------------------------------------------------------------------------------
 // I[c][jj][rq]: plane c at I + c*iplane_stride, column pitch IPW words (odd), byte k of word rq =
 // intermediate row 4*rq+k (relative to source row 4*rw0).
+// P[r][4*wx + c]: exactly the TMA box (row pitch PBW words): word wx of channel c of patch row r.
 template <int NW>
-__device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int plane_stride, int NCW,
+__device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int PBW,
                                            uint32_t *__restrict__ I, int iplane_stride, int IPW, int NRQ, int cw0,
                                            int ox0, int two, double scale, double support,
                                            const uint32_t *__restrict__ plx, int n_out) {
@@ -147,14 +163,14 @@ __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int p
         uint32_t o[4];
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
-            const uint32_t *row = P + (rq * 4 + rr) * NCW + wbase;
+            const uint32_t *row = P + (rq * 4 + rr) * PBW + 4 * wbase;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t a0 = 1u << (kPrecisionBits - 1), a1 = 0u;  // rounding term rides in the low plane
                 int32_t a2 = 0;
 #pragma unroll
                 for (int i = 0; i < NW; ++i) {
-                    const uint32_t wd = row[c * plane_stride + i];
+                    const uint32_t wd = row[4 * i + c];
                     a0 = dp4a_uu(wd, k0[i], a0);
                     a1 = dp4a_uu(wd, k1[i], a1);
                     a2 = dp4a_us(wd, k2[i], a2);
@@ -219,18 +235,19 @@ __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, 
 }
 
 struct DevPlacementT {
-    const uint8_t *src;    // cutout (mode 1) or w x h overlay to composite as is (mode 0)
+    const uint8_t *src;    // mode 0: w x h overlay composited as is (raw RGBA)
     const uint32_t *plx;   // [3*nwx][w] coefficient byte planes of the horizontal pass
     const uint32_t *ply;   // [3*nwy][h] vertical pass
+    const void *tmap;      // mode 1: CUtensorMap over the prepared cutout, box = pbw x nrbox words
     double scale_x, support_x;  // sw / w and 3 * max(1, scale): exactly the host builder's doubles
     double scale_y, support_y;
-    int32_t src_pitch;     // bytes
+    int32_t src_pitch;     // bytes (mode 0)
     int32_t sw, sh;
     int32_t x, y, w, h;    // destination box
     int32_t nwx, nwy;      // words per output sample (3, 4 or 5)
     int32_t mode;          // 0 = plain over, 1 = resample in the tile kernel
-    int32_t vec_ok;        // src 16-byte aligned with pitch % 16 == 0
-    int32_t pad_[3];
+    int32_t pbw;           // TMA box width in words (= 4 * patch words per row)
+    int32_t nrbox;         // TMA box height in rows (multiple of 4)
 };
 static_assert(sizeof(DevPlacementT) == 112, "DevPlacementT layout");
 
@@ -241,12 +258,14 @@ constexpr int kDescWords = sizeof(DevPlacementT) / 4;
 __global__ void __launch_bounds__(kThreads, 2)
 composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__restrict__ placements,
                        int patch_words, int inter_words, int *__restrict__ status) {
-    extern __shared__ uint32_t smem[];
-    uint32_t *ctile = smem;                   // kTileH * kCtPitch
+    extern __shared__ __align__(128) uint32_t smem[];
+    uint32_t *ctile = smem;                   // kTileH * kCtPitch (8320 B: keeps P 128-byte aligned for TMA)
     uint32_t *P = ctile + kTileH * kCtPitch;  // patch_words
     uint32_t *I = P + patch_words;            // inter_words
     __shared__ __align__(16) uint32_t desc_words[kDescCache * kDescWords];
     __shared__ uint32_t hit_mask[kDescCache / 32];
+    __shared__ uint8_t hit_list[kDescCache];
+    __shared__ __align__(8) uint64_t tma_bar;
 
     const DevCanvas cv = canvases[blockIdx.y];
     const int local = blockIdx.x;
@@ -257,117 +276,168 @@ composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacemen
     const int tw = tx1 - tx0, th = ty1 - ty0;
 
     // ---- placement descriptors -> shared memory (one coalesced pass), canvas tile -> shared memory ----
-    const int n_cached = min(cv.count, kDescCache);
     {
+        const int n0 = min(cv.count, kDescCache);
         const uint32_t *g = reinterpret_cast<const uint32_t *>(placements + cv.first);
-        for (int i = threadIdx.x; i < n_cached * kDescWords; i += kThreads) desc_words[i] = __ldg(g + i);
+        for (int i = threadIdx.x; i < n0 * kDescWords; i += kThreads) desc_words[i] = __ldg(g + i);
     }
     // the background tile streams in asynchronously (cp.async); it is first needed by an over step
+    {
+        const int xx = threadIdx.x & (kTileW - 1), y0 = threadIdx.x / kTileW;  // 4 rows per sweep
+        const uint8_t *g = cv.bg + (int64_t)(ty0 + y0) * cv.bg_pitch + (int64_t)(tx0 + xx) * 4;
+        uint32_t *d = ctile + y0 * kCtPitch + xx;
+        const int64_t gstep = (int64_t)(kThreads / kTileW) * cv.bg_pitch;
+        if (xx < tw) {
 #pragma unroll
-    for (int k = 0; k < kTileW * kTileH / kThreads; ++k) {
-        const int i = threadIdx.x + k * kThreads;
-        const int yy = i / kTileW, xx = i - yy * kTileW;
-        if (yy < th && xx < tw) {
-            if (cv.bg)
-                cp_async4(ctile + yy * kCtPitch + xx, cv.bg + (int64_t)(ty0 + yy) * cv.bg_pitch + (int64_t)(tx0 + xx) * 4);
-            else
-                ctile[yy * kCtPitch + xx] = cv.solid;
+            for (int k = 0; k < kTileH * kTileW / kThreads; ++k) {
+                if (y0 + k * (kThreads / kTileW) < th) {
+                    if (cv.bg) cp_async4(d, g); else *d = cv.solid;
+                }
+                g += gstep;
+                d += (kThreads / kTileW) * kCtPitch;
+            }
         }
     }
     __syncthreads();
     const DevPlacementT *desc = reinterpret_cast<const DevPlacementT *>(desc_words);
-    // which cached placements touch this tile: one ballot per warp of 32 descriptors
-    if (threadIdx.x < kDescCache) {
-        bool hit = false;
-        if ((int)threadIdx.x < n_cached) {
-            const DevPlacementT &d = desc[threadIdx.x];
-            hit = max(tx0, d.x) < min(tx1, d.x + d.w) && max(ty0, d.y) < min(ty1, d.y + d.h);
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, hit);
-        if ((threadIdx.x & 31) == 0) hit_mask[threadIdx.x >> 5] = m;
-    }
-    __syncthreads();
+    if (threadIdx.x == 0) mbar_init(&tma_bar, 1);
+    uint32_t tma_phase = 0;  // parity of the next TMA completion to wait for
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // ---- z-order walk over the placements that touch the tile ----
-    for (int pi = 0; pi < cv.count; ++pi) {
-        const DevPlacementT *pp;
-        if (pi < kDescCache) {
-            const uint32_t m = hit_mask[pi >> 5] >> (pi & 31);
-            if (m == 0u) {  // nothing left in this group of 32
-                pi |= 31;
+    // Geometry of a resampled placement on this tile; all threads compute it (cheap, no memory).
+    struct Geo {
+        int ix0, iy0, two, tho, ox0, oy0, cw0, rw0, NRQ;
+    };
+    auto geometry = [&](const DevPlacementT &d) {
+        Geo g;
+        g.ix0 = max(tx0, d.x);
+        g.iy0 = max(ty0, d.y);
+        const int ix1 = min(tx1, d.x + d.w), iy1 = min(ty1, d.y + d.h);
+        g.two = ix1 - g.ix0;
+        g.tho = iy1 - g.iy0;
+        g.ox0 = g.ix0 - d.x;
+        g.oy0 = g.iy0 - d.y;
+        g.cw0 = first_tap(g.ox0, d.scale_x, d.support_x) >> 2;
+        g.rw0 = first_tap(g.oy0, d.scale_y, d.support_y) >> 2;
+        g.NRQ = (first_tap(iy1 - 1 - d.y, d.scale_y, d.support_y) >> 2) + d.nwy - g.rw0;
+        return g;
+    };
+    // one elected thread starts the TMA of placement `d`'s source patch into P
+    auto issue_patch = [&](const DevPlacementT &d) {
+        const Geo g = geometry(d);
+        mbar_expect_tx(&tma_bar, (uint32_t)d.pbw * (uint32_t)d.nrbox * 4u);
+        tma_load_2d(P, d.tmap, 4 * g.cw0, 4 * g.rw0, &tma_bar);
+    };
+
+    // ---- z-order walk, kDescCache placements at a time ----
+    for (int group = 0; group < cv.count; group += kDescCache) {
+        const int n_cached = min(cv.count - group, kDescCache);
+        if (group > 0) {
+            __syncthreads();  // everyone is done with the previous group's descriptors
+            const uint32_t *g = reinterpret_cast<const uint32_t *>(placements + cv.first + group);
+            for (int i = threadIdx.x; i < n_cached * kDescWords; i += kThreads) desc_words[i] = __ldg(g + i);
+            __syncthreads();
+        }
+        // which cached placements touch this tile -> ordered hit list
+        if (threadIdx.x < kDescCache) {
+            bool hit = false;
+            if ((int)threadIdx.x < n_cached) {
+                const DevPlacementT &d = desc[threadIdx.x];
+                hit = max(tx0, d.x) < min(tx1, d.x + d.w) && max(ty0, d.y) < min(ty1, d.y + d.h);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) hit_mask[warp] = m;
+        }
+        __syncthreads();
+        if (threadIdx.x < kDescCache) {
+            const uint32_t m0 = hit_mask[0], m1 = hit_mask[1];
+            const uint32_t mine = warp == 0 ? m0 : m1;
+            if ((mine >> lane) & 1u)
+                hit_list[(warp == 0 ? 0 : __popc(m0)) + __popc(mine & ((1u << lane) - 1u))] = (uint8_t)threadIdx.x;
+        }
+        const int n_hits = __popc(hit_mask[0]) + __popc(hit_mask[1]);
+        __syncthreads();
+        // first resampled placement of the group: start its TMA now
+        int next_res = 0;
+        while (next_res < n_hits && desc[hit_list[next_res]].mode == 0) ++next_res;
+        if (next_res < n_hits && threadIdx.x == 0) issue_patch(desc[hit_list[next_res]]);
+
+        for (int k = 0; k < n_hits; ++k) {
+            const DevPlacementT &d = desc[hit_list[k]];
+            if (d.mode == 0) {
+                // identity-size placement: plain over straight from the cutout
+                const int ix0 = max(tx0, d.x), iy0 = max(ty0, d.y);
+                const int two = min(tx1, d.x + d.w) - ix0, tho = min(ty1, d.y + d.h) - iy0;
+                cp_async_wait_all();
+                __syncthreads();
+                const int xx = threadIdx.x & (kTileW - 1);
+                if (xx < two) {
+                    for (int yy = threadIdx.x / kTileW; yy < tho; yy += kThreads / kTileW) {
+                        const uint32_t s = ld_px(d.src, (int64_t)(iy0 + yy - d.y) * d.src_pitch + (int64_t)(ix0 + xx - d.x) * 4);
+                        uint32_t *c = ctile + (iy0 + yy - ty0) * kCtPitch + (ix0 + xx - tx0);
+                        *c = over_px(*c, s);
+                    }
+                }
+                __syncthreads();
                 continue;
             }
-            pi += __ffs((int)m) - 1;
-            pp = desc + pi;
-        } else {
-            pp = placements + cv.first + pi;  // beyond the cache: straight from global memory
-        }
-        const int px = pp->x, py = pp->y, pw = pp->w, ph = pp->h;
-        const int ix0 = max(tx0, px), iy0 = max(ty0, py);
-        const int ix1 = min(tx1, px + pw), iy1 = min(ty1, py + ph);
-        if (ix0 >= ix1 || iy0 >= iy1) continue;  // uniform across the CTA
-        const int two = ix1 - ix0, tho = iy1 - iy0;
-        const uint8_t *src = pp->src;
-        const int spitch = pp->src_pitch;
-        if (pp->mode == 0) {
-            // identity-size placement: plain over straight from the cutout
-            cp_async_wait_all();
-            __syncthreads();
-            for (int i = threadIdx.x; i < two * tho; i += kThreads) {
-                const int yy = i / two, xx = i - yy * two;
-                const uint32_t s = ld_px(src, (int64_t)(iy0 + yy - py) * spitch + (int64_t)(ix0 + xx - px) * 4);
-                uint32_t *d = ctile + (iy0 + yy - ty0) * kCtPitch + (ix0 + xx - tx0);
-                *d = over_px(*d, s);
+            const Geo g = geometry(d);
+            const int IPW = g.NRQ | 1;
+            const int iplane_stride = kTileW * IPW;
+            const bool fits = d.pbw * d.nrbox <= patch_words && 4 * iplane_stride <= inter_words && 4 * g.NRQ <= d.nrbox;
+            if (!fits && threadIdx.x == 0) atomicOr(status, kStatusPatchOverflow);  // host sizing bug: flagged
+            // coefficient rows -> L1 while the patch is in flight
+            if (warp < 2 && warp * 32 + lane < g.two) prefetch_coeffs(d.plx, d.nwx, d.w, g.ox0 + warp * 32 + lane);
+            if (warp == 2 && lane < g.tho) prefetch_coeffs(d.ply, d.nwy, d.h, g.oy0 + lane);
+            mbar_wait(&tma_bar, tma_phase);  // source patch has landed in P
+            tma_phase ^= 1u;
+            if (fits) {
+                if (d.nwx == 3)
+                    tile_hpass<3>(P, d.pbw, I, iplane_stride, IPW, g.NRQ, g.cw0, g.ox0, g.two, d.scale_x, d.support_x, d.plx, d.w);
+                else if (d.nwx == 4)
+                    tile_hpass<4>(P, d.pbw, I, iplane_stride, IPW, g.NRQ, g.cw0, g.ox0, g.two, d.scale_x, d.support_x, d.plx, d.w);
+                else
+                    tile_hpass<5>(P, d.pbw, I, iplane_stride, IPW, g.NRQ, g.cw0, g.ox0, g.two, d.scale_x, d.support_x, d.plx, d.w);
+            }
+            cp_async_wait_all();  // background tile (no-op after the first over)
+            __syncthreads();      // H pass done: P is free, I is complete
+            // next resampled placement: its patch streams in while this one runs its V pass
+            next_res = k + 1;
+            while (next_res < n_hits && desc[hit_list[next_res]].mode == 0) ++next_res;
+            if (next_res < n_hits && threadIdx.x == 0) issue_patch(desc[hit_list[next_res]]);
+            if (fits) {
+                if (d.nwy == 3)
+                    tile_vpass_over<3>(I, iplane_stride, IPW, ctile, g.rw0, g.oy0, g.tho, g.two, g.ix0 - tx0, g.iy0 - ty0, d.scale_y, d.support_y, d.ply, d.h);
+                else if (d.nwy == 4)
+                    tile_vpass_over<4>(I, iplane_stride, IPW, ctile, g.rw0, g.oy0, g.tho, g.two, g.ix0 - tx0, g.iy0 - ty0, d.scale_y, d.support_y, d.ply, d.h);
+                else
+                    tile_vpass_over<5>(I, iplane_stride, IPW, ctile, g.rw0, g.oy0, g.tho, g.two, g.ix0 - tx0, g.iy0 - ty0, d.scale_y, d.support_y, d.ply, d.h);
             }
             __syncthreads();
-            continue;
         }
-        const uint32_t *plx = pp->plx, *ply = pp->ply;
-        const int nwx = pp->nwx, nwy = pp->nwy;
-        const double scx = pp->scale_x, spx = pp->support_x, scy = pp->scale_y, spy = pp->support_y;
-        const int ox0 = ix0 - px, ox1 = ix1 - px, oy0 = iy0 - py, oy1 = iy1 - py;
-        const int cw0 = first_tap(ox0, scx, spx) >> 2, cw1 = (first_tap(ox1 - 1, scx, spx) >> 2) + nwx;
-        const int rw0 = first_tap(oy0, scy, spy) >> 2, rw1 = (first_tap(oy1 - 1, scy, spy) >> 2) + nwy;
-        {   // coefficient rows -> L1 while the patch is staged
-            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-            if (warp < 2 && warp * 32 + lane < two) prefetch_coeffs(plx, nwx, pw, ox0 + warp * 32 + lane);
-            if (warp == 2 && lane < tho) prefetch_coeffs(ply, nwy, ph, oy0 + lane);
-        }
-        const int NCW = cw1 - cw0, NRQ = rw1 - rw0, NR = 4 * NRQ;
-        const int IPW = NRQ | 1;
-        const int plane_stride = NR * NCW, iplane_stride = kTileW * IPW;
-        if (4 * plane_stride > patch_words || 4 * iplane_stride > inter_words) {
-            if (threadIdx.x == 0)
-                atomicOr(status, 4 * plane_stride > patch_words ? kStatusPatchOverflow : kStatusInterOverflow);
-            continue;  // host sizing bug: flagged, never silently wrong
-        }
-        stage_patch(P, plane_stride, NR, NCW, src, spitch, pp->sw, pp->sh, rw0, cw0, pp->vec_ok != 0);
-        __syncthreads();
-        if (nwx == 3)
-            tile_hpass<3>(P, plane_stride, NCW, I, iplane_stride, IPW, NRQ, cw0, ox0, two, scx, spx, plx, pw);
-        else if (nwx == 4)
-            tile_hpass<4>(P, plane_stride, NCW, I, iplane_stride, IPW, NRQ, cw0, ox0, two, scx, spx, plx, pw);
-        else
-            tile_hpass<5>(P, plane_stride, NCW, I, iplane_stride, IPW, NRQ, cw0, ox0, two, scx, spx, plx, pw);
-        cp_async_wait_all();  // background tile (no-op after the first placement)
-        __syncthreads();
-        if (nwy == 3)
-            tile_vpass_over<3>(I, iplane_stride, IPW, ctile, rw0, oy0, tho, two, ix0 - tx0, iy0 - ty0, scy, spy, ply, ph);
-        else if (nwy == 4)
-            tile_vpass_over<4>(I, iplane_stride, IPW, ctile, rw0, oy0, tho, two, ix0 - tx0, iy0 - ty0, scy, spy, ply, ph);
-        else
-            tile_vpass_over<5>(I, iplane_stride, IPW, ctile, rw0, oy0, tho, two, ix0 - tx0, iy0 - ty0, scy, spy, ply, ph);
-        __syncthreads();
     }
 
     // ---- write the tile once ----
     cp_async_wait_all();
     __syncthreads();
-    for (int i = threadIdx.x; i < kTileW * kTileH; i += kThreads) {
-        const int yy = i / kTileW, xx = i - yy * kTileW;
-        if (yy < th && xx < tw)
-            *reinterpret_cast<uint32_t *>(cv.out + (int64_t)(ty0 + yy) * cv.out_pitch + (int64_t)(tx0 + xx) * 4) =
-                ctile[yy * kCtPitch + xx];
+    if (tw == kTileW && ((reinterpret_cast<uintptr_t>(cv.out) | (uintptr_t)cv.out_pitch) & 15u) == 0) {
+        // full-width tile, 16-byte aligned rows: one 128-bit store per 4 pixels
+        const int x4 = (threadIdx.x & 15) * 4, y0 = threadIdx.x >> 4;  // 16 rows per sweep
+        uint8_t *g = cv.out + (int64_t)(ty0 + y0) * cv.out_pitch + (int64_t)(tx0 + x4) * 4;
+        const uint32_t *c = ctile + y0 * kCtPitch + x4;
+#pragma unroll
+        for (int k = 0; k < kTileH / 16; ++k) {
+            if (y0 + 16 * k < th)
+                *reinterpret_cast<uint4 *>(g) = make_uint4(c[0], c[1], c[2], c[3]);
+            g += 16 * cv.out_pitch;
+            c += 16 * kCtPitch;
+        }
+    } else {
+        const int xx = threadIdx.x & (kTileW - 1);
+        if (xx < tw)
+            for (int yy = threadIdx.x / kTileW; yy < th; yy += kThreads / kTileW)
+                *reinterpret_cast<uint32_t *>(cv.out + (int64_t)(ty0 + yy) * cv.out_pitch + (int64_t)(tx0 + xx) * 4) =
+                    ctile[yy * kCtPitch + xx];
     }
 }
 
