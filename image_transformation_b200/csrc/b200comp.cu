@@ -696,7 +696,9 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         int64_t patch = 0, inter = 0;
         int ncw = 0, nrq = 0;
         if (fused) {
-            ncw = words_bound(p.sw, p.w, kTileW, nwx);
+            // TMA: the box must start on a 16-byte boundary of the plane row and span a 16-byte multiple,
+            // so the kernel aligns the first word down to a multiple of 4 (+3 words of slack)
+            ncw = (words_bound(p.sw, p.w, kTileW, nwx) + 3 + 3) & ~3;
             nrq = words_bound(p.sh, p.h, kTileH, nwy);
             patch = (int64_t)4 * (4 * nrq) * ncw;          // TMA box: rows x (words x 4 channels)
             inter = (int64_t)4 * kTileW * (nrq | 1);       // 4 channel planes x columns x row-quads
@@ -810,10 +812,10 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
                 pd.src_pitch = p.src_pitch;
                 pd.sw = p.sw;
                 pd.sh = p.sh;
-                pd.w4 = (p.sw + 3) / 4;
+                pd.w4p = ((p.sw + 3) / 4 + 3) & ~3;
                 pd.vec_ok = ((reinterpret_cast<uintptr_t>(p.src) & 15u) == 0 && (p.src_pitch & 15) == 0) ? 1 : 0;
-                CUDA_TRY(dev_alloc((void **)&pd.dst, (size_t)pd.w4 * 16 * p.sh));
-                max_words = std::max<int64_t>(max_words, (int64_t)pd.w4 * p.sh);
+                CUDA_TRY(dev_alloc((void **)&pd.dst, (size_t)pd.w4p * 16 * p.sh));
+                max_words = std::max<int64_t>(max_words, (int64_t)pd.w4p * p.sh);
                 it = prep_index.emplace(key, (int)hprep.size()).first;
                 hprep.push_back(pd);
             }
@@ -821,11 +823,11 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             EncodeTiledFn enc = encode_tiled_fn();
             if (!enc) return fail(B200COMP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
             CUtensorMap tm;
-            const cuuint64_t gdim[2] = {(cuuint64_t)pd.w4 * 4, (cuuint64_t)pd.sh};
-            const cuuint64_t gstride[1] = {(cuuint64_t)pd.w4 * 16};
-            const cuuint32_t box[2] = {(cuuint32_t)hp[i].pbw, (cuuint32_t)hp[i].nrbox};
-            const cuuint32_t estride[2] = {1, 1};
-            const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, pd.dst, gdim, gstride, box, estride,
+            const cuuint64_t gdim[3] = {(cuuint64_t)pd.w4p, 4, (cuuint64_t)pd.sh};
+            const cuuint64_t gstride[2] = {(cuuint64_t)pd.w4p * 4, (cuuint64_t)pd.w4p * 16};
+            const cuuint32_t box[3] = {(cuuint32_t)hp[i].pbw / 4, 4, (cuuint32_t)hp[i].nrbox};
+            const cuuint32_t estride[3] = {1, 1, 1};
+            const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, pd.dst, gdim, gstride, box, estride,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS)

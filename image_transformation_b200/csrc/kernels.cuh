@@ -24,7 +24,7 @@ static_assert(sizeof(DevCanvas) == 72, "DevCanvas layout");
 
 constexpr int kTileW = 64;
 constexpr int kTileH = 32;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;  // 12 warps per CTA, two CTAs per SM (register-limited at 85 / thread)
 constexpr int kWarps = kThreads / 32;
 constexpr int kCtPitch = kTileW + 1;  // odd pitch: row-per-lane accesses hit distinct banks
 constexpr int kPrecisionBits = 22;

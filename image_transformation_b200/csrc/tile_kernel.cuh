@@ -57,25 +57,31 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // ---- prepare: RGBA cutout -> premultiplied, channel-planar words --------------------------------
 // One launch per plan run converts every distinct cutout the tile kernel resamples into the layout
-// its dp4a passes consume: for each row, for each group of 4 pixels, 16 bytes = (R4, G4, B4, A4)
-// with byte k of each word = pixel 4*g+k, colours premultiplied (Convert.c rgbA2rgba).  The tile
-// kernel then fetches source patches with TMA (cp.async.bulk.tensor) and does no per-pixel work
-// before the horizontal pass.  Pixels past the row end are zero.
+// its dp4a passes consume: every row becomes four channel planes of w4p words, byte k of word g =
+// pixel 4*g+k, colours premultiplied (Convert.c rgbA2rgba); w4p = words per plane, padded to a
+// multiple of 4 so plane and row strides are 16-byte multiples (a TMA requirement).  The tile kernel
+// then fetches a (words x 4 planes x rows) box per placement with ONE cp.async.bulk.tensor.3d and
+// does no per-pixel work before the horizontal pass.  Pixels past the row end are zero.
 struct PrepDesc {
     const uint8_t *src;
-    uint4 *dst;
+    uint32_t *dst;   // [sh][4][w4p]
     int64_t src_pitch;
     int32_t sw, sh;
-    int32_t w4;      // 4-pixel groups per row
+    int32_t w4p;     // words per channel plane of a row (multiple of 4)
     int32_t vec_ok;  // src 16-byte aligned with pitch % 16 == 0
 };
 
 __global__ void __launch_bounds__(256) prepare_cutouts_kernel(const PrepDesc *__restrict__ descs) {
     const PrepDesc d = descs[blockIdx.y];
-    const int64_t total = (int64_t)d.sh * d.w4;
+    const int64_t total = (int64_t)d.sh * d.w4p;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int r = (int)(i / d.w4), g = (int)(i - (int64_t)r * d.w4);
+        const int r = (int)(i / d.w4p), g = (int)(i - (int64_t)r * d.w4p);
         const int gx = 4 * g;
+        uint32_t *o = d.dst + ((int64_t)r * 4) * d.w4p + g;
+        if (gx >= d.sw) {  // padding words
+            o[0] = 0u; o[d.w4p] = 0u; o[2 * d.w4p] = 0u; o[3 * d.w4p] = 0u;
+            continue;
+        }
         const uint8_t *rowp = d.src + (int64_t)r * d.src_pitch + (int64_t)gx * 4;
         uint32_t p0, p1 = 0u, p2 = 0u, p3 = 0u;
         if (d.vec_ok && gx + 3 < d.sw) {
@@ -96,7 +102,7 @@ __global__ void __launch_bounds__(256) prepare_cutouts_kernel(const PrepDesc *__
         } else {
             transpose4(premultiply_px(p0), premultiply_px(p1), premultiply_px(p2), premultiply_px(p3), R, G, B, A);
         }
-        d.dst[i] = make_uint4(R, G, B, A);
+        o[0] = R; o[d.w4p] = G; o[2 * d.w4p] = B; o[3 * d.w4p] = A;
     }
 }
 
@@ -120,12 +126,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// 2-D tile of the prepared cutout -> shared memory; completion is signalled on `bar`
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tmap, int x, int y, uint64_t *bar) {
+// (words x 4 channel planes x rows) box of the prepared cutout -> shared memory; completion on `bar`
+__device__ __forceinline__ void tma_load_patch(void *smem_dst, const void *tmap, int word, int row, uint64_t *bar) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the buffer are done
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(word), "r"(0), "r"(row), "r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -138,7 +144,7 @@ __device__ __forceinline__ void prefetch_coeffs(const uint32_t *__restrict__ pl,
 // ---- H pass ---------------------------------------------------------------------------------
 // I[c][jj][rq]: plane c at I + c*iplane_stride, column pitch IPW words (odd), byte k of word rq =
 // intermediate row 4*rq+k (relative to source row 4*rw0).
-// P[r][4*wx + c]: exactly the TMA box (row pitch PBW words): word wx of channel c of patch row r.
+// P[r][c][wx]: exactly the 3-D TMA box (row pitch PBW words, channel plane pitch PBW/4 words).
 template <int NW>
 __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int PBW,
                                            uint32_t *__restrict__ I, int iplane_stride, int IPW, int NRQ, int cw0,
@@ -163,14 +169,14 @@ __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int P
         uint32_t o[4];
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
-            const uint32_t *row = P + (rq * 4 + rr) * PBW + 4 * wbase;
+            const uint32_t *row = P + (rq * 4 + rr) * PBW + wbase;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t a0 = 1u << (kPrecisionBits - 1), a1 = 0u;  // rounding term rides in the low plane
                 int32_t a2 = 0;
 #pragma unroll
                 for (int i = 0; i < NW; ++i) {
-                    const uint32_t wd = row[4 * i + c];
+                    const uint32_t wd = row[c * (PBW >> 2) + i];
                     a0 = dp4a_uu(wd, k0[i], a0);
                     a1 = dp4a_uu(wd, k1[i], a1);
                     a2 = dp4a_us(wd, k2[i], a2);
@@ -238,7 +244,7 @@ struct DevPlacementT {
     const uint8_t *src;    // mode 0: w x h overlay composited as is (raw RGBA)
     const uint32_t *plx;   // [3*nwx][w] coefficient byte planes of the horizontal pass
     const uint32_t *ply;   // [3*nwy][h] vertical pass
-    const void *tmap;      // mode 1: CUtensorMap over the prepared cutout, box = pbw x nrbox words
+    const void *tmap;      // mode 1: CUtensorMap over the prepared cutout, box = (pbw/4 words, 4 planes, nrbox rows)
     double scale_x, support_x;  // sw / w and 3 * max(1, scale): exactly the host builder's doubles
     double scale_y, support_y;
     int32_t src_pitch;     // bytes (mode 0)
@@ -289,7 +295,7 @@ composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacemen
         const int64_t gstep = (int64_t)(kThreads / kTileW) * cv.bg_pitch;
         if (xx < tw) {
 #pragma unroll
-            for (int k = 0; k < kTileH * kTileW / kThreads; ++k) {
+            for (int k = 0; k < (kTileH + kThreads / kTileW - 1) / (kThreads / kTileW); ++k) {
                 if (y0 + k * (kThreads / kTileW) < th) {
                     if (cv.bg) cp_async4(d, g); else *d = cv.solid;
                 }
@@ -317,7 +323,7 @@ composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacemen
         g.tho = iy1 - g.iy0;
         g.ox0 = g.ix0 - d.x;
         g.oy0 = g.iy0 - d.y;
-        g.cw0 = first_tap(g.ox0, d.scale_x, d.support_x) >> 2;
+        g.cw0 = (first_tap(g.ox0, d.scale_x, d.support_x) >> 2) & ~3;  // TMA boxes start on 16-byte boundaries
         g.rw0 = first_tap(g.oy0, d.scale_y, d.support_y) >> 2;
         g.NRQ = (first_tap(iy1 - 1 - d.y, d.scale_y, d.support_y) >> 2) + d.nwy - g.rw0;
         return g;
@@ -326,7 +332,7 @@ composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacemen
     auto issue_patch = [&](const DevPlacementT &d) {
         const Geo g = geometry(d);
         mbar_expect_tx(&tma_bar, (uint32_t)d.pbw * (uint32_t)d.nrbox * 4u);
-        tma_load_2d(P, d.tmap, 4 * g.cw0, 4 * g.rw0, &tma_bar);
+        tma_load_patch(P, d.tmap, g.cw0, 4 * g.rw0, &tma_bar);
     };
 
     // ---- z-order walk, kDescCache placements at a time ----
@@ -422,15 +428,16 @@ composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacemen
     __syncthreads();
     if (tw == kTileW && ((reinterpret_cast<uintptr_t>(cv.out) | (uintptr_t)cv.out_pitch) & 15u) == 0) {
         // full-width tile, 16-byte aligned rows: one 128-bit store per 4 pixels
-        const int x4 = (threadIdx.x & 15) * 4, y0 = threadIdx.x >> 4;  // 16 rows per sweep
+        constexpr int kRows = kThreads / 16;  // rows per sweep
+        const int x4 = (threadIdx.x & 15) * 4, y0 = threadIdx.x >> 4;
         uint8_t *g = cv.out + (int64_t)(ty0 + y0) * cv.out_pitch + (int64_t)(tx0 + x4) * 4;
         const uint32_t *c = ctile + y0 * kCtPitch + x4;
 #pragma unroll
-        for (int k = 0; k < kTileH / 16; ++k) {
-            if (y0 + 16 * k < th)
+        for (int k = 0; k < (kTileH + kRows - 1) / kRows; ++k) {
+            if (y0 + kRows * k < th)
                 *reinterpret_cast<uint4 *>(g) = make_uint4(c[0], c[1], c[2], c[3]);
-            g += 16 * cv.out_pitch;
-            c += 16 * kCtPitch;
+            g += (int64_t)kRows * cv.out_pitch;
+            c += kRows * kCtPitch;
         }
     } else {
         const int xx = threadIdx.x & (kTileW - 1);

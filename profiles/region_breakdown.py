@@ -33,10 +33,12 @@ def main():
     def find(s):
         return next(i + 1 for i, l in enumerate(src) if s in l)
 
-    marks = [(find("void stage_store("), "stage"), (find("void prefetch_l1"), "prefetch"),
+    marks = [(find("void prefetch_l1"), "prefetch"),
              (find("void tile_hpass("), "hpass"), (find("void tile_vpass_over("), "vpass"),
-             (find("struct DevPlacementT"), "main:setup"), (find("z-order walk over"), "main:loop+identity"),
-             (find("const uint32_t *plx = pp->plx"), "main:resample-glue"), (find("write the tile once"), "main:store")]
+             (find("struct DevPlacementT"), "main:setup"), (find("z-order walk, kDescCache"), "main:hit list"),
+             (find("identity-size placement: plain over"), "main:identity over"),
+             (find("const Geo g = geometry(d);\n            const int IPW") if False else find("const int IPW = g.NRQ | 1;"), "main:resample glue (TMA wait, syncs)"),
+             (find("write the tile once"), "main:store")]
 
     def region(f, ln):
         if f != cuh.split("/")[-1] or ln < marks[0][0]:
