@@ -472,6 +472,8 @@ struct b200comp_plan {
     };
     std::vector<Pre> pre;
     PrepDesc *d_prep = nullptr;  // distinct cutouts the tile kernel resamples (prepared every run)
+    uint32_t *d_flags = nullptr; // alpha summaries of the prepared cutouts
+    size_t flag_bytes = 0;
     int n_prep = 0;
     int prep_blocks_x = 1;
     std::vector<void *> owned;  // device allocations freed with the plan
@@ -799,6 +801,9 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         std::vector<PrepDesc> hprep;
         std::vector<CUtensorMap> hmaps;
         std::vector<int> map_of((size_t)std::max(1, n_placements), -1);
+        std::vector<int> prep_of((size_t)std::max(1, n_placements), -1);
+        std::vector<int64_t> flag_off;
+        int64_t flag_words = 0;
         int64_t max_words = 1;
         for (int i = 0; i < n_placements; ++i) {
             if (hp[i].mode != 1) continue;
@@ -815,6 +820,8 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
                 pd.w4p = ((p.sw + 3) / 4 + 3) & ~3;
                 pd.vec_ok = ((reinterpret_cast<uintptr_t>(p.src) & 15u) == 0 && (p.src_pitch & 15) == 0) ? 1 : 0;
                 CUDA_TRY(dev_alloc((void **)&pd.dst, (size_t)pd.w4p * 16 * p.sh));
+                flag_off.push_back(flag_words);
+                flag_words += (int64_t)((p.sh + 3) / 4) * (pd.w4p / 4);
                 max_words = std::max<int64_t>(max_words, (int64_t)pd.w4p * p.sh);
                 it = prep_index.emplace(key, (int)hprep.size()).first;
                 hprep.push_back(pd);
@@ -833,19 +840,29 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             if (r != CUDA_SUCCESS)
                 return fail(B200COMP_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for placement " + std::to_string(i));
             map_of[i] = (int)hmaps.size();
+            prep_of[i] = it->second;
             hmaps.push_back(tm);
         }
         if (!hprep.empty()) {
             CUtensorMap *d_maps = nullptr;
             CUDA_TRY(dev_alloc((void **)&d_maps, hmaps.size() * sizeof(CUtensorMap)));
             CUDA_TRY(dev_alloc((void **)&plan->d_prep, hprep.size() * sizeof(PrepDesc)));
+            CUDA_TRY(dev_alloc((void **)&plan->d_flags, (size_t)flag_words * 4));
+            plan->flag_bytes = (size_t)flag_words * 4;
+            for (size_t j = 0; j < hprep.size(); ++j) hprep[j].flags = plan->d_flags + flag_off[j];
             CUDA_TRY(cudaMemcpyAsync(d_maps, hmaps.data(), hmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(plan->d_prep, hprep.data(), hprep.size() * sizeof(PrepDesc), cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaStreamSynchronize(st));  // hmaps / hprep are locals
             plan->n_prep = (int)hprep.size();
             plan->prep_blocks_x = (int)std::max<int64_t>(1, std::min<int64_t>((max_words + 255) / 256, 64));
             for (int i = 0; i < n_placements; ++i)
-                if (map_of[i] >= 0) hp[i].tmap = d_maps + map_of[i];
+                if (map_of[i] >= 0) {
+                    const PrepDesc &pd = hprep[(size_t)prep_of[i]];
+                    hp[i].tmap = d_maps + map_of[i];
+                    hp[i].flags = pd.flags;
+                    hp[i].wq = pd.w4p / 4;
+                    hp[i].sh4 = (pd.sh + 3) / 4;
+                }
         }
     }
     CUDA_TRY(cudaMemcpyAsync(plan->d_tables, ts.host.data(), tbytes, cudaMemcpyHostToDevice, st));
@@ -887,6 +904,7 @@ int b200comp_plan_run(b200comp_plan *plan, void *stream) {
     if (plan->n_prep > 0) {
         // premultiplied planar copies of the cutouts the tile kernel resamples (re-made every run, so
         // the plan never shows stale pixels if the caller rewrites a cutout between runs)
+        CUDA_TRY(cudaMemsetAsync(plan->d_flags, 0, plan->flag_bytes, st));
         for (int p0 = 0; p0 < plan->n_prep; p0 += 65535) {
             const int np = std::min(65535, plan->n_prep - p0);
             prepare_cutouts_kernel<<<dim3((unsigned)plan->prep_blocks_x, (unsigned)np), 256, 0, st>>>(plan->d_prep + p0);

@@ -64,11 +64,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // does no per-pixel work before the horizontal pass.  Pixels past the row end are zero.
 struct PrepDesc {
     const uint8_t *src;
-    uint32_t *dst;   // [sh][4][w4p]
+    uint32_t *dst;    // [sh][4][w4p]
+    uint32_t *flags;  // [ceil(sh/4)][w4p/4] alpha summary of each 4-row x 16-pixel block (zeroed before the launch):
+                      // bit 0 = some alpha != 0, bit 1 = some alpha != 255
     int64_t src_pitch;
     int32_t sw, sh;
-    int32_t w4p;     // words per channel plane of a row (multiple of 4)
-    int32_t vec_ok;  // src 16-byte aligned with pitch % 16 == 0
+    int32_t w4p;      // words per channel plane of a row (multiple of 4)
+    int32_t vec_ok;   // src 16-byte aligned with pitch % 16 == 0
 };
 
 __global__ void __launch_bounds__(256) prepare_cutouts_kernel(const PrepDesc *__restrict__ descs) {
@@ -103,6 +105,12 @@ __global__ void __launch_bounds__(256) prepare_cutouts_kernel(const PrepDesc *__
             transpose4(premultiply_px(p0), premultiply_px(p1), premultiply_px(p2), premultiply_px(p3), R, G, B, A);
         }
         o[0] = R; o[d.w4p] = G; o[2 * d.w4p] = B; o[3 * d.w4p] = A;
+        // alpha summary: lets the tile kernel skip fully transparent patches and the alpha plane of
+        // fully opaque ones (pixels past the row end count as neither)
+        const int nv = min(4, d.sw - gx);
+        const uint32_t a_all = nv < 4 ? (A | (0xffffffffu << (8 * nv))) : A;
+        const uint32_t bits = (A != 0u ? 1u : 0u) | (a_all != 0xffffffffu ? 2u : 0u);
+        if (bits) atomicOr(d.flags + (int64_t)(r >> 2) * (d.w4p >> 2) + (g >> 2), bits);
     }
 }
 
@@ -149,7 +157,9 @@ template <int NW>
 __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int PBW,
                                            uint32_t *__restrict__ I, int iplane_stride, int IPW, int NRQ, int cw0,
                                            int ox0, int two, double scale, double support,
-                                           const uint32_t *__restrict__ plx, int n_out) {
+                                           const uint32_t *__restrict__ plx, int n_out, int nch) {
+    // nch = 3 when every source alpha in the patch is 255: the alpha plane is then 255 after both passes
+    // (255 * sum(k) + 2^21 >> 22 == 255 because |sum(k) - 2^22| <= taps) and is not computed
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ncg = (two + 31) >> 5;  // 1 or 2 column groups of 32
     const int cg = warp % ncg;
@@ -172,6 +182,7 @@ __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int P
             const uint32_t *row = P + (rq * 4 + rr) * PBW + wbase;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
+                if (c == 3 && nch == 3) break;
                 uint32_t a0 = 1u << (kPrecisionBits - 1), a1 = 0u;  // rounding term rides in the low plane
                 int32_t a2 = 0;
 #pragma unroll
@@ -192,7 +203,7 @@ __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int P
         d[0] = o[0];
         d[iplane_stride] = o[1];
         d[2 * iplane_stride] = o[2];
-        d[3 * iplane_stride] = o[3];
+        if (nch == 4) d[3 * iplane_stride] = o[3];
     }
 }
 
@@ -201,7 +212,7 @@ template <int NW>
 __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, int iplane_stride, int IPW,
                                                 uint32_t *__restrict__ ctile, int rw0, int oy0, int tho, int two,
                                                 int tile_dx, int tile_dy, double scale, double support,
-                                                const uint32_t *__restrict__ ply, int n_out) {
+                                                const uint32_t *__restrict__ ply, int n_out, int nch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane >= tho) return;
     const int y = oy0 + lane;
@@ -217,8 +228,10 @@ __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, 
     for (int x = warp; x < two; x += kWarps) {
         const uint32_t *col = I + x * IPW + wbase;
         int32_t acc[4];
+        acc[3] = 255 << kPrecisionBits;  // opaque patch: alpha is exactly 255
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+            if (c == 3 && nch == 3) break;
             uint32_t a0 = 1u << (kPrecisionBits - 1), a1 = 0u;
             int32_t a2 = 0;
 #pragma unroll
@@ -245,6 +258,7 @@ struct DevPlacementT {
     const uint32_t *plx;   // [3*nwx][w] coefficient byte planes of the horizontal pass
     const uint32_t *ply;   // [3*nwy][h] vertical pass
     const void *tmap;      // mode 1: CUtensorMap over the prepared cutout, box = (pbw/4 words, 4 planes, nrbox rows)
+    const uint32_t *flags; // mode 1: alpha summary of the prepared cutout, [sh4][wq] (see PrepDesc)
     double scale_x, support_x;  // sw / w and 3 * max(1, scale): exactly the host builder's doubles
     double scale_y, support_y;
     int32_t src_pitch;     // bytes (mode 0)
@@ -254,8 +268,9 @@ struct DevPlacementT {
     int32_t mode;          // 0 = plain over, 1 = resample in the tile kernel
     int32_t pbw;           // TMA box width in words (= 4 * patch words per row)
     int32_t nrbox;         // TMA box height in rows (multiple of 4)
+    int32_t wq, sh4;       // alpha summary extent: blocks per row, block rows
 };
-static_assert(sizeof(DevPlacementT) == 112, "DevPlacementT layout");
+static_assert(sizeof(DevPlacementT) == 128, "DevPlacementT layout");
 
 constexpr int kDescCache = 64;  // placement descriptors cached in shared memory per CTA
 constexpr int kDescWords = sizeof(DevPlacementT) / 4;
@@ -272,6 +287,7 @@ composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacemen
     __shared__ uint32_t hit_mask[kDescCache / 32];
     __shared__ uint8_t hit_list[kDescCache];
     __shared__ __align__(8) uint64_t tma_bar;
+    __shared__ uint32_t alpha_bits[2];  // OR of the alpha summary over the current patch (double buffered)
 
     const DevCanvas cv = canvases[blockIdx.y];
     const int local = blockIdx.x;
@@ -306,13 +322,18 @@ composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacemen
     }
     __syncthreads();
     const DevPlacementT *desc = reinterpret_cast<const DevPlacementT *>(desc_words);
-    if (threadIdx.x == 0) mbar_init(&tma_bar, 1);
+    if (threadIdx.x == 0) {
+        mbar_init(&tma_bar, 1);
+        alpha_bits[0] = 0u;
+        alpha_bits[1] = 0u;
+    }
+    uint32_t n_res = 0;  // resampled placements seen so far (selects the alpha_bits slot)
     uint32_t tma_phase = 0;  // parity of the next TMA completion to wait for
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // Geometry of a resampled placement on this tile; all threads compute it (cheap, no memory).
     struct Geo {
-        int ix0, iy0, two, tho, ox0, oy0, cw0, rw0, NRQ;
+        int ix0, iy0, two, tho, ox0, oy0, cw0, rw0, NRQ, bq0, bq1;
     };
     auto geometry = [&](const DevPlacementT &d) {
         Geo g;
@@ -323,7 +344,11 @@ composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacemen
         g.tho = iy1 - g.iy0;
         g.ox0 = g.ix0 - d.x;
         g.oy0 = g.iy0 - d.y;
-        g.cw0 = (first_tap(g.ox0, d.scale_x, d.support_x) >> 2) & ~3;  // TMA boxes start on 16-byte boundaries
+        const int w_first = first_tap(g.ox0, d.scale_x, d.support_x) >> 2;
+        const int w_last = (first_tap(ix1 - 1 - d.x, d.scale_x, d.support_x) >> 2) + d.nwx - 1;
+        g.bq0 = w_first >> 2;                   // alpha summary blocks (4 words) the patch touches
+        g.bq1 = min(w_last >> 2, d.wq - 1);
+        g.cw0 = w_first & ~3;  // TMA boxes start on 16-byte boundaries
         g.rw0 = first_tap(g.oy0, d.scale_y, d.support_y) >> 2;
         g.NRQ = (first_tap(iy1 - 1 - d.y, d.scale_y, d.support_y) >> 2) + d.nwy - g.rw0;
         return g;
@@ -392,18 +417,44 @@ composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacemen
             const int iplane_stride = kTileW * IPW;
             const bool fits = d.pbw * d.nrbox <= patch_words && 4 * iplane_stride <= inter_words && 4 * g.NRQ <= d.nrbox;
             if (!fits && threadIdx.x == 0) atomicOr(status, kStatusPatchOverflow);  // host sizing bug: flagged
+            // alpha summary of the patch (global loads overlap the TMA already in flight)
+            {
+                const int nbw = g.bq1 - g.bq0 + 1;
+                const int rq1 = min(g.rw0 + g.NRQ, d.sh4);
+                const int nb = nbw * (rq1 - g.rw0);
+                uint32_t bits = 0u;
+                for (int i = threadIdx.x; i < nb; i += kThreads) {
+                    const int br = i / nbw, bc = i - br * nbw;
+                    bits |= __ldg(d.flags + (int64_t)(g.rw0 + br) * d.wq + g.bq0 + bc);
+                }
+                bits = __reduce_or_sync(0xffffffffu, bits);
+                if (lane == 0 && bits) atomicOr(&alpha_bits[n_res & 1u], bits);
+                if (threadIdx.x == 0) alpha_bits[(n_res + 1u) & 1u] = 0u;  // slot of the next resampled placement
+            }
             // coefficient rows -> L1 while the patch is in flight
             if (warp < 2 && warp * 32 + lane < g.two) prefetch_coeffs(d.plx, d.nwx, d.w, g.ox0 + warp * 32 + lane);
             if (warp == 2 && lane < g.tho) prefetch_coeffs(d.ply, d.nwy, d.h, g.oy0 + lane);
             mbar_wait(&tma_bar, tma_phase);  // source patch has landed in P
             tma_phase ^= 1u;
+            __syncthreads();  // alpha_bits complete; everyone has consumed this TMA phase
+            const uint32_t abits = alpha_bits[n_res & 1u];
+            ++n_res;
+            const bool transparent = (abits & 1u) == 0u;  // nothing but alpha 0: the canvas does not change
+            const int nch = (abits & 2u) ? 4 : 3;         // every alpha 255: skip the alpha plane
+            if (transparent) {
+                next_res = k + 1;
+                while (next_res < n_hits && desc[hit_list[next_res]].mode == 0) ++next_res;
+                if (next_res < n_hits && threadIdx.x == 0) issue_patch(desc[hit_list[next_res]]);
+                __syncthreads();  // everyone has read alpha_bits before its slot is recycled
+                continue;
+            }
             if (fits) {
                 if (d.nwx == 3)
-                    tile_hpass<3>(P, d.pbw, I, iplane_stride, IPW, g.NRQ, g.cw0, g.ox0, g.two, d.scale_x, d.support_x, d.plx, d.w);
+                    tile_hpass<3>(P, d.pbw, I, iplane_stride, IPW, g.NRQ, g.cw0, g.ox0, g.two, d.scale_x, d.support_x, d.plx, d.w, nch);
                 else if (d.nwx == 4)
-                    tile_hpass<4>(P, d.pbw, I, iplane_stride, IPW, g.NRQ, g.cw0, g.ox0, g.two, d.scale_x, d.support_x, d.plx, d.w);
+                    tile_hpass<4>(P, d.pbw, I, iplane_stride, IPW, g.NRQ, g.cw0, g.ox0, g.two, d.scale_x, d.support_x, d.plx, d.w, nch);
                 else
-                    tile_hpass<5>(P, d.pbw, I, iplane_stride, IPW, g.NRQ, g.cw0, g.ox0, g.two, d.scale_x, d.support_x, d.plx, d.w);
+                    tile_hpass<5>(P, d.pbw, I, iplane_stride, IPW, g.NRQ, g.cw0, g.ox0, g.two, d.scale_x, d.support_x, d.plx, d.w, nch);
             }
             cp_async_wait_all();  // background tile (no-op after the first over)
             __syncthreads();      // H pass done: P is free, I is complete
@@ -413,11 +464,11 @@ composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacemen
             if (next_res < n_hits && threadIdx.x == 0) issue_patch(desc[hit_list[next_res]]);
             if (fits) {
                 if (d.nwy == 3)
-                    tile_vpass_over<3>(I, iplane_stride, IPW, ctile, g.rw0, g.oy0, g.tho, g.two, g.ix0 - tx0, g.iy0 - ty0, d.scale_y, d.support_y, d.ply, d.h);
+                    tile_vpass_over<3>(I, iplane_stride, IPW, ctile, g.rw0, g.oy0, g.tho, g.two, g.ix0 - tx0, g.iy0 - ty0, d.scale_y, d.support_y, d.ply, d.h, nch);
                 else if (d.nwy == 4)
-                    tile_vpass_over<4>(I, iplane_stride, IPW, ctile, g.rw0, g.oy0, g.tho, g.two, g.ix0 - tx0, g.iy0 - ty0, d.scale_y, d.support_y, d.ply, d.h);
+                    tile_vpass_over<4>(I, iplane_stride, IPW, ctile, g.rw0, g.oy0, g.tho, g.two, g.ix0 - tx0, g.iy0 - ty0, d.scale_y, d.support_y, d.ply, d.h, nch);
                 else
-                    tile_vpass_over<5>(I, iplane_stride, IPW, ctile, g.rw0, g.oy0, g.tho, g.two, g.ix0 - tx0, g.iy0 - ty0, d.scale_y, d.support_y, d.ply, d.h);
+                    tile_vpass_over<5>(I, iplane_stride, IPW, ctile, g.rw0, g.oy0, g.tho, g.two, g.ix0 - tx0, g.iy0 - ty0, d.scale_y, d.support_y, d.ply, d.h, nch);
             }
             __syncthreads();
         }
