@@ -27,6 +27,18 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 METRIC = "composited_canvas_megapixels_per_s"
 UNIT = "MP/s"
 
@@ -229,7 +241,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -420,19 +432,26 @@ def run_b200(args):
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse_args()
+    # keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, torchrun notices) write
+    # to fd 1; route everything to stderr and keep a private handle to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1 and "RANK" not in os.environ:
         # convenience: `python bench.py --gpus N` re-launches itself under torchrun
         port = 29500 + os.getpid() % 2000
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        os.dup2(_REAL_STDOUT, 1)  # the child prints the JSON line itself
         raise SystemExit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args)

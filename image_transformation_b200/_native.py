@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(_PKG, "_lib", "libb200comp.so")
 EXPORTED = (
     "b200comp_abi_version", "b200comp_last_error", "b200comp_device_count", "b200comp_ksize",
     "b200comp_build_coeffs", "b200comp_resize_rgba_lanczos", "b200comp_resample_rgba", "b200comp_alpha_over",
-    "b200comp_plan_create", "b200comp_plan_run", "b200comp_plan_destroy", "b200comp_plan_info",
+    "b200comp_plan_create", "b200comp_plan_run", "b200comp_plan_prepare", "b200comp_plan_run_canvases",
+    "b200comp_plan_destroy", "b200comp_plan_info",
     "b200comp_plan_check", "b200comp_composite_batch", "b200comp_composite_batch_host",
     "b200comp_composite_host", "b200comp_host_alloc", "b200comp_host_free", "b200comp_masked_median_rgb",
     "b200comp_fill_rgba", "b200comp_fill_gradient", "b200comp_masked_median_rgb_host",
@@ -77,6 +78,8 @@ def _load() -> ctypes.CDLL:
     L.b200comp_alpha_over.argtypes = [vp, c_int, c_int, c_size_t, vp, c_int, c_int, c_size_t, c_int, c_int, vp]
     L.b200comp_plan_create.argtypes = [POINTER(Canvas), c_int, POINTER(Placement), c_int, c_int, vp, POINTER(vp)]
     L.b200comp_plan_run.argtypes = [vp, vp]
+    L.b200comp_plan_prepare.argtypes = [vp, vp]
+    L.b200comp_plan_run_canvases.argtypes = [vp, c_int, c_int, vp]
     L.b200comp_plan_destroy.argtypes = [vp]
     L.b200comp_plan_info.argtypes = [vp, POINTER(c_int64)]
     L.b200comp_plan_check.argtypes = [vp, vp]

@@ -891,8 +891,10 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     return 0;
 }
 
-int b200comp_plan_run(b200comp_plan *plan, void *stream) {
-    if (!plan) return fail(B200COMP_EINVAL, "plan_run: null plan");
+// Stage 1 of a run: everything the tile kernel reads besides the caller's buffers (pre-resampled
+// overlays for extreme scales, prepared cutouts + alpha summaries).
+int b200comp_plan_prepare(b200comp_plan *plan, void *stream) {
+    if (!plan) return fail(B200COMP_EINVAL, "plan_prepare: null plan");
     cudaStream_t st = S(stream);
     for (auto &pr : plan->pre) {
         const int32_t *t = plan->d_tables;
@@ -911,14 +913,29 @@ int b200comp_plan_run(b200comp_plan *plan, void *stream) {
         }
         CUDA_TRY(cudaGetLastError());
     }
+    return 0;
+}
+
+// Stage 2: the fused tile kernel over canvases [first, first + count).
+int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *stream) {
+    if (!plan) return fail(B200COMP_EINVAL, "plan_run_canvases: null plan");
+    if (first < 0 || count < 0 || (int64_t)first + count > plan->n_canvases)
+        return fail(B200COMP_EINVAL, "plan_run_canvases: canvas range out of bounds");
+    cudaStream_t st = S(stream);
     // grid.y is limited to 65535 canvases per launch
-    for (int c0 = 0; c0 < plan->n_canvases; c0 += 65535) {
-        const int nc = std::min(65535, plan->n_canvases - c0);
+    for (int c0 = first; c0 < first + count; c0 += 65535) {
+        const int nc = std::min(65535, first + count - c0);
         composite_tiles_kernel<<<dim3((unsigned)plan->max_tiles, (unsigned)nc), kThreads, plan->smem_bytes, st>>>(
             plan->d_canvases + c0, plan->d_placements, plan->patch_words, plan->inter_words, plan->d_status);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+int b200comp_plan_run(b200comp_plan *plan, void *stream) {
+    int rc = b200comp_plan_prepare(plan, stream);
+    if (rc) return rc;
+    return b200comp_plan_run_canvases(plan, 0, plan->n_canvases, stream);
 }
 
 int b200comp_plan_info(const b200comp_plan *plan, int64_t *info) {

@@ -42,20 +42,24 @@ int b200comp_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? 0 
 // internal: set the message returned by b200comp_last_error() (defined in b200comp.cu)
 int b200comp_set_error_(int code, const char *msg);
 
+// Pipelined host-buffer batch.  Canvases are processed in super-chunks (`8 * chunk_canvases`, double
+// buffered on the device); inside a super-chunk three streams form a copy-in / compute / copy-out
+// pipeline over sub-chunks of `chunk_canvases`, so both PCIe directions and the SMs work concurrently,
+// while a helper thread resolves the NEXT super-chunk's plan (coefficient tables on the host threads).
 int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvases,
                                   const b200comp_placement *placements, int n_placements, int n_host_threads,
                                   int chunk_canvases, int n_streams) {
+    (void)n_streams;  // kept for ABI stability: the pipeline always uses three streams
     if (n_canvases < 1 || !canvases || n_placements < 0 || (n_placements > 0 && !placements))
         return b200comp_set_error_(B200COMP_EINVAL, "composite_batch_host: empty batch or null arrays");
     int device = 0;
     if (cudaGetDevice(&device) != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, "no CUDA device");
     if (n_host_threads <= 0) n_host_threads = std::max(1u, std::thread::hardware_concurrency());
     if (chunk_canvases <= 0) chunk_canvases = 8;
-    if (n_streams <= 0) n_streams = 3;
-    const int n_chunks = (n_canvases + chunk_canvases - 1) / chunk_canvases;
-    n_streams = std::min(n_streams, n_chunks);
+    const int super_canvases = std::min(n_canvases, 8 * chunk_canvases);
+    const int n_super = (n_canvases + super_canvases - 1) / super_canvases;
 
-    // ---- cutouts: upload each distinct host cutout once, 16-byte aligned pitch ----
+    // ---- validate, size the staging buffers, find the distinct cutouts ----
     typedef std::tuple<const uint8_t *, int, int, int64_t> SrcKey;
     std::map<SrcKey, size_t> src_off;
     std::vector<SrcKey> src_order;
@@ -68,123 +72,180 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
         if (src_off.find(k) == src_off.end()) {
             src_off[k] = pool_bytes;
             src_order.push_back(k);
-            pool_bytes += align_up((size_t)p.sw * 4, 16) * p.sh;
-            pool_bytes = align_up(pool_bytes, 256);
+            pool_bytes = align_up(pool_bytes + align_up((size_t)p.sw * 4, 16) * p.sh, 256);
         }
     }
-    DevBuf pool;
+    size_t max_canvas_bytes = 0;
+    bool any_bg = false;
+    for (int c = 0; c < n_canvases; ++c) {
+        const b200comp_canvas &cv = canvases[c];
+        if (!cv.out || cv.W < 1 || cv.H < 1 || cv.out_pitch < (int64_t)cv.W * 4 || (cv.bg && cv.bg_pitch < (int64_t)cv.W * 4))
+            return b200comp_set_error_(B200COMP_EINVAL, "composite_batch_host: bad canvas");
+        if (cv.n_placements < 0 || cv.first_placement < 0 || (int64_t)cv.first_placement + cv.n_placements > n_placements)
+            return b200comp_set_error_(B200COMP_EINVAL, "composite_batch_host: placement range out of bounds");
+        max_canvas_bytes = std::max(max_canvas_bytes, align_up((size_t)cv.W * 4, 16) * cv.H);
+        any_bg |= cv.bg != nullptr;
+    }
+    max_canvas_bytes = align_up(max_canvas_bytes, 256);
+
+    // ---- device resources ----
+    const int n_buf = n_super > 1 ? 2 : 1;
+    DevBuf pool, d_out[2], d_bg[2];
     if (pool.alloc(pool_bytes) != cudaSuccess) return b200comp_set_error_(B200COMP_ENOMEM, "cutout pool allocation failed");
-    cudaStream_t s0;
-    if (cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking) != cudaSuccess)
+    for (int b = 0; b < n_buf; ++b)
+        if (d_out[b].alloc(max_canvas_bytes * super_canvases) != cudaSuccess ||
+            (any_bg && d_bg[b].alloc(max_canvas_bytes * super_canvases) != cudaSuccess))
+            return b200comp_set_error_(B200COMP_ENOMEM, "canvas staging allocation failed");
+    cudaStream_t s_in = nullptr, s_exec = nullptr, s_out = nullptr, s_plan = nullptr;
+    struct StreamGuard {
+        cudaStream_t *s[4];
+        ~StreamGuard() { for (auto p : s) if (*p) cudaStreamDestroy(*p); }
+    } sguard{{&s_in, &s_exec, &s_out, &s_plan}};
+    if (cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s_exec, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s_plan, cudaStreamNonBlocking) != cudaSuccess)
         return b200comp_set_error_(B200COMP_ECUDA, "stream creation failed");
+    const int max_sub = (super_canvases + chunk_canvases - 1) / chunk_canvases;
+    std::vector<cudaEvent_t> ev_in((size_t)max_sub), ev_exec((size_t)max_sub);
+    struct EventGuard {
+        std::vector<cudaEvent_t> *a, *b;
+        ~EventGuard() { for (auto e : *a) if (e) cudaEventDestroy(e); for (auto e : *b) if (e) cudaEventDestroy(e); }
+    } eguard{&ev_in, &ev_exec};
+    for (auto &e : ev_in) e = nullptr;
+    for (auto &e : ev_exec) e = nullptr;
+    cudaEvent_t ev_pool = nullptr, ev_done[2] = {nullptr, nullptr};
+    for (int i = 0; i < max_sub; ++i)
+        if (cudaEventCreateWithFlags(&ev_in[(size_t)i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_exec[(size_t)i], cudaEventDisableTiming) != cudaSuccess)
+            return b200comp_set_error_(B200COMP_ECUDA, "event creation failed");
+    cudaEventCreateWithFlags(&ev_pool, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_done[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_done[1], cudaEventDisableTiming);
+
+    // cutouts: each distinct host cutout once, 16-byte aligned pitch (copy-in stream)
     for (const SrcKey &k : src_order) {
         const int sw = std::get<1>(k), sh = std::get<2>(k);
         cudaMemcpy2DAsync((uint8_t *)pool.p + src_off[k], align_up((size_t)sw * 4, 16), std::get<0>(k),
-                          (size_t)std::get<3>(k), (size_t)sw * 4, sh, cudaMemcpyHostToDevice, s0);
+                          (size_t)std::get<3>(k), (size_t)sw * 4, sh, cudaMemcpyHostToDevice, s_in);
     }
-    cudaError_t e0 = cudaStreamSynchronize(s0);
-    cudaStreamDestroy(s0);
-    if (e0 != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, cudaGetErrorString(e0));
+    cudaEventRecord(ev_pool, s_in);
 
-    // ---- per-stream worker: chunks of canvases, bg H2D -> fused kernel -> out D2H ----
-    size_t max_canvas_bytes = 0;
-    for (int c = 0; c < n_canvases; ++c) {
-        if (!canvases[c].out || canvases[c].W < 1 || canvases[c].H < 1)
-            return b200comp_set_error_(B200COMP_EINVAL, "composite_batch_host: bad canvas");
-        max_canvas_bytes = std::max(max_canvas_bytes, align_up((size_t)canvases[c].W * 4, 16) * canvases[c].H);
-    }
-    max_canvas_bytes = align_up(max_canvas_bytes, 256);
-    std::atomic<int> next_chunk(0);
-    std::atomic<int> first_rc(0);
-    std::vector<std::string> errs((size_t)n_streams);
-    const int builder_threads = std::max(1, n_host_threads / n_streams);
-
-    auto worker = [&](int tid) {
-        auto bail = [&](int rc, const std::string &m) {
-            int expected = 0;
-            if (first_rc.compare_exchange_strong(expected, rc)) errs[(size_t)tid] = m;
-        };
-        if (cudaSetDevice(device) != cudaSuccess) return bail(B200COMP_ECUDA, "cudaSetDevice failed");
-        cudaStream_t st;
-        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return bail(B200COMP_ECUDA, "stream creation failed");
-        DevBuf d_out, d_bg;
-        bool any_bg = false;
-        for (int c = 0; c < n_canvases; ++c) any_bg |= canvases[c].bg != nullptr;
-        if (d_out.alloc(max_canvas_bytes * chunk_canvases) != cudaSuccess ||
-            (any_bg && d_bg.alloc(max_canvas_bytes * chunk_canvases) != cudaSuccess)) {
-            cudaStreamDestroy(st);
-            return bail(B200COMP_ENOMEM, "canvas staging allocation failed");
-        }
+    // ---- plan of one super-chunk (runs on the helper thread: host-side table building) ----
+    struct SuperPlan {
+        b200comp_plan *plan = nullptr;
         std::vector<b200comp_canvas> cc;
         std::vector<b200comp_placement> pp;
-        for (;;) {
-            const int chunk = next_chunk.fetch_add(1);
-            if (chunk >= n_chunks || first_rc.load() != 0) break;
-            const int c_lo = chunk * chunk_canvases, c_hi = std::min(n_canvases, c_lo + chunk_canvases);
-            cc.clear();
-            pp.clear();
-            for (int c = c_lo; c < c_hi; ++c) {
-                b200comp_canvas cv = canvases[c];
-                const size_t dp = align_up((size_t)cv.W * 4, 16);
-                uint8_t *o = (uint8_t *)d_out.p + (size_t)(c - c_lo) * max_canvas_bytes;
-                if (cv.bg) {
-                    uint8_t *b = (uint8_t *)d_bg.p + (size_t)(c - c_lo) * max_canvas_bytes;
-                    cudaMemcpy2DAsync(b, dp, cv.bg, (size_t)cv.bg_pitch, (size_t)cv.W * 4, cv.H, cudaMemcpyHostToDevice, st);
-                    cv.bg = b;
-                    cv.bg_pitch = (int64_t)dp;
-                }
-                cv.out = o;
-                cv.out_pitch = (int64_t)dp;
-                if (cv.n_placements < 0 || cv.first_placement < 0 || (int64_t)cv.first_placement + cv.n_placements > n_placements) {
-                    bail(B200COMP_EINVAL, "composite_batch_host: placement range out of bounds");
-                    break;
-                }
-                const int first = (int)pp.size();
-                for (int i = 0; i < cv.n_placements; ++i) {
-                    b200comp_placement p = placements[cv.first_placement + i];
-                    SrcKey k(p.src, p.sw, p.sh, p.src_pitch);
-                    p.src = (const uint8_t *)pool.p + src_off[k];
-                    p.src_pitch = (int64_t)align_up((size_t)p.sw * 4, 16);
-                    pp.push_back(p);
-                }
-                cv.first_placement = first;
-                cc.push_back(cv);
+        int rc = 0;
+        std::string err;
+    };
+    auto build_plan = [&](int si, SuperPlan *sp) {
+        cudaSetDevice(device);
+        const int c_lo = si * super_canvases, c_hi = std::min(n_canvases, c_lo + super_canvases);
+        const int buf = si % n_buf;
+        for (int c = c_lo; c < c_hi; ++c) {
+            b200comp_canvas cv = canvases[c];
+            const size_t dp = align_up((size_t)cv.W * 4, 16);
+            if (cv.bg) {
+                cv.bg = (const uint8_t *)d_bg[buf].p + (size_t)(c - c_lo) * max_canvas_bytes;
+                cv.bg_pitch = (int64_t)dp;
             }
-            if (first_rc.load() != 0) break;
-            b200comp_plan *plan = nullptr;
-            int rc = b200comp_plan_create(cc.data(), (int)cc.size(), pp.data(), (int)pp.size(), builder_threads, st, &plan);
-            if (!rc) rc = b200comp_plan_run(plan, st);
-            if (!rc) {
-                for (int c = c_lo; c < c_hi; ++c) {
-                    const b200comp_canvas &cv = canvases[c];
-                    cudaMemcpy2DAsync(cv.out, (size_t)cv.out_pitch, cc[(size_t)(c - c_lo)].out,
-                                      (size_t)cc[(size_t)(c - c_lo)].out_pitch, (size_t)cv.W * 4, cv.H,
-                                      cudaMemcpyDeviceToHost, st);
-                }
-                rc = b200comp_plan_check(plan, st);  // synchronises the stream
+            cv.out = (uint8_t *)d_out[buf].p + (size_t)(c - c_lo) * max_canvas_bytes;
+            cv.out_pitch = (int64_t)dp;
+            const int first = (int)sp->pp.size();
+            for (int i = 0; i < cv.n_placements; ++i) {
+                b200comp_placement p = placements[cv.first_placement + i];
+                SrcKey k(p.src, p.sw, p.sh, p.src_pitch);
+                p.src = (const uint8_t *)pool.p + src_off[k];
+                p.src_pitch = (int64_t)align_up((size_t)p.sw * 4, 16);
+                sp->pp.push_back(p);
             }
-            if (rc) bail(rc, b200comp_last_error());
-            if (plan) b200comp_plan_destroy(plan);
-            if (rc) break;
+            cv.first_placement = first;
+            sp->cc.push_back(cv);
         }
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) bail(B200COMP_ECUDA, cudaGetErrorString(e));
-        cudaStreamDestroy(st);
+        sp->rc = b200comp_plan_create(sp->cc.data(), (int)sp->cc.size(), sp->pp.data(), (int)sp->pp.size(),
+                                      n_host_threads, s_plan, &sp->plan);
+        if (sp->rc) sp->err = b200comp_last_error();
     };
 
-    if (n_streams == 1) {
-        worker(0);
-    } else {
-        std::vector<std::thread> th;
-        for (int t = 0; t < n_streams; ++t) th.emplace_back(worker, t);
-        for (auto &t : th) t.join();
+    int rc = 0;
+    std::string err;
+    SuperPlan cur, nxt;
+    std::thread helper(build_plan, 0, &cur);
+    for (int si = 0; si < n_super && rc == 0; ++si) {
+        const int c_lo = si * super_canvases, c_hi = std::min(n_canvases, c_lo + super_canvases);
+        const int buf = si % n_buf;
+        const int n_sub = (c_hi - c_lo + chunk_canvases - 1) / chunk_canvases;
+        // copy-in of this super-chunk's backgrounds can start before its plan is ready, but not before the
+        // previous user of this staging buffer (two super-chunks ago) has been copied out
+        if (si >= n_buf) cudaStreamWaitEvent(s_in, ev_done[buf], 0);
+        for (int j = 0; j < n_sub; ++j) {
+            const int lo = c_lo + j * chunk_canvases, hi = std::min(c_hi, lo + chunk_canvases);
+            for (int c = lo; c < hi; ++c) {
+                const b200comp_canvas &cv = canvases[c];
+                if (!cv.bg) continue;
+                cudaMemcpy2DAsync((uint8_t *)d_bg[buf].p + (size_t)(c - c_lo) * max_canvas_bytes, align_up((size_t)cv.W * 4, 16),
+                                  cv.bg, (size_t)cv.bg_pitch, (size_t)cv.W * 4, cv.H, cudaMemcpyHostToDevice, s_in);
+            }
+            cudaEventRecord(ev_in[(size_t)j], s_in);
+        }
+        helper.join();  // plan of this super-chunk
+        if (cur.rc) {
+            rc = cur.rc;
+            err = cur.err;
+            break;
+        }
+        if (si + 1 < n_super) {
+            nxt = SuperPlan();
+            helper = std::thread(build_plan, si + 1, &nxt);
+        }
+        if (si >= n_buf) cudaStreamWaitEvent(s_exec, ev_done[buf], 0);
+        cudaStreamWaitEvent(s_exec, ev_pool, 0);
+        rc = b200comp_plan_prepare(cur.plan, s_exec);
+        for (int j = 0; j < n_sub && rc == 0; ++j) {
+            const int lo = c_lo + j * chunk_canvases, hi = std::min(c_hi, lo + chunk_canvases);
+            cudaStreamWaitEvent(s_exec, ev_in[(size_t)j], 0);
+            rc = b200comp_plan_run_canvases(cur.plan, lo - c_lo, hi - lo, s_exec);
+            cudaEventRecord(ev_exec[(size_t)j], s_exec);
+            cudaStreamWaitEvent(s_out, ev_exec[(size_t)j], 0);
+            for (int c = lo; c < hi; ++c) {
+                const b200comp_canvas &cv = canvases[c];
+                cudaMemcpy2DAsync(cv.out, (size_t)cv.out_pitch, (uint8_t *)d_out[buf].p + (size_t)(c - c_lo) * max_canvas_bytes,
+                                  align_up((size_t)cv.W * 4, 16), (size_t)cv.W * 4, cv.H, cudaMemcpyDeviceToHost, s_out);
+            }
+        }
+        cudaEventRecord(ev_done[buf], s_out);
+        if (rc) err = b200comp_last_error();
+        // the events of this super-chunk are reused by the next one: drain the pipeline stage by stage
+        // (the NEXT plan is already being built on the helper thread meanwhile)
+        if (rc == 0) {
+            rc = b200comp_plan_check(cur.plan, s_exec);
+            if (rc) err = b200comp_last_error();
+        }
+        cudaError_t e = cudaStreamSynchronize(s_out);
+        if (rc == 0 && e != cudaSuccess) {
+            rc = B200COMP_ECUDA;
+            err = cudaGetErrorString(e);
+        }
+        cudaStreamSynchronize(s_plan);
+        b200comp_plan_destroy(cur.plan);
+        cur = SuperPlan();
+        if (si + 1 < n_super) {
+            helper.join();
+            cur = std::move(nxt);
+            helper = std::thread([] {});  // keep `helper` joinable for the uniform join above
+        }
     }
-    cudaSetDevice(device);
-    if (first_rc.load() != 0) {
-        for (auto &m : errs)
-            if (!m.empty()) return b200comp_set_error_(first_rc.load(), m.c_str());
-        return b200comp_set_error_(first_rc.load(), "composite_batch_host failed");
+    if (helper.joinable()) helper.join();
+    if (cur.plan) {
+        cudaDeviceSynchronize();
+        b200comp_plan_destroy(cur.plan);
     }
+    cudaDeviceSynchronize();
+    if (ev_pool) cudaEventDestroy(ev_pool);
+    if (ev_done[0]) cudaEventDestroy(ev_done[0]);
+    if (ev_done[1]) cudaEventDestroy(ev_done[1]);
+    if (rc) return b200comp_set_error_(rc, err.c_str());
     return 0;
 }
 

@@ -122,8 +122,14 @@ typedef struct b200comp_plan b200comp_plan;
  * DEVICE pointers and must stay valid until the plan is destroyed. */
 int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const b200comp_placement *placements,
                          int n_placements, int n_host_threads, void *stream, b200comp_plan **plan);
-/* Launch the batch (asynchronous on `stream`).  Re-runnable. */
+/* Launch the batch (asynchronous on `stream`).  Re-runnable.  Equivalent to b200comp_plan_prepare
+ * followed by b200comp_plan_run_canvases over every canvas. */
 int b200comp_plan_run(b200comp_plan *plan, void *stream);
+/* The two stages separately, so a caller can pipeline copies with compute: `prepare` builds what the
+ * tile kernel reads besides the caller's buffers (premultiplied planar cutouts, pre-resampled overlays
+ * of extreme scales); `run_canvases` launches the fused kernel for canvases [first, first + count). */
+int b200comp_plan_prepare(b200comp_plan *plan, void *stream);
+int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *stream);
 /* Frees the plan's device memory stream-ordered on the stream it was created on; the caller
  * must have synchronised every stream the plan ran on. */
 int b200comp_plan_destroy(b200comp_plan *plan);
