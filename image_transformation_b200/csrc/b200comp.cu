@@ -663,6 +663,21 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         ~Guard() { if (p) b200comp_plan_destroy(p); }
     } guard{plan};
     CUDA_TRY(cudaGetDevice(&plan->device));
+    {
+        // plans come and go (one per chunk in the host-buffer pipeline): keep freed blocks in the
+        // stream-ordered pool instead of returning them to the driver at every synchronisation
+        static std::mutex mu;
+        static std::vector<int> tuned;
+        std::lock_guard<std::mutex> lock(mu);
+        if (std::find(tuned.begin(), tuned.end(), plan->device) == tuned.end()) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, plan->device) == cudaSuccess) {
+                uint64_t keep = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            tuned.push_back(plan->device);
+        }
+    }
     plan->create_stream = st;
     plan->n_canvases = n_canvases;
 
@@ -803,7 +818,11 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         std::vector<int> map_of((size_t)std::max(1, n_placements), -1);
         std::vector<int> prep_of((size_t)std::max(1, n_placements), -1);
         std::vector<int64_t> flag_off;
+        std::vector<size_t> prep_off;
         int64_t flag_words = 0;
+        size_t prep_bytes = 0;
+        struct PendingMap { int placement, prep; };
+        std::vector<PendingMap> pending;
         int64_t max_words = 1;
         for (int i = 0; i < n_placements; ++i) {
             if (hp[i].mode != 1) continue;
@@ -819,31 +838,39 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
                 pd.sh = p.sh;
                 pd.w4p = ((p.sw + 3) / 4 + 3) & ~3;
                 pd.vec_ok = ((reinterpret_cast<uintptr_t>(p.src) & 15u) == 0 && (p.src_pitch & 15) == 0) ? 1 : 0;
-                CUDA_TRY(dev_alloc((void **)&pd.dst, (size_t)pd.w4p * 16 * p.sh));
+                prep_off.push_back(prep_bytes);
+                prep_bytes += ((size_t)pd.w4p * 16 * p.sh + 255) & ~(size_t)255;
                 flag_off.push_back(flag_words);
                 flag_words += (int64_t)((p.sh + 3) / 4) * (pd.w4p / 4);
                 max_words = std::max<int64_t>(max_words, (int64_t)pd.w4p * p.sh);
                 it = prep_index.emplace(key, (int)hprep.size()).first;
                 hprep.push_back(pd);
             }
-            const PrepDesc &pd = hprep[(size_t)it->second];
-            EncodeTiledFn enc = encode_tiled_fn();
-            if (!enc) return fail(B200COMP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
-            CUtensorMap tm;
-            const cuuint64_t gdim[3] = {(cuuint64_t)pd.w4p, 4, (cuuint64_t)pd.sh};
-            const cuuint64_t gstride[2] = {(cuuint64_t)pd.w4p * 4, (cuuint64_t)pd.w4p * 16};
-            const cuuint32_t box[3] = {(cuuint32_t)hp[i].pbw / 4, 4, (cuuint32_t)hp[i].nrbox};
-            const cuuint32_t estride[3] = {1, 1, 1};
-            const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, pd.dst, gdim, gstride, box, estride,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS)
-                return fail(B200COMP_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for placement " + std::to_string(i));
-            map_of[i] = (int)hmaps.size();
-            prep_of[i] = it->second;
-            hmaps.push_back(tm);
+            pending.push_back(PendingMap{i, it->second});
         }
         if (!hprep.empty()) {
+            uint8_t *d_prepared = nullptr;  // one allocation for every prepared cutout of the plan
+            CUDA_TRY(dev_alloc((void **)&d_prepared, prep_bytes));
+            for (size_t j = 0; j < hprep.size(); ++j) hprep[j].dst = reinterpret_cast<uint32_t *>(d_prepared + prep_off[j]);
+            EncodeTiledFn enc = encode_tiled_fn();
+            if (!enc) return fail(B200COMP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+            for (const PendingMap &pm : pending) {
+                const int i = pm.placement;
+                const PrepDesc &pd = hprep[(size_t)pm.prep];
+                CUtensorMap tm;
+                const cuuint64_t gdim[3] = {(cuuint64_t)pd.w4p, 4, (cuuint64_t)pd.sh};
+                const cuuint64_t gstride[2] = {(cuuint64_t)pd.w4p * 4, (cuuint64_t)pd.w4p * 16};
+                const cuuint32_t box[3] = {(cuuint32_t)hp[i].pbw / 4, 4, (cuuint32_t)hp[i].nrbox};
+                const cuuint32_t estride[3] = {1, 1, 1};
+                const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, pd.dst, gdim, gstride, box, estride,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS)
+                    return fail(B200COMP_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for placement " + std::to_string(i));
+                map_of[i] = (int)hmaps.size();
+                prep_of[i] = pm.prep;
+                hmaps.push_back(tm);
+            }
             CUtensorMap *d_maps = nullptr;
             CUDA_TRY(dev_alloc((void **)&d_maps, hmaps.size() * sizeof(CUtensorMap)));
             CUDA_TRY(dev_alloc((void **)&plan->d_prep, hprep.size() * sizeof(PrepDesc)));

@@ -56,7 +56,10 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
     if (cudaGetDevice(&device) != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, "no CUDA device");
     if (n_host_threads <= 0) n_host_threads = std::max(1u, std::thread::hardware_concurrency());
     if (chunk_canvases <= 0) chunk_canvases = 8;
-    const int super_canvases = std::min(n_canvases, 8 * chunk_canvases);
+    // super-chunk: about a quarter of the batch (so the pipeline has depth), between 2 and 16 sub-chunks
+    int super_canvases = ((n_canvases + 3) / 4 + chunk_canvases - 1) / chunk_canvases * chunk_canvases;
+    super_canvases = std::max(2 * chunk_canvases, std::min(16 * chunk_canvases, super_canvases));
+    super_canvases = std::min(n_canvases, super_canvases);
     const int n_super = (n_canvases + super_canvases - 1) / super_canvases;
 
     // ---- validate, size the staging buffers, find the distinct cutouts ----
@@ -107,7 +110,7 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
         cudaStreamCreateWithFlags(&s_plan, cudaStreamNonBlocking) != cudaSuccess)
         return b200comp_set_error_(B200COMP_ECUDA, "stream creation failed");
     const int max_sub = (super_canvases + chunk_canvases - 1) / chunk_canvases;
-    std::vector<cudaEvent_t> ev_in((size_t)max_sub), ev_exec((size_t)max_sub);
+    std::vector<cudaEvent_t> ev_in((size_t)max_sub * 2), ev_exec((size_t)max_sub * 2);  // one set per staging buffer
     struct EventGuard {
         std::vector<cudaEvent_t> *a, *b;
         ~EventGuard() { for (auto e : *a) if (e) cudaEventDestroy(e); for (auto e : *b) if (e) cudaEventDestroy(e); }
@@ -115,7 +118,7 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
     for (auto &e : ev_in) e = nullptr;
     for (auto &e : ev_exec) e = nullptr;
     cudaEvent_t ev_pool = nullptr, ev_done[2] = {nullptr, nullptr};
-    for (int i = 0; i < max_sub; ++i)
+    for (int i = 0; i < 2 * max_sub; ++i)
         if (cudaEventCreateWithFlags(&ev_in[(size_t)i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&ev_exec[(size_t)i], cudaEventDisableTiming) != cudaSuccess)
             return b200comp_set_error_(B200COMP_ECUDA, "event creation failed");
@@ -170,15 +173,36 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
 
     int rc = 0;
     std::string err;
-    SuperPlan cur, nxt;
-    std::thread helper(build_plan, 0, &cur);
-    for (int si = 0; si < n_super && rc == 0; ++si) {
+    SuperPlan live[2];  // plans of the super-chunks in flight, by staging buffer
+    SuperPlan built;    // plan being resolved by the helper thread
+    auto retire = [&](int buf) {  // wait for the super-chunk that used `buf`, check it, free its plan
+        if (!live[buf].plan) return;
+        if (rc) cudaDeviceSynchronize();  // error path: nothing may still be using the plan's memory
+        cudaError_t e = cudaEventSynchronize(ev_done[buf]);
+        if (rc == 0 && e != cudaSuccess) {
+            rc = B200COMP_ECUDA;
+            err = cudaGetErrorString(e);
+        }
+        if (rc == 0) {
+            const int c = b200comp_plan_check(live[buf].plan, s_exec);
+            if (c) {
+                rc = c;
+                err = b200comp_last_error();
+            }
+        }
+        cudaStreamSynchronize(s_plan);
+        b200comp_plan_destroy(live[buf].plan);
+        live[buf] = SuperPlan();
+    };
+    std::thread helper(build_plan, 0, &built);
+    for (int si = 0; si < n_super; ++si) {
         const int c_lo = si * super_canvases, c_hi = std::min(n_canvases, c_lo + super_canvases);
         const int buf = si % n_buf;
         const int n_sub = (c_hi - c_lo + chunk_canvases - 1) / chunk_canvases;
-        // copy-in of this super-chunk's backgrounds can start before its plan is ready, but not before the
-        // previous user of this staging buffer (two super-chunks ago) has been copied out
-        if (si >= n_buf) cudaStreamWaitEvent(s_in, ev_done[buf], 0);
+        cudaEvent_t *e_in = ev_in.data() + (size_t)buf * max_sub, *e_exec = ev_exec.data() + (size_t)buf * max_sub;
+        retire(buf);  // the previous user of this staging buffer (two super-chunks ago)
+        if (rc) break;
+        // copy-in of the backgrounds overlaps the helper thread's table building
         for (int j = 0; j < n_sub; ++j) {
             const int lo = c_lo + j * chunk_canvases, hi = std::min(c_hi, lo + chunk_canvases);
             for (int c = lo; c < hi; ++c) {
@@ -187,27 +211,30 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
                 cudaMemcpy2DAsync((uint8_t *)d_bg[buf].p + (size_t)(c - c_lo) * max_canvas_bytes, align_up((size_t)cv.W * 4, 16),
                                   cv.bg, (size_t)cv.bg_pitch, (size_t)cv.W * 4, cv.H, cudaMemcpyHostToDevice, s_in);
             }
-            cudaEventRecord(ev_in[(size_t)j], s_in);
+            cudaEventRecord(e_in[j], s_in);
         }
         helper.join();  // plan of this super-chunk
-        if (cur.rc) {
-            rc = cur.rc;
-            err = cur.err;
+        live[buf] = std::move(built);
+        built = SuperPlan();
+        if (live[buf].rc) {
+            rc = live[buf].rc;
+            err = live[buf].err;
+            helper = std::thread([] {});
             break;
         }
-        if (si + 1 < n_super) {
-            nxt = SuperPlan();
-            helper = std::thread(build_plan, si + 1, &nxt);
-        }
-        if (si >= n_buf) cudaStreamWaitEvent(s_exec, ev_done[buf], 0);
+        if (si + 1 < n_super)
+            helper = std::thread(build_plan, si + 1, &built);
+        else
+            helper = std::thread([] {});
+        cudaStreamSynchronize(s_plan);  // descriptors and tables of this plan are on the device
         cudaStreamWaitEvent(s_exec, ev_pool, 0);
-        rc = b200comp_plan_prepare(cur.plan, s_exec);
+        rc = b200comp_plan_prepare(live[buf].plan, s_exec);
         for (int j = 0; j < n_sub && rc == 0; ++j) {
             const int lo = c_lo + j * chunk_canvases, hi = std::min(c_hi, lo + chunk_canvases);
-            cudaStreamWaitEvent(s_exec, ev_in[(size_t)j], 0);
-            rc = b200comp_plan_run_canvases(cur.plan, lo - c_lo, hi - lo, s_exec);
-            cudaEventRecord(ev_exec[(size_t)j], s_exec);
-            cudaStreamWaitEvent(s_out, ev_exec[(size_t)j], 0);
+            cudaStreamWaitEvent(s_exec, e_in[j], 0);
+            rc = b200comp_plan_run_canvases(live[buf].plan, lo - c_lo, hi - lo, s_exec);
+            cudaEventRecord(e_exec[j], s_exec);
+            cudaStreamWaitEvent(s_out, e_exec[j], 0);
             for (int c = lo; c < hi; ++c) {
                 const b200comp_canvas &cv = canvases[c];
                 cudaMemcpy2DAsync(cv.out, (size_t)cv.out_pitch, (uint8_t *)d_out[buf].p + (size_t)(c - c_lo) * max_canvas_bytes,
@@ -215,31 +242,24 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
             }
         }
         cudaEventRecord(ev_done[buf], s_out);
-        if (rc) err = b200comp_last_error();
-        // the events of this super-chunk are reused by the next one: drain the pipeline stage by stage
-        // (the NEXT plan is already being built on the helper thread meanwhile)
-        if (rc == 0) {
-            rc = b200comp_plan_check(cur.plan, s_exec);
-            if (rc) err = b200comp_last_error();
-        }
-        cudaError_t e = cudaStreamSynchronize(s_out);
-        if (rc == 0 && e != cudaSuccess) {
-            rc = B200COMP_ECUDA;
-            err = cudaGetErrorString(e);
-        }
-        cudaStreamSynchronize(s_plan);
-        b200comp_plan_destroy(cur.plan);
-        cur = SuperPlan();
-        if (si + 1 < n_super) {
-            helper.join();
-            cur = std::move(nxt);
-            helper = std::thread([] {});  // keep `helper` joinable for the uniform join above
+        if (rc) {
+            err = b200comp_last_error();
+            break;
         }
     }
     if (helper.joinable()) helper.join();
-    if (cur.plan) {
-        cudaDeviceSynchronize();
-        b200comp_plan_destroy(cur.plan);
+    if (built.plan) {  // built but never launched (error path)
+        cudaStreamSynchronize(s_plan);
+        b200comp_plan_destroy(built.plan);
+    }
+    {
+        const int keep_rc = rc;
+        const std::string keep_err = err;
+        for (int b = 0; b < 2; ++b) retire(b);
+        if (keep_rc) {
+            rc = keep_rc;
+            err = keep_err;
+        }
     }
     cudaDeviceSynchronize();
     if (ev_pool) cudaEventDestroy(ev_pool);
