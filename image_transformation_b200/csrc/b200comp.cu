@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -476,11 +477,25 @@ struct b200comp_plan {
     size_t flag_bytes = 0;
     int n_prep = 0;
     int prep_blocks_x = 1;
+    // command streams of the persistent tile kernel (rebuilt by the binning kernels at every run)
+    int G = 1;                       // persistent CTAs = streams
+    int64_t stream_capacity = 0;     // records (exact upper bound from the host-side box/tile count)
+    Cmd *d_streams = nullptr;
+    int32_t *d_bin = nullptr;        // [G][K] per-tile slot counts, scanned in place
+    int64_t *d_stream_off = nullptr; // [G + 1]
+    uint8_t *d_maps = nullptr;       // every CUtensorMap of the plan (placements, overlays, canvases)
+    std::vector<int64_t> tiles_before;  // prefix sum of tiles per canvas (n_canvases + 1)
     std::vector<void *> owned;  // device allocations freed with the plan
 };
 
 static const size_t kMaxSmemBytes = 200 * 1024;    // opt-in dynamic shared memory limit we request
 static const size_t kFusedSmemCap = 112 * 1024;    // placements needing more go through the generic kernels
+// dynamic shared memory of the tile kernel: alignment slack + resident tiles + patch + intermediate +
+// command ring + mbarriers
+static size_t tile_smem_bytes(int64_t patch_words, int64_t inter_words) {
+    return 1024 + ((size_t)kTileBufs * kTileWords + (size_t)patch_words + (size_t)inter_words) * 4 + kRing * sizeof(Cmd) +
+           (kTileBufs + 1) * sizeof(uint64_t);
+}
 static_assert(sizeof(b200comp_placement) == 48 && sizeof(b200comp_canvas) == 56, "public struct layout");
 
 #pragma GCC visibility push(default)
@@ -686,7 +701,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     std::vector<DevPlacementT> hp((size_t)std::max(1, n_placements));
     std::vector<std::pair<TableRef, TableRef>> tref((size_t)std::max(1, n_placements));
     std::vector<int> pre_index((size_t)std::max(1, n_placements), -1);
-    int max_patch = 16, max_inter = 16;
+    int max_patch = kOverlayBoxW * kTileH, max_inter = 16;  // the patch buffer also stages identity overlays
     int64_t n_fused = 0, n_ident = 0;
     for (int i = 0; i < n_placements; ++i) {
         const b200comp_placement &p = placements[i];
@@ -719,7 +734,8 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             nrq = words_bound(p.sh, p.h, kTileH, nwy);
             patch = (int64_t)4 * (4 * nrq) * ncw;          // TMA box: rows x (words x 4 channels)
             inter = (int64_t)4 * kTileW * (nrq | 1);       // 4 channel planes x columns x row-quads
-            fused = ((size_t)kTileH * kCtPitch + patch + inter) * 4 <= kFusedSmemCap && 4 * ncw <= 256 && 4 * nrq <= 256;
+            fused = tile_smem_bytes(patch, inter) <= kFusedSmemCap && 4 * ncw <= 256 && 4 * nrq <= 256 &&
+                    p.sw < 262144 && p.sh < 262144;
         }
         if (fused) {
             d.mode = 1;
@@ -750,13 +766,13 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             plan->pre.push_back(pr);
             d.mode = 0;
             d.sw = p.w; d.sh = p.h;
-            d.src_pitch = p.w * 4;
+            d.src_pitch = (p.w * 4 + 15) & ~15;
         }
     }
 
     // ---- canvases / tiles ----
     std::vector<DevCanvas> hc((size_t)n_canvases);
-    int64_t tiles = 0, algo = 0;
+    int64_t tiles = 0, algo = 0, step_records = 0;
     for (int c = 0; c < n_canvases; ++c) {
         const b200comp_canvas &cv = canvases[c];
         if (!cv.out || cv.W < 1 || cv.H < 1) return fail(B200COMP_EINVAL, "plan_create: canvas " + std::to_string(c) + " has no output or empty size");
@@ -772,6 +788,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         d.tiles_x = (cv.W + kTileW - 1) / kTileW;
         d.tiles_y = (cv.H + kTileH - 1) / kTileH;
         d.tile_base = tiles;
+        plan->tiles_before.push_back(tiles);
         tiles += (int64_t)d.tiles_x * d.tiles_y;
         if ((int64_t)d.tiles_x * d.tiles_y > INT32_MAX) return fail(B200COMP_EINVAL, "plan_create: canvas too large");
         plan->max_tiles = std::max(plan->max_tiles, d.tiles_x * d.tiles_y);
@@ -779,9 +796,21 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         for (int i = 0; i < cv.n_placements; ++i) {
             const b200comp_placement &p = placements[cv.first_placement + i];
             algo += (int64_t)p.sw * p.sh * 4;
+            // tiles the box touches = records the binning pass writes for it
+            const int64_t x0 = std::max<int64_t>(0, p.x), y0 = std::max<int64_t>(0, p.y);
+            const int64_t x1 = std::min<int64_t>(cv.W, (int64_t)p.x + p.w), y1 = std::min<int64_t>(cv.H, (int64_t)p.y + p.h);
+            if (x0 < x1 && y0 < y1)
+                step_records += ((x1 - 1) / kTileW - x0 / kTileW + 1) * ((y1 - 1) / kTileH - y0 / kTileH + 1);
         }
     }
+    plan->tiles_before.push_back(tiles);
     plan->n_tiles = tiles;
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device);
+        plan->G = std::max(1, std::min(1024, 2 * sms));
+        plan->stream_capacity = tiles + step_records + plan->G;
+    }
 
     // ---- build tables on the host threads, upload everything ----
     ts.build(n_host_threads);
@@ -796,7 +825,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     CUDA_TRY(dev_alloc((void **)&plan->d_canvases, hc.size() * sizeof(DevCanvas)));
     CUDA_TRY(dev_alloc((void **)&plan->d_status, sizeof(int)));
     for (auto &pr : plan->pre) {
-        CUDA_TRY(dev_alloc((void **)&pr.dst, (size_t)pr.w * pr.h * 4));
+        CUDA_TRY(dev_alloc((void **)&pr.dst, (size_t)((pr.w * 4 + 15) & ~15) * pr.h));
         if (pr.w != pr.sw && pr.h != pr.sh)
             CUDA_TRY(dev_alloc((void **)&pr.scratch, (size_t)std::max((int64_t)pr.sh * pr.w, (int64_t)pr.h * pr.sw) * 4));
     }
@@ -848,12 +877,13 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             }
             pending.push_back(PendingMap{i, it->second});
         }
+        EncodeTiledFn enc = encode_tiled_fn();
+        if (!enc) return fail(B200COMP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        const cuuint32_t estride[3] = {1, 1, 1};
         if (!hprep.empty()) {
             uint8_t *d_prepared = nullptr;  // one allocation for every prepared cutout of the plan
             CUDA_TRY(dev_alloc((void **)&d_prepared, prep_bytes));
             for (size_t j = 0; j < hprep.size(); ++j) hprep[j].dst = reinterpret_cast<uint32_t *>(d_prepared + prep_off[j]);
-            EncodeTiledFn enc = encode_tiled_fn();
-            if (!enc) return fail(B200COMP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
             for (const PendingMap &pm : pending) {
                 const int i = pm.placement;
                 const PrepDesc &pd = hprep[(size_t)pm.prep];
@@ -861,7 +891,6 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
                 const cuuint64_t gdim[3] = {(cuuint64_t)pd.w4p, 4, (cuuint64_t)pd.sh};
                 const cuuint64_t gstride[2] = {(cuuint64_t)pd.w4p * 4, (cuuint64_t)pd.w4p * 16};
                 const cuuint32_t box[3] = {(cuuint32_t)hp[i].pbw / 4, 4, (cuuint32_t)hp[i].nrbox};
-                const cuuint32_t estride[3] = {1, 1, 1};
                 const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, pd.dst, gdim, gstride, box, estride,
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -871,26 +900,80 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
                 prep_of[i] = pm.prep;
                 hmaps.push_back(tm);
             }
-            CUtensorMap *d_maps = nullptr;
-            CUDA_TRY(dev_alloc((void **)&d_maps, hmaps.size() * sizeof(CUtensorMap)));
             CUDA_TRY(dev_alloc((void **)&plan->d_prep, hprep.size() * sizeof(PrepDesc)));
             CUDA_TRY(dev_alloc((void **)&plan->d_flags, (size_t)flag_words * 4));
             plan->flag_bytes = (size_t)flag_words * 4;
             for (size_t j = 0; j < hprep.size(); ++j) hprep[j].flags = plan->d_flags + flag_off[j];
-            CUDA_TRY(cudaMemcpyAsync(d_maps, hmaps.data(), hmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(plan->d_prep, hprep.data(), hprep.size() * sizeof(PrepDesc), cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaStreamSynchronize(st));  // hmaps / hprep are locals
             plan->n_prep = (int)hprep.size();
             plan->prep_blocks_x = (int)std::max<int64_t>(1, std::min<int64_t>((max_words + 255) / 256, 64));
-            for (int i = 0; i < n_placements; ++i)
-                if (map_of[i] >= 0) {
-                    const PrepDesc &pd = hprep[(size_t)prep_of[i]];
-                    hp[i].tmap = d_maps + map_of[i];
-                    hp[i].flags = pd.flags;
-                    hp[i].wq = pd.w4p / 4;
-                    hp[i].sh4 = (pd.sh + 3) / 4;
-                }
         }
+        // 2-D maps: u32 pixels x rows.  Overlays composited as they are: one 68x32-pixel box per tile step.
+        // Canvases: 32x32-pixel boxes with the 128-byte swizzle (tile_kernel.cuh ct_off).  Buffers TMA cannot
+        // address (base not 16-byte aligned, pitch not a multiple of 16) keep a null map: generic loads/stores.
+        auto encode_2d = [&](const void *base, int64_t pitch, int w, int h, int bw, int bh, bool swizzle, CUtensorMap *tm) -> bool {
+            if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (pitch & 15) != 0 || pitch <= 0) return false;
+            const cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)h};
+            const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
+            const cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)bh};
+            return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), gdim, gstride, box, estride,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        };
+        {
+            std::map<SrcKey, int> overlay_map;
+            for (int i = 0; i < n_placements; ++i) {
+                if (hp[i].mode != 0) continue;
+                SrcKey key(hp[i].src, hp[i].sw, hp[i].sh, (int64_t)hp[i].src_pitch);
+                auto it = overlay_map.find(key);
+                if (it == overlay_map.end()) {
+                    CUtensorMap tm;
+                    int idx = -1;
+                    if (encode_2d(hp[i].src, hp[i].src_pitch, hp[i].sw, hp[i].sh, kOverlayBoxW, kTileH, false, &tm)) {
+                        idx = (int)hmaps.size();
+                        hmaps.push_back(tm);
+                    }
+                    it = overlay_map.emplace(key, idx).first;
+                }
+                map_of[i] = it->second;
+            }
+        }
+        std::vector<int> bg_map_of((size_t)n_canvases, -1), out_map_of((size_t)n_canvases, -1);
+        for (int c = 0; c < n_canvases; ++c) {
+            CUtensorMap tm;
+            if (hc[c].bg && encode_2d(hc[c].bg, hc[c].bg_pitch, hc[c].W, hc[c].H, 32, kTileH, true, &tm)) {
+                bg_map_of[c] = (int)hmaps.size();
+                hmaps.push_back(tm);
+            }
+            if (encode_2d(hc[c].out, hc[c].out_pitch, hc[c].W, hc[c].H, 32, kTileH, true, &tm)) {
+                out_map_of[c] = (int)hmaps.size();
+                hmaps.push_back(tm);
+            }
+        }
+        CUDA_TRY(dev_alloc((void **)&plan->d_maps, std::max<size_t>(1, hmaps.size()) * sizeof(CUtensorMap)));
+        if (!hmaps.empty())
+            CUDA_TRY(cudaMemcpyAsync(plan->d_maps, hmaps.data(), hmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));  // hmaps / hprep are locals
+        for (int i = 0; i < n_placements; ++i) {
+            if (map_of[i] >= 0) hp[i].tmap = plan->d_maps + (size_t)map_of[i] * sizeof(CUtensorMap);
+            if (prep_of[i] >= 0) {
+                const PrepDesc &pd = hprep[(size_t)prep_of[i]];
+                hp[i].flags = pd.flags;
+                hp[i].wq = pd.w4p / 4;
+                hp[i].sh4 = (pd.sh + 3) / 4;
+            }
+        }
+        for (int c = 0; c < n_canvases; ++c) {
+            hc[c].bg_map = bg_map_of[c] >= 0 ? plan->d_maps + (size_t)bg_map_of[c] * sizeof(CUtensorMap) : nullptr;
+            hc[c].out_map = out_map_of[c] >= 0 ? plan->d_maps + (size_t)out_map_of[c] * sizeof(CUtensorMap) : nullptr;
+        }
+    }
+    // command streams: records + ring read-ahead slack; per-tile counts; stream offsets
+    {
+        const int64_t K = (tiles + plan->G - 1) / plan->G;
+        CUDA_TRY(dev_alloc((void **)&plan->d_streams, (size_t)(plan->stream_capacity + kRing) * sizeof(Cmd)));
+        CUDA_TRY(dev_alloc((void **)&plan->d_bin, (size_t)plan->G * (size_t)std::max<int64_t>(1, K) * sizeof(int32_t)));
+        CUDA_TRY(dev_alloc((void **)&plan->d_stream_off, (size_t)(plan->G + 1) * sizeof(int64_t)));
     }
     CUDA_TRY(cudaMemcpyAsync(plan->d_tables, ts.host.data(), tbytes, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(plan->d_placements, hp.data(), hp.size() * sizeof(DevPlacementT), cudaMemcpyHostToDevice, st));
@@ -900,11 +983,11 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
 
     plan->patch_words = max_patch;
     plan->inter_words = max_inter;
-    plan->smem_bytes = ((size_t)kTileH * kCtPitch + max_patch + max_inter) * 4;
-    CUDA_TRY(cudaFuncSetAttribute(composite_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemBytes));
+    plan->smem_bytes = tile_smem_bytes(max_patch, max_inter);
+    CUDA_TRY(cudaFuncSetAttribute(composite_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemBytes));
 
     plan->info[B200COMP_INFO_ALGORITHMIC_BYTES] = algo;
-    plan->info[B200COMP_INFO_LAUNCHES_PER_RUN] = 1 + (plan->n_prep > 0 ? 1 : 0);
+    plan->info[B200COMP_INFO_LAUNCHES_PER_RUN] = 4 + (plan->n_prep > 0 ? 1 : 0);  // 3 binning kernels + tile kernel
     for (auto &pr : plan->pre) plan->info[B200COMP_INFO_LAUNCHES_PER_RUN] += (pr.w != pr.sw && pr.h != pr.sh) ? 2 : 1;
     plan->info[B200COMP_INFO_FUSED_PLACEMENTS] = n_fused;
     plan->info[B200COMP_INFO_IDENTITY_PLACEMENTS] = n_ident;
@@ -925,7 +1008,7 @@ int b200comp_plan_prepare(b200comp_plan *plan, void *stream) {
     cudaStream_t st = S(stream);
     for (auto &pr : plan->pre) {
         const int32_t *t = plan->d_tables;
-        int rc = resample_two_pass(pr.src, pr.sw, pr.sh, pr.sp, pr.dst, pr.w, pr.h, (int64_t)pr.w * 4, t + pr.tx.k_off,
+        int rc = resample_two_pass(pr.src, pr.sw, pr.sh, pr.sp, pr.dst, pr.w, pr.h, (int64_t)((pr.w * 4 + 15) & ~15), t + pr.tx.k_off,
                                    t + pr.tx.b_off, pr.tx.ks, t + pr.ty.k_off, t + pr.ty.b_off, pr.ty.ks, pr.scratch,
                                    pr.flags, st);
         if (rc) return rc;
@@ -949,13 +1032,43 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
     if (first < 0 || count < 0 || (int64_t)first + count > plan->n_canvases)
         return fail(B200COMP_EINVAL, "plan_run_canvases: canvas range out of bounds");
     cudaStream_t st = S(stream);
-    // grid.y is limited to 65535 canvases per launch
+    if (count == 0) return 0;
+    // Runs of one plan share its command-stream buffers: they must be ordered on the stream.
+    const int64_t tile0 = plan->tiles_before[(size_t)first];
+    const int64_t n_tiles = plan->tiles_before[(size_t)first + count] - tile0;
+    const int G = plan->G;
+    const int K = (int)((n_tiles + G - 1) / G);
+    const unsigned gx = (unsigned)((plan->max_tiles + 127) / 128);
+    // B200COMP_DEBUG_SYNC=1: synchronise after every launch so a device fault names its kernel
+    static const bool debug_sync = std::getenv("B200COMP_DEBUG_SYNC") != nullptr;
+    auto checkpoint = [&](const char *what) -> int {
+        if (!debug_sync) return 0;
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(B200COMP_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+        return 0;
+    };
+    for (int c0 = first; c0 < first + count; c0 += 65535) {  // grid.y is limited to 65535 canvases per launch
+        const int nc = std::min(65535, first + count - c0);
+        bin_count_kernel<<<dim3(gx, (unsigned)nc), 128, 0, st>>>(plan->d_canvases + c0, plan->d_placements, tile0, G, K, plan->d_bin);
+    }
+    if (int rc = checkpoint("bin_count_kernel")) return rc;
+    bin_scan_kernel<<<1, 1024, 0, st>>>(plan->d_bin, G, K, n_tiles, plan->d_stream_off, plan->d_streams,
+                                        plan->stream_capacity, plan->d_status);
+    if (int rc = checkpoint("bin_scan_kernel")) return rc;
     for (int c0 = first; c0 < first + count; c0 += 65535) {
         const int nc = std::min(65535, first + count - c0);
-        composite_tiles_kernel<<<dim3((unsigned)plan->max_tiles, (unsigned)nc), kThreads, plan->smem_bytes, st>>>(
-            plan->d_canvases + c0, plan->d_placements, plan->patch_words, plan->inter_words, plan->d_status);
+        bin_fill_kernel<<<dim3(gx, (unsigned)nc), 128, 0, st>>>(
+            plan->d_canvases + c0, c0, plan->d_placements, tile0, G, K, plan->d_bin, plan->d_stream_off, plan->d_streams,
+            plan->stream_capacity, plan->d_maps, reinterpret_cast<const uint32_t *>(plan->d_tables), plan->patch_words,
+            plan->inter_words, plan->d_status);
     }
+    if (int rc = checkpoint("bin_fill_kernel")) return rc;
+    composite_stream_kernel<<<(unsigned)G, kThreads, plan->smem_bytes, st>>>(
+        plan->d_streams, plan->d_stream_off, plan->d_canvases, plan->d_maps,
+        reinterpret_cast<const uint32_t *>(plan->d_tables), plan->patch_words, plan->inter_words);
     CUDA_TRY(cudaGetLastError());
+    if (int rc = checkpoint("composite_stream_kernel")) return rc;
     return 0;
 }
 
@@ -963,6 +1076,18 @@ int b200comp_plan_run(b200comp_plan *plan, void *stream) {
     int rc = b200comp_plan_prepare(plan, stream);
     if (rc) return rc;
     return b200comp_plan_run_canvases(plan, 0, plan->n_canvases, stream);
+}
+
+// internal (tools/): copy the command streams of the last run to the host.  out: records of 16 words;
+// offs: G + 1 stream offsets.  Returns the number of records copied or a negative error.
+int64_t b200comp_plan_debug_streams_(b200comp_plan *plan, uint32_t *out, int64_t max_records, int64_t *offs, int *n_streams) {
+    if (!plan || !out || !offs) return B200COMP_EINVAL;
+    cudaDeviceSynchronize();
+    cudaMemcpy(offs, plan->d_stream_off, (size_t)(plan->G + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost);
+    if (n_streams) *n_streams = plan->G;
+    const int64_t n = std::min<int64_t>(max_records, std::min<int64_t>(offs[plan->G], plan->stream_capacity));
+    cudaMemcpy(out, plan->d_streams, (size_t)n * sizeof(Cmd), cudaMemcpyDeviceToHost);
+    return n;
 }
 
 int b200comp_plan_info(const b200comp_plan *plan, int64_t *info) {
@@ -977,7 +1102,7 @@ int b200comp_plan_check(b200comp_plan *plan, void *stream) {
     int h = 0;
     CUDA_TRY(cudaMemcpyAsync(&h, plan->d_status, sizeof h, cudaMemcpyDeviceToHost, S(stream)));
     CUDA_TRY(cudaStreamSynchronize(S(stream)));
-    if (h != 0) return fail(B200COMP_EINTERNAL, "tile kernel reported a shared-memory sizing violation (status " + std::to_string(h) + ")");
+    if (h != 0) return fail(B200COMP_EINTERNAL, "binning reported a sizing violation (status " + std::to_string(h) + ")");
     return 0;
 }
 

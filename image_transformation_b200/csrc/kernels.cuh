@@ -19,17 +19,44 @@ struct DevCanvas {
     int32_t first, count;  // placement range
     int32_t tiles_x, tiles_y;
     int32_t pad_;
+    const void *bg_map;   // CUtensorMap (32x32-pixel boxes, 128-byte swizzle) over bg, or null: generic loads
+    const void *out_map;  // same over out, or null: generic stores
 };
-static_assert(sizeof(DevCanvas) == 72, "DevCanvas layout");
+static_assert(sizeof(DevCanvas) == 88, "DevCanvas layout");
 
 constexpr int kTileW = 64;
 constexpr int kTileH = 32;
 constexpr int kThreads = 384;  // 12 warps per CTA, two CTAs per SM (register-limited at 85 / thread)
 constexpr int kWarps = kThreads / 32;
-constexpr int kCtPitch = kTileW + 1;  // odd pitch: row-per-lane accesses hit distinct banks
 constexpr int kPrecisionBits = 22;
+constexpr int kTileWords = kTileW * kTileH;  // one resident canvas tile: two 32x32-pixel halves, 128-byte swizzled
+constexpr int kOverlayBoxW = kTileW + 4;       // identity overlays: box widened so its start can be 16-byte aligned
+constexpr int kTileBufs = 4;                 // canvas tiles in flight per CTA (background prefetch / compute / store)
 
-enum : int { kStatusPatchOverflow = 1, kStatusInterOverflow = 2 };
+enum : int { kStatusPatchOverflow = 1, kStatusInterOverflow = 2, kStatusStreamOverflow = 4 };
+
+// ------------------------------------------------------------------ command streams
+// The tile kernel is persistent: CTA c of G walks the canvas tiles t = c, c + G, c + 2G, ... of a run.
+// A binning pass turns (canvases, placements) into one command stream per CTA, so the tile kernel never
+// chases pointers: it prefetches fixed-size records from a linear array.  A record is 16 words:
+//   TILE      w0 kind, w1 n_steps, w2 tx0, w3 ty0, w4 tw | th << 16, w5 solid, w6 flags, w7 canvas index,
+//             w8-9 bg tensor map, w10-11 out tensor map
+//   RESAMPLE  w0 kind, w1 nwx | nwy << 8 | nch << 16 | NRQ << 24, w2 dx | dy << 8 | two << 16 | tho << 24,
+//             w3 ox0, w4 oy0, w5 cw0 | rw0 << 16, w6 w (coefficient plane stride x), w7 h,
+//             w8 tensor map index, w9 plx word offset, w10 ply word offset, w11 pbw | nrbox << 16,
+//             w12-13 scale_x, w14-15 scale_y
+//   IDENT_TMA w0 kind, w2 as above, w3 / w4 source coordinates of the box (w3 a multiple of 4: TMA boxes
+//             start on 16-byte boundaries), w5 pixels from the box start to the tile origin, w8 map index
+//   IDENT_LDG w0 kind, w2 as above, w3 / w4 source coordinates of the intersection, w6 pitch, w12-13 src
+struct __align__(16) Cmd {
+    uint32_t w[16];
+};
+static_assert(sizeof(Cmd) == 64, "Cmd layout");
+enum : uint32_t { kCmdTile = 0, kCmdResample = 1, kCmdIdentTma = 2, kCmdIdentLdg = 3, kCmdNop = 4, kCmdEnd = 5 };
+enum : uint32_t { kTileBgTma = 1, kTileOutTma = 2, kTileHasBg = 4 };
+constexpr int kRing = 8;       // command ring slots in shared memory
+constexpr int kRingAhead = 6;  // records fetched ahead of the consumer
+constexpr int kLook = 3;       // records the producer may run ahead of the consumer
 
 // ------------------------------------------------------------------ pixel arithmetic
 // ImagingUtils.h MULDIV255

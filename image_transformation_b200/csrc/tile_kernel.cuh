@@ -149,6 +149,35 @@ __device__ __forceinline__ void prefetch_coeffs(const uint32_t *__restrict__ pl,
     for (int q = 0; q < 3 * nw; ++q) prefetch_l1(pl + (int64_t)q * n_out + idx);
 }
 
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tmap, int x, int y, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void *tmap, int x, int y, const void *smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(tmap), "r"(x), "r"(y), "r"(smem_u32(smem_src)) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Word offset of canvas pixel (row r, column x) inside a resident tile buffer.  A tile is two 32x32-pixel
+// halves, each exactly what one TMA box with CU_TENSOR_MAP_SWIZZLE_128B leaves in shared memory: rows of
+// 128 bytes whose 16-byte chunk index is XORed with (row & 7).  The vertical pass walks rows with the
+// lanes of a warp at a fixed column: the swizzle spreads those 32 accesses over 8 banks x 4 words.
+__device__ __forceinline__ uint32_t ct_off(int r, int x) {
+    return (uint32_t)(((x & 32) << 5) | (r << 5) | ((((x >> 2) ^ r) & 7) << 2) | (x & 3));
+}
+
 // ---- H pass ---------------------------------------------------------------------------------
 // I[c][jj][rq]: plane c at I + c*iplane_stride, column pitch IPW words (odd), byte k of word rq =
 // intermediate row 4*rq+k (relative to source row 4*rw0).
@@ -224,7 +253,8 @@ __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, 
         k1[i] = __ldg(ply + (int64_t)(1 * NW + i) * n_out + y);
         k2[i] = __ldg(ply + (int64_t)(2 * NW + i) * n_out + y);
     }
-    uint32_t *crow = ctile + (tile_dy + lane) * kCtPitch + tile_dx;
+    const int r = tile_dy + lane;
+    uint32_t *crow = ctile + (r << 5);
     for (int x = warp; x < two; x += kWarps) {
         const uint32_t *col = I + x * IPW + wbase;
         int32_t acc[4];
@@ -249,7 +279,9 @@ __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, 
         if (acc[3] < (1 << kPrecisionBits)) continue;  // transparent: canvas pixel unchanged
         const bool opaque = acc[3] >= (255 << kPrecisionBits);
         const uint32_t s = clip8i(acc[0]) | (clip8i(acc[1]) << 8) | (clip8i(acc[2]) << 16) | (clip8i(acc[3]) << 24);
-        crow[x] = opaque ? s : over_px(crow[x], unpremultiply_px(s));
+        const int X = tile_dx + x;
+        uint32_t *cpx = crow + (((X & 32) << 5) | ((((X >> 2) ^ r) & 7) << 2) | (X & 3));
+        *cpx = opaque ? s : over_px(*cpx, unpremultiply_px(s));
     }
 }
 
@@ -258,6 +290,7 @@ struct DevPlacementT {
     const uint32_t *plx;   // [3*nwx][w] coefficient byte planes of the horizontal pass
     const uint32_t *ply;   // [3*nwy][h] vertical pass
     const void *tmap;      // mode 1: CUtensorMap over the prepared cutout, box = (pbw/4 words, 4 planes, nrbox rows)
+                           // mode 0: CUtensorMap over the raw overlay, box = 64 x 32 pixels (null: generic loads)
     const uint32_t *flags; // mode 1: alpha summary of the prepared cutout, [sh4][wq] (see PrepDesc)
     double scale_x, support_x;  // sw / w and 3 * max(1, scale): exactly the host builder's doubles
     double scale_y, support_y;
@@ -272,231 +305,453 @@ struct DevPlacementT {
 };
 static_assert(sizeof(DevPlacementT) == 128, "DevPlacementT layout");
 
-constexpr int kDescCache = 64;  // placement descriptors cached in shared memory per CTA
-constexpr int kDescWords = sizeof(DevPlacementT) / 4;
-
-// grid = (max tiles per canvas, n canvases): blockIdx.y is the canvas, blockIdx.x its tile.
-__global__ void __launch_bounds__(kThreads, 2)
-composite_tiles_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__restrict__ placements,
-                       int patch_words, int inter_words, int *__restrict__ status) {
-    extern __shared__ __align__(128) uint32_t smem[];
-    uint32_t *ctile = smem;                   // kTileH * kCtPitch (8320 B: keeps P 128-byte aligned for TMA)
-    uint32_t *P = ctile + kTileH * kCtPitch;  // patch_words
-    uint32_t *I = P + patch_words;            // inter_words
-    __shared__ __align__(16) uint32_t desc_words[kDescCache * kDescWords];
-    __shared__ uint32_t hit_mask[kDescCache / 32];
-    __shared__ uint8_t hit_list[kDescCache];
-    __shared__ __align__(8) uint64_t tma_bar;
-    __shared__ uint32_t alpha_bits[2];  // OR of the alpha summary over the current patch (double buffered)
-
-    const DevCanvas cv = canvases[blockIdx.y];
-    const int local = blockIdx.x;
-    if (local >= cv.tiles_x * cv.tiles_y) return;  // canvases of different sizes share one grid
+// ---- binning: (canvases, placements) -> one command stream per persistent CTA -----------------------
+// Tile t (numbered over the canvases of the run) belongs to CTA t % G and is its (t / G)-th tile.
+// count: slots each tile needs (1 + placements whose box touches it), stored stream-major so that the
+// scan kernel walks one contiguous row per stream.
+__global__ void __launch_bounds__(128)
+bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__restrict__ placements,
+                 int64_t run_tile_base, int G, int K, int32_t *__restrict__ cnt) {
+    const DevCanvas &cv = canvases[blockIdx.y];
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= cv.tiles_x * cv.tiles_y) return;
     const int ty = local / cv.tiles_x, tx = local - ty * cv.tiles_x;
     const int tx0 = tx * kTileW, ty0 = ty * kTileH;
     const int tx1 = min(cv.W, tx0 + kTileW), ty1 = min(cv.H, ty0 + kTileH);
-    const int tw = tx1 - tx0, th = ty1 - ty0;
-
-    // ---- placement descriptors -> shared memory (one coalesced pass), canvas tile -> shared memory ----
-    {
-        const int n0 = min(cv.count, kDescCache);
-        const uint32_t *g = reinterpret_cast<const uint32_t *>(placements + cv.first);
-        for (int i = threadIdx.x; i < n0 * kDescWords; i += kThreads) desc_words[i] = __ldg(g + i);
+    int n = 1;
+    for (int i = 0; i < cv.count; ++i) {
+        const DevPlacementT &d = placements[cv.first + i];
+        const int x = __ldg(&d.x), y = __ldg(&d.y), w = __ldg(&d.w), h = __ldg(&d.h);
+        n += (max(tx0, x) < min(tx1, x + w) && max(ty0, y) < min(ty1, y + h)) ? 1 : 0;
     }
-    // the background tile streams in asynchronously (cp.async); it is first needed by an over step
-    {
-        const int xx = threadIdx.x & (kTileW - 1), y0 = threadIdx.x / kTileW;  // 4 rows per sweep
-        const uint8_t *g = cv.bg + (int64_t)(ty0 + y0) * cv.bg_pitch + (int64_t)(tx0 + xx) * 4;
-        uint32_t *d = ctile + y0 * kCtPitch + xx;
-        const int64_t gstep = (int64_t)(kThreads / kTileW) * cv.bg_pitch;
-        if (xx < tw) {
-#pragma unroll
-            for (int k = 0; k < (kTileH + kThreads / kTileW - 1) / (kThreads / kTileW); ++k) {
-                if (y0 + k * (kThreads / kTileW) < th) {
-                    if (cv.bg) cp_async4(d, g); else *d = cv.solid;
-                }
-                g += gstep;
-                d += (kThreads / kTileW) * kCtPitch;
-            }
+    const int64_t t = cv.tile_base - run_tile_base + local;
+    cnt[(t % G) * K + t / G] = n;
+}
+
+// exclusive scan of every stream's row (in place), stream offsets, END records.  One block, thread = stream.
+__global__ void __launch_bounds__(1024)
+bin_scan_kernel(int32_t *__restrict__ cnt, int G, int K, int64_t n_tiles, int64_t *__restrict__ stream_off,
+                Cmd *__restrict__ streams, int64_t capacity, int *__restrict__ status) {
+    __shared__ int64_t lens[1024];
+    const int c = threadIdx.x;
+    int64_t len = 0;
+    if (c < G) {
+        const int64_t nk = n_tiles > c ? (n_tiles - c + G - 1) / G : 0;
+        int32_t *row = cnt + (int64_t)c * K;
+        int32_t acc = 0;
+        for (int64_t k = 0; k < nk; ++k) {
+            const int32_t v = row[k];
+            row[k] = acc;
+            acc += v;
         }
+        len = (int64_t)acc + 1;  // + END
+    }
+    lens[c] = len;
+    __syncthreads();
+    if (c == 0) {
+        int64_t a = 0;
+        for (int i = 0; i < G; ++i) {
+            const int64_t t = lens[i];
+            lens[i] = a;
+            a += t;
+        }
+        stream_off[G] = a;
+        if (a > capacity) atomicOr(status, kStatusStreamOverflow);
     }
     __syncthreads();
-    const DevPlacementT *desc = reinterpret_cast<const DevPlacementT *>(desc_words);
-    if (threadIdx.x == 0) {
-        mbar_init(&tma_bar, 1);
-        alpha_bits[0] = 0u;
-        alpha_bits[1] = 0u;
+    if (c < G) {
+        stream_off[c] = lens[c];
+        const int64_t e = lens[c] + len - 1;
+        if (e < capacity) streams[e].w[0] = kCmdEnd;
     }
-    uint32_t n_res = 0;  // resampled placements seen so far (selects the alpha_bits slot)
-    uint32_t tma_phase = 0;  // parity of the next TMA completion to wait for
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+}
 
-    // Geometry of a resampled placement on this tile; all threads compute it (cheap, no memory).
-    struct Geo {
-        int ix0, iy0, two, tho, ox0, oy0, cw0, rw0, NRQ, bq0, bq1;
-    };
-    auto geometry = [&](const DevPlacementT &d) {
-        Geo g;
-        g.ix0 = max(tx0, d.x);
-        g.iy0 = max(ty0, d.y);
-        const int ix1 = min(tx1, d.x + d.w), iy1 = min(ty1, d.y + d.h);
-        g.two = ix1 - g.ix0;
-        g.tho = iy1 - g.iy0;
-        g.ox0 = g.ix0 - d.x;
-        g.oy0 = g.iy0 - d.y;
-        const int w_first = first_tap(g.ox0, d.scale_x, d.support_x) >> 2;
-        const int w_last = (first_tap(ix1 - 1 - d.x, d.scale_x, d.support_x) >> 2) + d.nwx - 1;
-        g.bq0 = w_first >> 2;                   // alpha summary blocks (4 words) the patch touches
-        g.bq1 = min(w_last >> 2, d.wq - 1);
-        g.cw0 = w_first & ~3;  // TMA boxes start on 16-byte boundaries
-        g.rw0 = first_tap(g.oy0, d.scale_y, d.support_y) >> 2;
-        g.NRQ = (first_tap(iy1 - 1 - d.y, d.scale_y, d.support_y) >> 2) + d.nwy - g.rw0;
-        return g;
-    };
-    // one elected thread starts the TMA of placement `d`'s source patch into P
-    auto issue_patch = [&](const DevPlacementT &d) {
-        const Geo g = geometry(d);
-        mbar_expect_tx(&tma_bar, (uint32_t)d.pbw * (uint32_t)d.nrbox * 4u);
-        tma_load_patch(P, d.tmap, g.cw0, 4 * g.rw0, &tma_bar);
-    };
+// Geometry of a resampled placement on a tile (identical doubles to the host table builder).
+struct Geo {
+    int ix0, iy0, two, tho, ox0, oy0, cw0, rw0, NRQ, bq0, bq1;
+};
+__device__ __forceinline__ Geo tile_geometry(const DevPlacementT &d, int tx0, int ty0, int tx1, int ty1) {
+    Geo g;
+    g.ix0 = max(tx0, d.x);
+    g.iy0 = max(ty0, d.y);
+    const int ix1 = min(tx1, d.x + d.w), iy1 = min(ty1, d.y + d.h);
+    g.two = ix1 - g.ix0;
+    g.tho = iy1 - g.iy0;
+    g.ox0 = g.ix0 - d.x;
+    g.oy0 = g.iy0 - d.y;
+    const int w_first = first_tap(g.ox0, d.scale_x, d.support_x) >> 2;
+    const int w_last = (first_tap(ix1 - 1 - d.x, d.scale_x, d.support_x) >> 2) + d.nwx - 1;
+    g.bq0 = w_first >> 2;  // alpha summary blocks (4 words) the patch touches
+    g.bq1 = min(w_last >> 2, d.wq - 1);
+    g.cw0 = w_first & ~3;  // TMA boxes start on 16-byte boundaries
+    g.rw0 = first_tap(g.oy0, d.scale_y, d.support_y) >> 2;
+    g.NRQ = (first_tap(iy1 - 1 - d.y, d.scale_y, d.support_y) >> 2) + d.nwy - g.rw0;
+    return g;
+}
 
-    // ---- z-order walk, kDescCache placements at a time ----
-    for (int group = 0; group < cv.count; group += kDescCache) {
-        const int n_cached = min(cv.count - group, kDescCache);
-        if (group > 0) {
-            __syncthreads();  // everyone is done with the previous group's descriptors
-            const uint32_t *g = reinterpret_cast<const uint32_t *>(placements + cv.first + group);
-            for (int i = threadIdx.x; i < n_cached * kDescWords; i += kThreads) desc_words[i] = __ldg(g + i);
-            __syncthreads();
-        }
-        // which cached placements touch this tile -> ordered hit list
-        if (threadIdx.x < kDescCache) {
-            bool hit = false;
-            if ((int)threadIdx.x < n_cached) {
-                const DevPlacementT &d = desc[threadIdx.x];
-                hit = max(tx0, d.x) < min(tx1, d.x + d.w) && max(ty0, d.y) < min(ty1, d.y + d.h);
+__device__ __forceinline__ void store_cmd(Cmd *dst, const uint32_t (&w)[16]) {
+    uint4 *q = reinterpret_cast<uint4 *>(dst);
+    q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    q[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    q[3] = make_uint4(w[12], w[13], w[14], w[15]);
+}
+
+// fill: thread = tile.  Writes the TILE record and one record per touching placement, in z-order:
+// resample steps carry the tile geometry and the OR of the alpha summary over the source patch (fully
+// transparent patches become NOPs, fully opaque ones skip the alpha plane in the tile kernel).
+__global__ void __launch_bounds__(128)
+bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPlacementT *__restrict__ placements,
+                int64_t run_tile_base, int G, int K, const int32_t *__restrict__ scan,
+                const int64_t *__restrict__ stream_off, Cmd *__restrict__ streams, int64_t capacity,
+                const uint8_t *__restrict__ maps_base, const uint32_t *__restrict__ tables_base, int patch_words,
+                int inter_words, int *__restrict__ status) {
+    const DevCanvas &cv = canvases[blockIdx.y];
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= cv.tiles_x * cv.tiles_y) return;
+    const int ty = local / cv.tiles_x, tx = local - ty * cv.tiles_x;
+    const int tx0 = tx * kTileW, ty0 = ty * kTileH;
+    const int tx1 = min(cv.W, tx0 + kTileW), ty1 = min(cv.H, ty0 + kTileH);
+    const int64_t t = cv.tile_base - run_tile_base + local;
+    const int64_t base = stream_off[t % G] + scan[(t % G) * K + t / G];
+    int n_slots = 0, n_steps = 0;
+    uint32_t w[16];
+    for (int i = 0; i < cv.count; ++i) {
+        const DevPlacementT &d = placements[cv.first + i];
+        if (!(max(tx0, d.x) < min(tx1, d.x + d.w) && max(ty0, d.y) < min(ty1, d.y + d.h))) continue;
+        ++n_slots;
+        const int64_t at = base + n_slots;
+        if (at >= capacity) continue;  // flagged by the scan kernel
+#pragma unroll
+        for (int k = 0; k < 16; ++k) w[k] = 0u;
+        w[0] = kCmdNop;
+        if (d.mode == 0) {
+            const int ix0 = max(tx0, d.x), iy0 = max(ty0, d.y);
+            const int two = min(tx1, d.x + d.w) - ix0, tho = min(ty1, d.y + d.h) - iy0;
+            w[2] = (uint32_t)(ix0 - tx0) | ((uint32_t)(iy0 - ty0) << 8) | ((uint32_t)two << 16) | ((uint32_t)tho << 24);
+            if (d.tmap) {
+                // TMA boxes start on 16-byte boundaries: the box begins up to 3 pixels left of the tile
+                // origin (w5 = that shift) and is kOverlayBoxW = 68 pixels wide
+                w[0] = kCmdIdentTma;
+                const int cx = tx0 - d.x;
+                w[3] = (uint32_t)(cx & ~3);
+                w[5] = (uint32_t)(cx & 3);
+                w[4] = (uint32_t)(ty0 - d.y);
+                w[8] = (uint32_t)((reinterpret_cast<const uint8_t *>(d.tmap) - maps_base) >> 7);
+            } else {
+                w[0] = kCmdIdentLdg;
+                w[3] = (uint32_t)(ix0 - d.x);
+                w[4] = (uint32_t)(iy0 - d.y);
+                w[6] = (uint32_t)d.src_pitch;
+                const uint64_t p = reinterpret_cast<uint64_t>(d.src);
+                w[12] = (uint32_t)p;
+                w[13] = (uint32_t)(p >> 32);
             }
-            const uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) hit_mask[warp] = m;
-        }
-        __syncthreads();
-        if (threadIdx.x < kDescCache) {
-            const uint32_t m0 = hit_mask[0], m1 = hit_mask[1];
-            const uint32_t mine = warp == 0 ? m0 : m1;
-            if ((mine >> lane) & 1u)
-                hit_list[(warp == 0 ? 0 : __popc(m0)) + __popc(mine & ((1u << lane) - 1u))] = (uint8_t)threadIdx.x;
-        }
-        const int n_hits = __popc(hit_mask[0]) + __popc(hit_mask[1]);
-        __syncthreads();
-        // first resampled placement of the group: start its TMA now
-        int next_res = 0;
-        while (next_res < n_hits && desc[hit_list[next_res]].mode == 0) ++next_res;
-        if (next_res < n_hits && threadIdx.x == 0) issue_patch(desc[hit_list[next_res]]);
-
-        for (int k = 0; k < n_hits; ++k) {
-            const DevPlacementT &d = desc[hit_list[k]];
-            if (d.mode == 0) {
-                // identity-size placement: plain over straight from the cutout
-                const int ix0 = max(tx0, d.x), iy0 = max(ty0, d.y);
-                const int two = min(tx1, d.x + d.w) - ix0, tho = min(ty1, d.y + d.h) - iy0;
-                cp_async_wait_all();
-                __syncthreads();
-                const int xx = threadIdx.x & (kTileW - 1);
-                if (xx < two) {
-                    for (int yy = threadIdx.x / kTileW; yy < tho; yy += kThreads / kTileW) {
-                        const uint32_t s = ld_px(d.src, (int64_t)(iy0 + yy - d.y) * d.src_pitch + (int64_t)(ix0 + xx - d.x) * 4);
-                        uint32_t *c = ctile + (iy0 + yy - ty0) * kCtPitch + (ix0 + xx - tx0);
-                        *c = over_px(*c, s);
-                    }
-                }
-                __syncthreads();
-                continue;
-            }
-            const Geo g = geometry(d);
+            ++n_steps;
+        } else {
+            const Geo g = tile_geometry(d, tx0, ty0, tx1, ty1);
             const int IPW = g.NRQ | 1;
-            const int iplane_stride = kTileW * IPW;
-            const bool fits = d.pbw * d.nrbox <= patch_words && 4 * iplane_stride <= inter_words && 4 * g.NRQ <= d.nrbox;
-            if (!fits && threadIdx.x == 0) atomicOr(status, kStatusPatchOverflow);  // host sizing bug: flagged
-            // alpha summary of the patch (global loads overlap the TMA already in flight)
-            {
+            const bool fits = d.pbw * d.nrbox <= patch_words && 4 * kTileW * IPW <= inter_words && 4 * g.NRQ <= d.nrbox &&
+                              g.cw0 < 65536 && g.rw0 < 65536;
+            if (!fits) {
+                atomicOr(status, kStatusPatchOverflow);  // host sizing bug: flagged, step dropped
+            } else {
                 const int nbw = g.bq1 - g.bq0 + 1;
                 const int rq1 = min(g.rw0 + g.NRQ, d.sh4);
-                const int nb = nbw * (rq1 - g.rw0);
                 uint32_t bits = 0u;
-                for (int i = threadIdx.x; i < nb; i += kThreads) {
-                    const int br = i / nbw, bc = i - br * nbw;
-                    bits |= __ldg(d.flags + (int64_t)(g.rw0 + br) * d.wq + g.bq0 + bc);
+                for (int br = g.rw0; br < rq1; ++br) {
+                    const uint32_t *fr = d.flags + (int64_t)br * d.wq + g.bq0;
+                    for (int bc = 0; bc < nbw; ++bc) bits |= __ldg(fr + bc);
                 }
-                bits = __reduce_or_sync(0xffffffffu, bits);
-                if (lane == 0 && bits) atomicOr(&alpha_bits[n_res & 1u], bits);
-                if (threadIdx.x == 0) alpha_bits[(n_res + 1u) & 1u] = 0u;  // slot of the next resampled placement
+                if (bits & 1u) {  // otherwise nothing but alpha 0: the canvas does not change
+                    w[0] = kCmdResample;
+                    w[1] = (uint32_t)d.nwx | ((uint32_t)d.nwy << 8) | ((bits & 2u) ? (4u << 16) : (3u << 16)) | ((uint32_t)g.NRQ << 24);
+                    w[2] = (uint32_t)(g.ix0 - tx0) | ((uint32_t)(g.iy0 - ty0) << 8) | ((uint32_t)g.two << 16) | ((uint32_t)g.tho << 24);
+                    w[3] = (uint32_t)g.ox0;
+                    w[4] = (uint32_t)g.oy0;
+                    w[5] = (uint32_t)g.cw0 | ((uint32_t)g.rw0 << 16);
+                    w[6] = (uint32_t)d.w;
+                    w[7] = (uint32_t)d.h;
+                    w[8] = (uint32_t)((reinterpret_cast<const uint8_t *>(d.tmap) - maps_base) >> 7);
+                    w[9] = (uint32_t)(d.plx - tables_base);
+                    w[10] = (uint32_t)(d.ply - tables_base);
+                    w[11] = (uint32_t)d.pbw | ((uint32_t)d.nrbox << 16);
+                    const uint64_t sx = (uint64_t)__double_as_longlong(d.scale_x), sy = (uint64_t)__double_as_longlong(d.scale_y);
+                    w[12] = (uint32_t)sx; w[13] = (uint32_t)(sx >> 32);
+                    w[14] = (uint32_t)sy; w[15] = (uint32_t)(sy >> 32);
+                    ++n_steps;
+                }
             }
-            // coefficient rows -> L1 while the patch is in flight
-            if (warp < 2 && warp * 32 + lane < g.two) prefetch_coeffs(d.plx, d.nwx, d.w, g.ox0 + warp * 32 + lane);
-            if (warp == 2 && lane < g.tho) prefetch_coeffs(d.ply, d.nwy, d.h, g.oy0 + lane);
-            mbar_wait(&tma_bar, tma_phase);  // source patch has landed in P
-            tma_phase ^= 1u;
-            __syncthreads();  // alpha_bits complete; everyone has consumed this TMA phase
-            const uint32_t abits = alpha_bits[n_res & 1u];
-            ++n_res;
-            const bool transparent = (abits & 1u) == 0u;  // nothing but alpha 0: the canvas does not change
-            const int nch = (abits & 2u) ? 4 : 3;         // every alpha 255: skip the alpha plane
-            if (transparent) {
-                next_res = k + 1;
-                while (next_res < n_hits && desc[hit_list[next_res]].mode == 0) ++next_res;
-                if (next_res < n_hits && threadIdx.x == 0) issue_patch(desc[hit_list[next_res]]);
-                __syncthreads();  // everyone has read alpha_bits before its slot is recycled
-                continue;
-            }
-            if (fits) {
-                if (d.nwx == 3)
-                    tile_hpass<3>(P, d.pbw, I, iplane_stride, IPW, g.NRQ, g.cw0, g.ox0, g.two, d.scale_x, d.support_x, d.plx, d.w, nch);
-                else if (d.nwx == 4)
-                    tile_hpass<4>(P, d.pbw, I, iplane_stride, IPW, g.NRQ, g.cw0, g.ox0, g.two, d.scale_x, d.support_x, d.plx, d.w, nch);
-                else
-                    tile_hpass<5>(P, d.pbw, I, iplane_stride, IPW, g.NRQ, g.cw0, g.ox0, g.two, d.scale_x, d.support_x, d.plx, d.w, nch);
-            }
-            cp_async_wait_all();  // background tile (no-op after the first over)
-            __syncthreads();      // H pass done: P is free, I is complete
-            // next resampled placement: its patch streams in while this one runs its V pass
-            next_res = k + 1;
-            while (next_res < n_hits && desc[hit_list[next_res]].mode == 0) ++next_res;
-            if (next_res < n_hits && threadIdx.x == 0) issue_patch(desc[hit_list[next_res]]);
-            if (fits) {
-                if (d.nwy == 3)
-                    tile_vpass_over<3>(I, iplane_stride, IPW, ctile, g.rw0, g.oy0, g.tho, g.two, g.ix0 - tx0, g.iy0 - ty0, d.scale_y, d.support_y, d.ply, d.h, nch);
-                else if (d.nwy == 4)
-                    tile_vpass_over<4>(I, iplane_stride, IPW, ctile, g.rw0, g.oy0, g.tho, g.two, g.ix0 - tx0, g.iy0 - ty0, d.scale_y, d.support_y, d.ply, d.h, nch);
-                else
-                    tile_vpass_over<5>(I, iplane_stride, IPW, ctile, g.rw0, g.oy0, g.tho, g.two, g.ix0 - tx0, g.iy0 - ty0, d.scale_y, d.support_y, d.ply, d.h, nch);
-            }
-            __syncthreads();
+        }
+        store_cmd(streams + at, w);
+    }
+    if (base >= capacity) return;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w[k] = 0u;
+    w[0] = kCmdTile;
+    w[1] = (uint32_t)n_steps;
+    w[2] = (uint32_t)tx0;
+    w[3] = (uint32_t)ty0;
+    w[4] = (uint32_t)(tx1 - tx0) | ((uint32_t)(ty1 - ty0) << 16);
+    w[5] = cv.solid;
+    w[6] = (cv.bg ? kTileHasBg : 0u) | (cv.bg && cv.bg_map ? kTileBgTma : 0u) | (cv.out_map ? kTileOutTma : 0u);
+    w[7] = (uint32_t)(canvas0 + (int)blockIdx.y);
+    const uint64_t bm = reinterpret_cast<uint64_t>(cv.bg_map), om = reinterpret_cast<uint64_t>(cv.out_map);
+    w[8] = (uint32_t)bm; w[9] = (uint32_t)(bm >> 32);
+    w[10] = (uint32_t)om; w[11] = (uint32_t)(om >> 32);
+    store_cmd(streams + base, w);
+}
+
+// ---- the persistent tile kernel ------------------------------------------------------------------
+// CTA c consumes command stream c.  Everything it touches arrives asynchronously and ahead of use:
+//   * command records: cp.async into an 8-slot ring, 6 records ahead
+//   * background tiles: TMA (two 32x32-pixel boxes, 128-byte swizzle) into one of kTileBufs resident
+//     tile buffers, up to two tiles ahead; finished tiles leave through TMA stores (bulk groups)
+//   * source patches: one TMA box per step, issued as soon as the previous step's horizontal pass has
+//     released the patch buffer -- also across tile boundaries
+// Thread 0 is the producer (it only issues copies; it never waits for data on behalf of others).
+__global__ void __launch_bounds__(kThreads, 2)
+composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict__ stream_off,
+                        const DevCanvas *__restrict__ canvases, const uint8_t *__restrict__ maps,
+                        const uint32_t *__restrict__ tables, int patch_words, int inter_words) {
+    extern __shared__ uint32_t smem_raw[];
+    // tile buffers need 1024-byte alignment (swizzle atom); the launch reserves the slack
+    uint32_t *ctile = reinterpret_cast<uint32_t *>(
+        reinterpret_cast<uint8_t *>(smem_raw) + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    uint32_t *P = ctile + kTileBufs * kTileWords;  // patch_words (multiple of 32 words: stays 128-byte aligned)
+    uint32_t *I = P + patch_words;                 // inter_words
+    Cmd *ring = reinterpret_cast<Cmd *>(I + inter_words);
+    uint64_t *bg_full = reinterpret_cast<uint64_t *>(ring + kRing);
+    uint64_t *patch_full = bg_full + kTileBufs;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Cmd *stream = streams + stream_off[blockIdx.x];
+
+    if (tid == 0) {
+        for (int b = 0; b < kTileBufs; ++b) mbar_init(&bg_full[b], 1);
+        mbar_init(patch_full, 1);
+    }
+    if (tid < 4) {  // ring prologue: records 0 .. kRingAhead-1, one group each
+#pragma unroll
+        for (int i = 0; i < kRingAhead; ++i) {
+            cp_async16(reinterpret_cast<uint8_t *>(ring + i) + 16 * tid, reinterpret_cast<const uint8_t *>(stream + i) + 16 * tid);
+            cp_async_commit();
         }
     }
 
-    // ---- write the tile once ----
-    cp_async_wait_all();
-    __syncthreads();
-    if (tw == kTileW && ((reinterpret_cast<uintptr_t>(cv.out) | (uintptr_t)cv.out_pitch) & 15u) == 0) {
-        // full-width tile, 16-byte aligned rows: one 128-bit store per 4 pixels
-        constexpr int kRows = kThreads / 16;  // rows per sweep
-        const int x4 = (threadIdx.x & 15) * 4, y0 = threadIdx.x >> 4;
-        uint8_t *g = cv.out + (int64_t)(ty0 + y0) * cv.out_pitch + (int64_t)(tx0 + x4) * 4;
-        const uint32_t *c = ctile + y0 * kCtPitch + x4;
-#pragma unroll
-        for (int k = 0; k < (kTileH + kRows - 1) / kRows; ++k) {
-            if (y0 + kRows * k < th)
-                *reinterpret_cast<uint4 *>(g) = make_uint4(c[0], c[1], c[2], c[3]);
-            g += (int64_t)kRows * cv.out_pitch;
-            c += kRows * kCtPitch;
+    // consumer state (uniform across the CTA)
+    int pos = 0;          // record being consumed
+    int ctseq = -1;       // sequence number of the current tile (buffer ctseq % kTileBufs)
+    uint32_t pseq = 0;    // patches consumed so far (parity of patch_full)
+    int steps_left = 0;
+    bool bg_pending = false;
+    int c_tx0 = 0, c_ty0 = 0, c_tw = 0, c_th = 0;
+    uint32_t c_flags = 0, c_canvas = 0;
+    const void *c_out_map = nullptr;
+    // producer state (thread 0)
+    int ppos = 0, ptseq = 0;
+    bool patch_busy = false, p_done = false;
+
+    auto producer_advance = [&](int limit) {
+        while (!p_done && ppos <= limit) {
+            const Cmd &c = ring[ppos & (kRing - 1)];
+            const uint32_t kind = c.w[0];
+            if (kind == kCmdTile) {
+                if (ptseq - ctseq > kTileBufs - 2) break;  // no free tile buffer yet
+                if (c.w[6] & kTileBgTma) {
+                    const int b = ptseq & (kTileBufs - 1);
+                    const int tw = (int)(c.w[4] & 0xffffu);
+                    const void *map = reinterpret_cast<const void *>((uint64_t)c.w[8] | ((uint64_t)c.w[9] << 32));
+                    bulk_wait_read<1>();  // the store that last read this buffer (kTileBufs tiles ago) is done
+                    fence_async_smem();
+                    mbar_expect_tx(&bg_full[b], tw > 32 ? 8192u : 4096u);
+                    tma_load_2d(ctile + b * kTileWords, map, (int)c.w[2], (int)c.w[3], &bg_full[b]);
+                    if (tw > 32) tma_load_2d(ctile + b * kTileWords + 1024, map, (int)c.w[2] + 32, (int)c.w[3], &bg_full[b]);
+                }
+                ++ptseq;
+            } else if (kind == kCmdResample) {
+                if (patch_busy) break;
+                mbar_expect_tx(patch_full, (c.w[11] & 0xffffu) * (c.w[11] >> 16) * 4u);
+                tma_load_patch(P, maps + ((uint64_t)c.w[8] << 7), (int)(c.w[5] & 0xffffu), 4 * (int)(c.w[5] >> 16), patch_full);
+                patch_busy = true;
+            } else if (kind == kCmdIdentTma) {
+                if (patch_busy) break;
+                fence_async_smem();
+                mbar_expect_tx(patch_full, (uint32_t)(kOverlayBoxW * kTileH) * 4u);
+                tma_load_2d(P, maps + ((uint64_t)c.w[8] << 7), (int)c.w[3], (int)c.w[4], patch_full);
+                patch_busy = true;
+            } else if (kind == kCmdEnd) {
+                p_done = true;
+                break;
+            }
+            ++ppos;
         }
-    } else {
-        const int xx = threadIdx.x & (kTileW - 1);
-        if (xx < tw)
-            for (int yy = threadIdx.x / kTileW; yy < th; yy += kThreads / kTileW)
-                *reinterpret_cast<uint32_t *>(cv.out + (int64_t)(ty0 + yy) * cv.out_pitch + (int64_t)(tx0 + xx) * 4) =
-                    ctile[yy * kCtPitch + xx];
+    };
+
+    // all threads: the tile's pixels are final -> write it out (TMA store, or generic stores)
+    auto finish_tile = [&]() {
+        uint32_t *ct = ctile + (ctseq & (kTileBufs - 1)) * kTileWords;
+        if (bg_pending) {
+            mbar_wait(&bg_full[ctseq & (kTileBufs - 1)], (uint32_t)(ctseq / kTileBufs) & 1u);
+            bg_pending = false;
+        }
+        if (c_flags & kTileOutTma) {
+            fence_async_smem();  // generic writes to the tile -> visible to the async proxy
+            __syncthreads();
+            if (tid == 0) {
+                tma_store_2d(c_out_map, c_tx0, c_ty0, ct);
+                if (c_tw > 32) tma_store_2d(c_out_map, c_tx0 + 32, c_ty0, ct + 1024);
+                bulk_commit();
+            }
+        } else {
+            __syncthreads();
+            const DevCanvas &cv = canvases[c_canvas];
+            uint8_t *out = cv.out;
+            const int64_t pitch = cv.out_pitch;
+            const int xx = tid & (kTileW - 1);
+            if (xx < c_tw)
+                for (int yy = tid / kTileW; yy < c_th; yy += kThreads / kTileW)
+                    *reinterpret_cast<uint32_t *>(out + (int64_t)(c_ty0 + yy) * pitch + (int64_t)(c_tx0 + xx) * 4) = ct[ct_off(yy, xx)];
+            if (tid == 0) bulk_commit();  // every tile is one bulk group, so the group counting stays uniform
+        }
+    };
+
+    for (;;) {
+        if (tid < 4) {
+            cp_async_wait<kRingAhead - 1 - kLook>();  // records <= pos + kLook have landed
+            cp_async16(reinterpret_cast<uint8_t *>(ring + ((pos + kRingAhead) & (kRing - 1))) + 16 * tid,
+                       reinterpret_cast<const uint8_t *>(stream + pos + kRingAhead) + 16 * tid);
+            cp_async_commit();
+        }
+        __syncthreads();  // (A) ring visible; every thread is done with the previous record
+        const Cmd &cmd = ring[pos & (kRing - 1)];
+        const uint32_t kind = cmd.w[0];
+        if (kind == kCmdEnd) break;
+        if (tid == 0) producer_advance(pos + kLook);
+        if (kind == kCmdNop) {
+            ++pos;
+            continue;
+        }
+        if (kind == kCmdTile) {
+            ++ctseq;
+            steps_left = (int)cmd.w[1];
+            c_tx0 = (int)cmd.w[2];
+            c_ty0 = (int)cmd.w[3];
+            c_tw = (int)(cmd.w[4] & 0xffffu);
+            c_th = (int)(cmd.w[4] >> 16);
+            c_flags = cmd.w[6];
+            c_canvas = cmd.w[7];
+            c_out_map = reinterpret_cast<const void *>((uint64_t)cmd.w[10] | ((uint64_t)cmd.w[11] << 32));
+            if (c_flags & kTileBgTma) {
+                bg_pending = true;
+            } else {
+                // solid colour, or a background TMA cannot address: fill the buffer here
+                const uint32_t solid = cmd.w[5];
+                if (tid == 0) bulk_wait_read<kTileBufs - 1>();  // the store that last read this buffer is done
+                __syncthreads();
+                uint32_t *ct = ctile + (ctseq & (kTileBufs - 1)) * kTileWords;
+                const int xx = tid & (kTileW - 1);
+                if (c_flags & kTileHasBg) {
+                    const DevCanvas &cv = canvases[c_canvas];
+                    const uint8_t *bg = cv.bg;
+                    const int64_t pitch = cv.bg_pitch;
+                    if (xx < c_tw)
+                        for (int yy = tid / kTileW; yy < c_th; yy += kThreads / kTileW)
+                            ct[ct_off(yy, xx)] = ld_px(bg, (int64_t)(c_ty0 + yy) * pitch + (int64_t)(c_tx0 + xx) * 4);
+                } else {
+                    for (int yy = tid / kTileW; yy < kTileH; yy += kThreads / kTileW) ct[ct_off(yy, xx)] = solid;
+                }
+                bg_pending = false;
+            }
+            if (steps_left == 0) finish_tile();
+            ++pos;
+            continue;
+        }
+        uint32_t *ct = ctile + (ctseq & (kTileBufs - 1)) * kTileWords;
+        const int dx = (int)(cmd.w[2] & 0xffu), dy = (int)((cmd.w[2] >> 8) & 0xffu);
+        const int two = (int)((cmd.w[2] >> 16) & 0xffu), tho = (int)(cmd.w[2] >> 24);
+        if (kind == kCmdResample) {
+            const int nwx = (int)(cmd.w[1] & 0xffu), nwy = (int)((cmd.w[1] >> 8) & 0xffu);
+            const int nch = (int)((cmd.w[1] >> 16) & 0xffu), NRQ = (int)(cmd.w[1] >> 24);
+            const int ox0 = (int)cmd.w[3], oy0 = (int)cmd.w[4];
+            const int cw0 = (int)(cmd.w[5] & 0xffffu), rw0 = (int)(cmd.w[5] >> 16);
+            const int n_out_x = (int)cmd.w[6], n_out_y = (int)cmd.w[7];
+            const uint32_t *plx = tables + cmd.w[9], *ply = tables + cmd.w[10];
+            const int pbw = (int)(cmd.w[11] & 0xffffu);
+            const double scale_x = __longlong_as_double((long long)((uint64_t)cmd.w[12] | ((uint64_t)cmd.w[13] << 32)));
+            const double scale_y = __longlong_as_double((long long)((uint64_t)cmd.w[14] | ((uint64_t)cmd.w[15] << 32)));
+            // a skipped pass is the 1-tap identity: scale 1, support 1 -> first tap = the sample itself
+            const double support_x = scale_x == 1.0 ? 1.0 : __dmul_rn(3.0, fmax(scale_x, 1.0));
+            const double support_y = scale_y == 1.0 ? 1.0 : __dmul_rn(3.0, fmax(scale_y, 1.0));
+            const int IPW = NRQ | 1;
+            const int iplane_stride = kTileW * IPW;
+            // coefficient rows -> L1 while the patch is in flight
+            if (warp < 2 && warp * 32 + lane < two) prefetch_coeffs(plx, nwx, n_out_x, ox0 + warp * 32 + lane);
+            if (warp == 2 && lane < tho) prefetch_coeffs(ply, nwy, n_out_y, oy0 + lane);
+            mbar_wait(patch_full, pseq & 1u);  // source patch has landed in P
+            ++pseq;
+            if (nwx == 3)
+                tile_hpass<3>(P, pbw, I, iplane_stride, IPW, NRQ, cw0, ox0, two, scale_x, support_x, plx, n_out_x, nch);
+            else if (nwx == 4)
+                tile_hpass<4>(P, pbw, I, iplane_stride, IPW, NRQ, cw0, ox0, two, scale_x, support_x, plx, n_out_x, nch);
+            else
+                tile_hpass<5>(P, pbw, I, iplane_stride, IPW, NRQ, cw0, ox0, two, scale_x, support_x, plx, n_out_x, nch);
+            __syncthreads();  // (B) H pass done: P is free, I is complete
+            if (tid == 0) {
+                patch_busy = false;
+                producer_advance(pos + kLook);  // the next patch streams in during this V pass
+            }
+            if (bg_pending) {
+                mbar_wait(&bg_full[ctseq & (kTileBufs - 1)], (uint32_t)(ctseq / kTileBufs) & 1u);
+                bg_pending = false;
+            }
+            if (nwy == 3)
+                tile_vpass_over<3>(I, iplane_stride, IPW, ct, rw0, oy0, tho, two, dx, dy, scale_y, support_y, ply, n_out_y, nch);
+            else if (nwy == 4)
+                tile_vpass_over<4>(I, iplane_stride, IPW, ct, rw0, oy0, tho, two, dx, dy, scale_y, support_y, ply, n_out_y, nch);
+            else
+                tile_vpass_over<5>(I, iplane_stride, IPW, ct, rw0, oy0, tho, two, dx, dy, scale_y, support_y, ply, n_out_y, nch);
+        } else if (kind == kCmdIdentTma) {
+            // identity-size overlay: P holds the 64x32 source pixels under this tile (zero outside the overlay)
+            mbar_wait(patch_full, pseq & 1u);
+            ++pseq;
+            if (bg_pending) {
+                mbar_wait(&bg_full[ctseq & (kTileBufs - 1)], (uint32_t)(ctseq / kTileBufs) & 1u);
+                bg_pending = false;
+            }
+            const int xx = tid & (kTileW - 1);
+            const int shift = (int)cmd.w[5];
+            if (xx >= dx && xx < dx + two)
+                for (int yy = dy + tid / kTileW; yy < dy + tho; yy += kThreads / kTileW) {
+                    uint32_t *c = ct + ct_off(yy, xx);
+                    *c = over_px(*c, P[yy * kOverlayBoxW + xx + shift]);
+                }
+            __syncthreads();  // (B) P is free
+            if (tid == 0) {
+                patch_busy = false;
+                producer_advance(pos + kLook);
+            }
+        } else {  // kCmdIdentLdg: overlay read with plain loads (source not addressable by TMA)
+            if (bg_pending) {
+                mbar_wait(&bg_full[ctseq & (kTileBufs - 1)], (uint32_t)(ctseq / kTileBufs) & 1u);
+                bg_pending = false;
+            }
+            const uint8_t *src = reinterpret_cast<const uint8_t *>((uint64_t)cmd.w[12] | ((uint64_t)cmd.w[13] << 32));
+            const int64_t spitch = (int64_t)cmd.w[6];
+            const int sx0 = (int)cmd.w[3], sy0 = (int)cmd.w[4];
+            const int xx = tid & (kTileW - 1);
+            if (xx < two)
+                for (int yy = tid / kTileW; yy < tho; yy += kThreads / kTileW) {
+                    const uint32_t s = ld_px(src, (int64_t)(sy0 + yy) * spitch + (int64_t)(sx0 + xx) * 4);
+                    uint32_t *c = ct + ct_off(dy + yy, dx + xx);
+                    *c = over_px(*c, s);
+                }
+        }
+        if (--steps_left == 0) finish_tile();
+        ++pos;
     }
+    if (tid < 4) cp_async_wait<0>();
+    if (tid == 0) bulk_wait_all();  // stores still reading shared memory
 }
 
 }  // namespace b200comp
