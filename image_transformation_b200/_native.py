@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, c_char_p, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "_lib", "libb200comp.so")
+# B200COMP_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("B200COMP_LIB") or os.path.join(_PKG, "_lib", "libb200comp.so")
 
 # every symbol include/b200comp.h declares (tests check the library exports all of them)
 EXPORTED = (

@@ -494,7 +494,7 @@ static const size_t kFusedSmemCap = 112 * 1024;    // placements needing more go
 // command ring + mbarriers
 static size_t tile_smem_bytes(int64_t patch_words, int64_t inter_words) {
     return 1024 + ((size_t)kTileBufs * kTileWords + (size_t)patch_words + (size_t)inter_words) * 4 + kRing * sizeof(Cmd) +
-           (kTileBufs + 1) * sizeof(uint64_t);
+           (kTileBufs + 1) * sizeof(uint64_t) + 36 * sizeof(uint32_t);
 }
 static_assert(sizeof(b200comp_placement) == 48 && sizeof(b200comp_canvas) == 56, "public struct layout");
 
@@ -1039,6 +1039,8 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
     const int G = plan->G;
     const int K = (int)((n_tiles + G - 1) / G);
     const unsigned gx = (unsigned)((plan->max_tiles + 127) / 128);
+    const unsigned gxf = (unsigned)((plan->max_tiles + kFillWarps - 1) / kFillWarps);
+    unsigned long long *cursor = reinterpret_cast<unsigned long long *>(plan->d_stream_off + G);  // record allocator
     // B200COMP_DEBUG_SYNC=1: synchronise after every launch so a device fault names its kernel
     static const bool debug_sync = std::getenv("B200COMP_DEBUG_SYNC") != nullptr;
     auto checkpoint = [&](const char *what) -> int {
@@ -1050,15 +1052,16 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
     };
     for (int c0 = first; c0 < first + count; c0 += 65535) {  // grid.y is limited to 65535 canvases per launch
         const int nc = std::min(65535, first + count - c0);
-        bin_count_kernel<<<dim3(gx, (unsigned)nc), 128, 0, st>>>(plan->d_canvases + c0, plan->d_placements, tile0, G, K, plan->d_bin);
+        bin_count_kernel<<<dim3(gx, (unsigned)nc), 128, 0, st>>>(plan->d_canvases + c0, plan->d_placements, tile0, G, K, plan->d_bin,
+                                                                 c0 == first ? cursor : nullptr);
     }
     if (int rc = checkpoint("bin_count_kernel")) return rc;
-    bin_scan_kernel<<<1, 1024, 0, st>>>(plan->d_bin, G, K, n_tiles, plan->d_stream_off, plan->d_streams,
-                                        plan->stream_capacity, plan->d_status);
+    bin_scan_kernel<<<(unsigned)((G + 7) / 8), 256, 0, st>>>(plan->d_bin, G, K, n_tiles, plan->d_stream_off, cursor,
+                                                             plan->d_streams, plan->stream_capacity, plan->d_status);
     if (int rc = checkpoint("bin_scan_kernel")) return rc;
     for (int c0 = first; c0 < first + count; c0 += 65535) {
         const int nc = std::min(65535, first + count - c0);
-        bin_fill_kernel<<<dim3(gx, (unsigned)nc), 128, 0, st>>>(
+        bin_fill_kernel<<<dim3(gxf, (unsigned)nc), kFillWarps * 32, 0, st>>>(
             plan->d_canvases + c0, c0, plan->d_placements, tile0, G, K, plan->d_bin, plan->d_stream_off, plan->d_streams,
             plan->stream_capacity, plan->d_maps, reinterpret_cast<const uint32_t *>(plan->d_tables), plan->patch_words,
             plan->inter_words, plan->d_status);
@@ -1088,6 +1091,20 @@ int64_t b200comp_plan_debug_streams_(b200comp_plan *plan, uint32_t *out, int64_t
     const int64_t n = std::min<int64_t>(max_records, std::min<int64_t>(offs[plan->G], plan->stream_capacity));
     cudaMemcpy(out, plan->d_streams, (size_t)n * sizeof(Cmd), cudaMemcpyDeviceToHost);
     return n;
+}
+
+// internal (tools/): phase cycle counters of a -DB200COMP_PROFILE=1 build; reset after reading
+int b200comp_debug_profile_(unsigned long long *out16) {
+#if B200COMP_PROFILE
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_prof, sizeof(unsigned long long) * 16);
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_prof, z, sizeof z);
+    return 0;
+#else
+    (void)out16;
+    return B200COMP_EINVAL;
+#endif
 }
 
 int b200comp_plan_info(const b200comp_plan *plan, int64_t *info) {

@@ -26,8 +26,18 @@ static_assert(sizeof(DevCanvas) == 88, "DevCanvas layout");
 
 constexpr int kTileW = 64;
 constexpr int kTileH = 32;
-constexpr int kThreads = 384;  // 12 warps per CTA, two CTAs per SM (register-limited at 85 / thread)
+#ifndef B200COMP_THREADS
+#define B200COMP_THREADS 384
+#endif
+constexpr int kThreads = B200COMP_THREADS;  // warps per CTA x 32; two CTAs per SM
 constexpr int kWarps = kThreads / 32;
+// The last warp is the producer: its lane 0 issues every asynchronous copy (command ring, TMA loads and stores)
+// and does no pass work, so that bookkeeping never delays the compute warps at a barrier.
+constexpr int kComputeWarps = kWarps - 1;
+constexpr int kComputeThreads = kComputeWarps * 32;
+constexpr int kProducerTid = kComputeThreads;
+constexpr int kRowSweep = kComputeThreads / kTileW;  // tile rows covered per sweep of the element-wise loops
+constexpr int kElemThreads = kRowSweep * kTileW;     // threads taking part in them (whole rows only)
 constexpr int kPrecisionBits = 22;
 constexpr int kTileWords = kTileW * kTileH;  // one resident canvas tile: two 32x32-pixel halves, 128-byte swizzled
 constexpr int kOverlayBoxW = kTileW + 4;       // identity overlays: box widened so its start can be 16-byte aligned

@@ -17,6 +17,10 @@
 #pragma once
 #include "kernels.cuh"
 
+#ifndef B200COMP_HSPLIT
+#define B200COMP_HSPLIT 0  // horizontal pass work unit: 1 = (row quad, channel), 0 = row quad (measured faster)
+#endif
+
 namespace b200comp {
 
 __device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
@@ -24,6 +28,26 @@ __device__ __forceinline__ int32_t dp4a_us(uint32_t a, uint32_t b, int32_t c) {
     int32_t d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
+}
+
+// One output sample of a pass: sum over NW words of (4 samples) x (4 taps held as three byte planes).
+// The planes are chained through the accumulator input -- top plane first, each partial sum moved up one
+// byte (PRMT, not a shift-add: IMAD/LEA would compete with dp4a for the FMA-heavy pipe) -- so no separate
+// recombination is needed: result = sum(s * k) + 2^21 modulo 2^32, exactly Pillow's int accumulator
+// (the rounding term 1 << 21 enters as 32 << 16 in the top plane).
+template <int NW>
+__device__ __forceinline__ int32_t tap_sum(const uint32_t (&wd)[NW], const uint32_t (&k0)[NW], const uint32_t (&k1)[NW],
+                                           const uint32_t (&k2)[NW]) {
+    int32_t t = 32;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) t = dp4a_us(wd[i], k2[i], t);
+    uint32_t u = __byte_perm((uint32_t)t, 0u, 0x2104);  // << 8
+#pragma unroll
+    for (int i = 0; i < NW; ++i) u = dp4a_uu(wd[i], k1[i], u);
+    u = __byte_perm(u, 0u, 0x2104);
+#pragma unroll
+    for (int i = 0; i < NW; ++i) u = dp4a_uu(wd[i], k0[i], u);
+    return (int32_t)u;
 }
 
 // 4 RGBA pixels -> 4 channel words (byte k of each word = pixel k)
@@ -190,9 +214,13 @@ __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int P
     // nch = 3 when every source alpha in the patch is 255: the alpha plane is then 255 after both passes
     // (255 * sum(k) + 2^21 >> 22 == 255 because |sum(k) - 2^22| <= taps) and is not computed
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ncg = (two + 31) >> 5;  // 1 or 2 column groups of 32
-    const int cg = warp % ncg;
-    const int rstep = kWarps / ncg;
+    if (warp >= kComputeWarps) return;
+    // two column groups of 32: the first (kComputeWarps + 1) / 2 warps take columns 0..31, the rest 32..63
+    constexpr int kHalf = (kComputeWarps + 1) / 2;
+    const bool two_groups = two > 32;
+    const int cg = (two_groups && warp >= kHalf) ? 1 : 0;
+    const int wfirst = cg ? warp - kHalf : warp;                                     // this warp's index in its group
+    const int rstep = two_groups ? (cg ? kComputeWarps - kHalf : kHalf) : kComputeWarps;  // warps in the group
     const int jj = cg * 32 + lane;
     if (jj >= two) return;
     const int j = ox0 + jj;
@@ -204,46 +232,64 @@ __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int P
         k1[i] = __ldg(plx + (int64_t)(1 * NW + i) * n_out + j);
         k2[i] = __ldg(plx + (int64_t)(2 * NW + i) * n_out + j);
     }
-    for (int rq = warp / ncg; rq < NRQ; rq += rstep) {
-        uint32_t o[4];
+#if B200COMP_HSPLIT
+    // unit = (row quad, channel): 4 rows x 32 columns of one channel plane.  NRQ * nch units spread evenly
+    // over the warps of this column group (a unit per row quad would leave warps idle at the barrier).
+    const int n_units = NRQ * nch;
+    const int plane = PBW >> 2;
+    for (int u = wfirst; u < n_units; u += rstep) {
+        const int rq = nch == 4 ? (u >> 2) : (int)(((uint32_t)u * 43691u) >> 17);  // u / 3 for u < 98304
+        const int c = u - rq * nch;
+        const uint32_t *row = P + (rq * 4) * PBW + c * plane + wbase;
+        uint32_t o = 0u;
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
-            const uint32_t *row = P + (rq * 4 + rr) * PBW + wbase;
+            uint32_t wd[NW];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c == 3 && nch == 3) break;
-                uint32_t a0 = 1u << (kPrecisionBits - 1), a1 = 0u;  // rounding term rides in the low plane
-                int32_t a2 = 0;
-#pragma unroll
-                for (int i = 0; i < NW; ++i) {
-                    const uint32_t wd = row[c * (PBW >> 2) + i];
-                    a0 = dp4a_uu(wd, k0[i], a0);
-                    a1 = dp4a_uu(wd, k1[i], a1);
-                    a2 = dp4a_us(wd, k2[i], a2);
-                }
-                const uint32_t v = clip8i((int32_t)(a0 + (a1 << 8) + ((uint32_t)a2 << 16)));
-                if (rr == 0) o[c] = v;
-                else if (rr == 1) o[c] = __byte_perm(o[c], v, 0x3240);
-                else if (rr == 2) o[c] = __byte_perm(o[c], v, 0x3410);
-                else o[c] = __byte_perm(o[c], v, 0x4210);
-            }
+            for (int i = 0; i < NW; ++i) wd[i] = row[rr * PBW + i];
+            const uint32_t v = clip8i(tap_sum<NW>(wd, k0, k1, k2));
+            if (rr == 0) o = v;
+            else if (rr == 1) o = __byte_perm(o, v, 0x3240);
+            else if (rr == 2) o = __byte_perm(o, v, 0x3410);
+            else o = __byte_perm(o, v, 0x4210);
         }
-        uint32_t *d = I + jj * IPW + rq;
-        d[0] = o[0];
-        d[iplane_stride] = o[1];
-        d[2 * iplane_stride] = o[2];
-        if (nch == 4) d[3 * iplane_stride] = o[3];
+        I[c * iplane_stride + jj * IPW + rq] = o;
     }
+#else
+    // unit = row quad: 4 rows x 32 columns x all channel planes
+    const int plane = PBW >> 2;
+    for (int rq = wfirst; rq < NRQ; rq += rstep) {
+        const uint32_t *row = P + (rq * 4) * PBW + wbase;
+        uint32_t *d = I + jj * IPW + rq;
+        for (int c = 0; c < nch; ++c) {
+            uint32_t o = 0u;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                uint32_t wd[NW];
+#pragma unroll
+                for (int i = 0; i < NW; ++i) wd[i] = row[rr * PBW + i];
+                const uint32_t v = clip8i(tap_sum<NW>(wd, k0, k1, k2));
+                if (rr == 0) o = v;
+                else if (rr == 1) o = __byte_perm(o, v, 0x3240);
+                else if (rr == 2) o = __byte_perm(o, v, 0x3410);
+                else o = __byte_perm(o, v, 0x4210);
+            }
+            *d = o;
+            row += plane;
+            d += iplane_stride;
+        }
+    }
+#endif
 }
 
 // ---- V pass + un-premultiply + over -------------------------------------------------------------
-template <int NW>
+template <int NW, int NCH>
 __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, int iplane_stride, int IPW,
                                                 uint32_t *__restrict__ ctile, int rw0, int oy0, int tho, int two,
                                                 int tile_dx, int tile_dy, double scale, double support,
-                                                const uint32_t *__restrict__ ply, int n_out, int nch) {
+                                                const uint32_t *__restrict__ ply, int n_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane >= tho) return;
+    if (lane >= tho || warp >= kComputeWarps) return;
     const int y = oy0 + lane;
     const int wbase = (first_tap(y, scale, support) >> 2) - rw0;
     uint32_t k0[NW], k1[NW], k2[NW];
@@ -255,23 +301,21 @@ __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, 
     }
     const int r = tile_dy + lane;
     uint32_t *crow = ctile + (r << 5);
-    for (int x = warp; x < two; x += kWarps) {
+    for (int x = warp; x < two; x += kComputeWarps) {
         const uint32_t *col = I + x * IPW + wbase;
         int32_t acc[4];
-        acc[3] = 255 << kPrecisionBits;  // opaque patch: alpha is exactly 255
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (c == 3 && nch == 3) break;
-            uint32_t a0 = 1u << (kPrecisionBits - 1), a1 = 0u;
-            int32_t a2 = 0;
+        for (int c = 0; c < NCH; ++c) {
+            uint32_t wd[NW];
 #pragma unroll
-            for (int i = 0; i < NW; ++i) {
-                const uint32_t wd = col[c * iplane_stride + i];
-                a0 = dp4a_uu(wd, k0[i], a0);
-                a1 = dp4a_uu(wd, k1[i], a1);
-                a2 = dp4a_us(wd, k2[i], a2);
-            }
-            acc[c] = (int32_t)(a0 + (a1 << 8) + ((uint32_t)a2 << 16));
+            for (int i = 0; i < NW; ++i) wd[i] = col[c * iplane_stride + i];
+            acc[c] = tap_sum<NW>(wd, k0, k1, k2);
+        }
+        const int X = tile_dx + x;
+        uint32_t *cpx = crow + (((X & 32) << 5) | ((((X >> 2) ^ r) & 7) << 2) | (X & 3));
+        if (NCH == 3) {  // every source alpha is 255: the pixel replaces the canvas pixel
+            *cpx = clip8i(acc[0]) | (clip8i(acc[1]) << 8) | (clip8i(acc[2]) << 16) | 0xff000000u;
+            continue;
         }
         // Alpha tests on the raw accumulator (clip8(acc) == 0 / == 255).  Do NOT test the clamped value:
         // CUDA 12.9 ptxas folds `clamp(x) == 255` into VIMNMX.RELU's predicate output with the wrong
@@ -279,8 +323,6 @@ __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, 
         if (acc[3] < (1 << kPrecisionBits)) continue;  // transparent: canvas pixel unchanged
         const bool opaque = acc[3] >= (255 << kPrecisionBits);
         const uint32_t s = clip8i(acc[0]) | (clip8i(acc[1]) << 8) | (clip8i(acc[2]) << 16) | (clip8i(acc[3]) << 24);
-        const int X = tile_dx + x;
-        uint32_t *cpx = crow + (((X & 32) << 5) | ((((X >> 2) ^ r) & 7) << 2) | (X & 3));
         *cpx = opaque ? s : over_px(*cpx, unpremultiply_px(s));
     }
 }
@@ -311,7 +353,9 @@ static_assert(sizeof(DevPlacementT) == 128, "DevPlacementT layout");
 // scan kernel walks one contiguous row per stream.
 __global__ void __launch_bounds__(128)
 bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__restrict__ placements,
-                 int64_t run_tile_base, int G, int K, int32_t *__restrict__ cnt) {
+                 int64_t run_tile_base, int G, int K, int32_t *__restrict__ cnt,
+                 unsigned long long *__restrict__ cursor) {
+    if (cursor && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *cursor = 0ull;  // first launch of a run
     const DevCanvas &cv = canvases[blockIdx.y];
     const int local = blockIdx.x * blockDim.x + threadIdx.x;
     if (local >= cv.tiles_x * cv.tiles_y) return;
@@ -328,41 +372,35 @@ bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__
     cnt[(t % G) * K + t / G] = n;
 }
 
-// exclusive scan of every stream's row (in place), stream offsets, END records.  One block, thread = stream.
-__global__ void __launch_bounds__(1024)
+// exclusive scan of every stream's row (in place), one warp per stream; the stream's region of the record
+// array is claimed with one atomicAdd (streams need not be stored in order), END record written.
+__global__ void __launch_bounds__(256)
 bin_scan_kernel(int32_t *__restrict__ cnt, int G, int K, int64_t n_tiles, int64_t *__restrict__ stream_off,
-                Cmd *__restrict__ streams, int64_t capacity, int *__restrict__ status) {
-    __shared__ int64_t lens[1024];
-    const int c = threadIdx.x;
-    int64_t len = 0;
-    if (c < G) {
-        const int64_t nk = n_tiles > c ? (n_tiles - c + G - 1) / G : 0;
-        int32_t *row = cnt + (int64_t)c * K;
-        int32_t acc = 0;
-        for (int64_t k = 0; k < nk; ++k) {
-            const int32_t v = row[k];
-            row[k] = acc;
-            acc += v;
+                unsigned long long *__restrict__ cursor, Cmd *__restrict__ streams, int64_t capacity,
+                int *__restrict__ status) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= G) return;
+    const int64_t nk = n_tiles > c ? (n_tiles - c + G - 1) / G : 0;
+    int32_t *row = cnt + (int64_t)c * K;
+    int32_t carry = 0;
+    for (int64_t k0 = 0; k0 < nk; k0 += 32) {
+        const int64_t k = k0 + lane;
+        const int32_t v = k < nk ? row[k] : 0;
+        int32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t t = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += t;
         }
-        len = (int64_t)acc + 1;  // + END
+        if (k < nk) row[k] = carry + x - v;
+        carry += __shfl_sync(0xffffffffu, x, 31);
     }
-    lens[c] = len;
-    __syncthreads();
-    if (c == 0) {
-        int64_t a = 0;
-        for (int i = 0; i < G; ++i) {
-            const int64_t t = lens[i];
-            lens[i] = a;
-            a += t;
-        }
-        stream_off[G] = a;
-        if (a > capacity) atomicOr(status, kStatusStreamOverflow);
-    }
-    __syncthreads();
-    if (c < G) {
-        stream_off[c] = lens[c];
-        const int64_t e = lens[c] + len - 1;
-        if (e < capacity) streams[e].w[0] = kCmdEnd;
+    if (lane == 0) {
+        const int64_t len = (int64_t)carry + 1;  // + END
+        const int64_t base = (int64_t)atomicAdd(cursor, (unsigned long long)len);
+        stream_off[c] = base;
+        if (base + len <= capacity) streams[base + len - 1].w[0] = kCmdEnd;
+        else atomicOr(status, kStatusStreamOverflow);
     }
 }
 
@@ -397,17 +435,20 @@ __device__ __forceinline__ void store_cmd(Cmd *dst, const uint32_t (&w)[16]) {
     q[3] = make_uint4(w[12], w[13], w[14], w[15]);
 }
 
-// fill: thread = tile.  Writes the TILE record and one record per touching placement, in z-order:
-// resample steps carry the tile geometry and the OR of the alpha summary over the source patch (fully
-// transparent patches become NOPs, fully opaque ones skip the alpha plane in the tile kernel).
-__global__ void __launch_bounds__(128)
+// fill: warp = tile, lane = placement (32 at a time, z-order kept by ballot ranks).  Writes the TILE record
+// and one record per touching placement: resample steps carry the tile geometry and the OR of the alpha
+// summary over the source patch (fully transparent patches become NOPs, fully opaque ones skip the alpha
+// plane in the tile kernel).
+constexpr int kFillWarps = 4;
+__global__ void __launch_bounds__(kFillWarps * 32)
 bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPlacementT *__restrict__ placements,
                 int64_t run_tile_base, int G, int K, const int32_t *__restrict__ scan,
                 const int64_t *__restrict__ stream_off, Cmd *__restrict__ streams, int64_t capacity,
                 const uint8_t *__restrict__ maps_base, const uint32_t *__restrict__ tables_base, int patch_words,
                 int inter_words, int *__restrict__ status) {
     const DevCanvas &cv = canvases[blockIdx.y];
-    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int local = blockIdx.x * kFillWarps + (threadIdx.x >> 5);
     if (local >= cv.tiles_x * cv.tiles_y) return;
     const int ty = local / cv.tiles_x, tx = local - ty * cv.tiles_x;
     const int tx0 = tx * kTileW, ty0 = ty * kTileH;
@@ -416,76 +457,97 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
     const int64_t base = stream_off[t % G] + scan[(t % G) * K + t / G];
     int n_slots = 0, n_steps = 0;
     uint32_t w[16];
-    for (int i = 0; i < cv.count; ++i) {
-        const DevPlacementT &d = placements[cv.first + i];
-        if (!(max(tx0, d.x) < min(tx1, d.x + d.w) && max(ty0, d.y) < min(ty1, d.y + d.h))) continue;
-        ++n_slots;
-        const int64_t at = base + n_slots;
-        if (at >= capacity) continue;  // flagged by the scan kernel
-#pragma unroll
-        for (int k = 0; k < 16; ++k) w[k] = 0u;
-        w[0] = kCmdNop;
-        if (d.mode == 0) {
-            const int ix0 = max(tx0, d.x), iy0 = max(ty0, d.y);
-            const int two = min(tx1, d.x + d.w) - ix0, tho = min(ty1, d.y + d.h) - iy0;
-            w[2] = (uint32_t)(ix0 - tx0) | ((uint32_t)(iy0 - ty0) << 8) | ((uint32_t)two << 16) | ((uint32_t)tho << 24);
-            if (d.tmap) {
-                // TMA boxes start on 16-byte boundaries: the box begins up to 3 pixels left of the tile
-                // origin (w5 = that shift) and is kOverlayBoxW = 68 pixels wide
-                w[0] = kCmdIdentTma;
-                const int cx = tx0 - d.x;
-                w[3] = (uint32_t)(cx & ~3);
-                w[5] = (uint32_t)(cx & 3);
-                w[4] = (uint32_t)(ty0 - d.y);
-                w[8] = (uint32_t)((reinterpret_cast<const uint8_t *>(d.tmap) - maps_base) >> 7);
-            } else {
-                w[0] = kCmdIdentLdg;
-                w[3] = (uint32_t)(ix0 - d.x);
-                w[4] = (uint32_t)(iy0 - d.y);
-                w[6] = (uint32_t)d.src_pitch;
-                const uint64_t p = reinterpret_cast<uint64_t>(d.src);
-                w[12] = (uint32_t)p;
-                w[13] = (uint32_t)(p >> 32);
-            }
-            ++n_steps;
-        } else {
-            const Geo g = tile_geometry(d, tx0, ty0, tx1, ty1);
-            const int IPW = g.NRQ | 1;
-            const bool fits = d.pbw * d.nrbox <= patch_words && 4 * kTileW * IPW <= inter_words && 4 * g.NRQ <= d.nrbox &&
-                              g.cw0 < 65536 && g.rw0 < 65536;
-            if (!fits) {
-                atomicOr(status, kStatusPatchOverflow);  // host sizing bug: flagged, step dropped
-            } else {
-                const int nbw = g.bq1 - g.bq0 + 1;
-                const int rq1 = min(g.rw0 + g.NRQ, d.sh4);
-                uint32_t bits = 0u;
-                for (int br = g.rw0; br < rq1; ++br) {
-                    const uint32_t *fr = d.flags + (int64_t)br * d.wq + g.bq0;
-                    for (int bc = 0; bc < nbw; ++bc) bits |= __ldg(fr + bc);
-                }
-                if (bits & 1u) {  // otherwise nothing but alpha 0: the canvas does not change
-                    w[0] = kCmdResample;
-                    w[1] = (uint32_t)d.nwx | ((uint32_t)d.nwy << 8) | ((bits & 2u) ? (4u << 16) : (3u << 16)) | ((uint32_t)g.NRQ << 24);
-                    w[2] = (uint32_t)(g.ix0 - tx0) | ((uint32_t)(g.iy0 - ty0) << 8) | ((uint32_t)g.two << 16) | ((uint32_t)g.tho << 24);
-                    w[3] = (uint32_t)g.ox0;
-                    w[4] = (uint32_t)g.oy0;
-                    w[5] = (uint32_t)g.cw0 | ((uint32_t)g.rw0 << 16);
-                    w[6] = (uint32_t)d.w;
-                    w[7] = (uint32_t)d.h;
-                    w[8] = (uint32_t)((reinterpret_cast<const uint8_t *>(d.tmap) - maps_base) >> 7);
-                    w[9] = (uint32_t)(d.plx - tables_base);
-                    w[10] = (uint32_t)(d.ply - tables_base);
-                    w[11] = (uint32_t)d.pbw | ((uint32_t)d.nrbox << 16);
-                    const uint64_t sx = (uint64_t)__double_as_longlong(d.scale_x), sy = (uint64_t)__double_as_longlong(d.scale_y);
-                    w[12] = (uint32_t)sx; w[13] = (uint32_t)(sx >> 32);
-                    w[14] = (uint32_t)sy; w[15] = (uint32_t)(sy >> 32);
-                    ++n_steps;
-                }
-            }
+    for (int i0 = 0; i0 < cv.count; i0 += 32) {
+        const int i = i0 + lane;
+        bool hit = false;
+        const DevPlacementT &d = placements[cv.first + min(i, cv.count - 1)];
+        if (i < cv.count) hit = max(tx0, d.x) < min(tx1, d.x + d.w) && max(ty0, d.y) < min(ty1, d.y + d.h);
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        // resampled placements: tile geometry per lane, then the alpha summary of each patch is ORed by the
+        // whole warp (the rectangle of lane b is broadcast, every lane reads a slice of it)
+        Geo g = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        bool fits = false;
+        if (hit && d.mode != 0) {
+            g = tile_geometry(d, tx0, ty0, tx1, ty1);
+            fits = d.pbw * d.nrbox <= patch_words && 4 * kTileW * (g.NRQ | 1) <= inter_words && 4 * g.NRQ <= d.nrbox &&
+                   g.cw0 < 65536 && g.rw0 < 65536;
+            if (!fits) atomicOr(status, kStatusPatchOverflow);  // host sizing bug: flagged, step dropped
         }
-        store_cmd(streams + at, w);
+        uint32_t my_bits = 0u;
+        for (uint32_t mr = __ballot_sync(0xffffffffu, fits); mr; mr &= mr - 1u) {
+            const int b = __ffs((int)mr) - 1;
+            const unsigned long long fp = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(d.flags), b);
+            const int wq = __shfl_sync(0xffffffffu, d.wq, b), bq0 = __shfl_sync(0xffffffffu, g.bq0, b);
+            const int nbw = __shfl_sync(0xffffffffu, g.bq1 - g.bq0 + 1, b);
+            const int r0 = __shfl_sync(0xffffffffu, g.rw0, b), r1 = __shfl_sync(0xffffffffu, min(g.rw0 + g.NRQ, d.sh4), b);
+            const uint32_t *fl = reinterpret_cast<const uint32_t *>((uintptr_t)fp);
+            const int nb = nbw * (r1 - r0);
+            uint32_t bits = 0u;
+            for (int q = lane; q < nb; q += 32) {
+                const int br = q / nbw, bc = q - br * nbw;
+                bits |= __ldg(fl + (int64_t)(r0 + br) * wq + bq0 + bc);
+            }
+            bits = __reduce_or_sync(0xffffffffu, bits);
+            if (lane == b) my_bits = bits;
+        }
+        bool step = false;
+        if (hit) {
+            const int64_t at = base + 1 + n_slots + __popc(m & ((1u << lane) - 1u));
+#pragma unroll
+            for (int k = 0; k < 16; ++k) w[k] = 0u;
+            w[0] = kCmdNop;
+            if (d.mode == 0) {
+                const int ix0 = max(tx0, d.x), iy0 = max(ty0, d.y);
+                const int two = min(tx1, d.x + d.w) - ix0, tho = min(ty1, d.y + d.h) - iy0;
+                w[2] = (uint32_t)(ix0 - tx0) | ((uint32_t)(iy0 - ty0) << 8) | ((uint32_t)two << 16) | ((uint32_t)tho << 24);
+                if (d.tmap) {
+                    // TMA boxes start on 16-byte boundaries: the box begins up to 3 pixels left of the tile
+                    // origin (w5 = that shift) and is kOverlayBoxW = 68 pixels wide
+                    w[0] = kCmdIdentTma;
+                    const int cx = tx0 - d.x;
+                    w[3] = (uint32_t)(cx & ~3);
+                    w[5] = (uint32_t)(cx & 3);
+                    w[4] = (uint32_t)(ty0 - d.y);
+                    w[8] = (uint32_t)((reinterpret_cast<const uint8_t *>(d.tmap) - maps_base) >> 7);
+                } else {
+                    w[0] = kCmdIdentLdg;
+                    w[3] = (uint32_t)(ix0 - d.x);
+                    w[4] = (uint32_t)(iy0 - d.y);
+                    w[6] = (uint32_t)d.src_pitch;
+                    const uint64_t p = reinterpret_cast<uint64_t>(d.src);
+                    w[12] = (uint32_t)p;
+                    w[13] = (uint32_t)(p >> 32);
+                }
+                step = true;
+            } else {
+                if (fits) {
+                    const uint32_t bits = my_bits;
+                    if (bits & 1u) {  // otherwise nothing but alpha 0: the canvas does not change
+                        w[0] = kCmdResample;
+                        w[1] = (uint32_t)d.nwx | ((uint32_t)d.nwy << 8) | ((bits & 2u) ? (4u << 16) : (3u << 16)) | ((uint32_t)g.NRQ << 24);
+                        w[2] = (uint32_t)(g.ix0 - tx0) | ((uint32_t)(g.iy0 - ty0) << 8) | ((uint32_t)g.two << 16) | ((uint32_t)g.tho << 24);
+                        w[3] = (uint32_t)g.ox0;
+                        w[4] = (uint32_t)g.oy0;
+                        w[5] = (uint32_t)g.cw0 | ((uint32_t)g.rw0 << 16);
+                        w[6] = (uint32_t)d.w;
+                        w[7] = (uint32_t)d.h;
+                        w[8] = (uint32_t)((reinterpret_cast<const uint8_t *>(d.tmap) - maps_base) >> 7);
+                        w[9] = (uint32_t)(d.plx - tables_base);
+                        w[10] = (uint32_t)(d.ply - tables_base);
+                        w[11] = (uint32_t)d.pbw | ((uint32_t)d.nrbox << 16);
+                        const uint64_t sx = (uint64_t)__double_as_longlong(d.scale_x), sy = (uint64_t)__double_as_longlong(d.scale_y);
+                        w[12] = (uint32_t)sx; w[13] = (uint32_t)(sx >> 32);
+                        w[14] = (uint32_t)sy; w[15] = (uint32_t)(sy >> 32);
+                        step = true;
+                    }
+                }
+            }
+            if (at < capacity) store_cmd(streams + at, w);  // overflow is flagged by the scan kernel
+        }
+        n_slots += __popc(m);
+        n_steps += __popc(__ballot_sync(0xffffffffu, step));
     }
-    if (base >= capacity) return;
+    if (lane != 0 || base >= capacity) return;
 #pragma unroll
     for (int k = 0; k < 16; ++k) w[k] = 0u;
     w[0] = kCmdTile;
@@ -501,6 +563,28 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
     w[10] = (uint32_t)om; w[11] = (uint32_t)(om >> 32);
     store_cmd(streams + base, w);
 }
+
+// Optional phase timing (-DB200COMP_PROFILE=1): cycles one observer thread per CTA spends in each phase of
+// the step loop, summed over CTAs into g_prof (read with b200comp_debug_profile_).
+#ifndef B200COMP_PROFILE
+#define B200COMP_PROFILE 0
+#endif
+#if B200COMP_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF_MARK(slot)                                                      \
+    do {                                                                     \
+        if (tid == B200COMP_PROFILE_TID) {                                   \
+            const long long now__ = clock64();                               \
+            prof_acc[slot] += (unsigned long long)(now__ - prof_t);          \
+            prof_t = now__;                                                  \
+        }                                                                    \
+    } while (0)
+#ifndef B200COMP_PROFILE_TID
+#define B200COMP_PROFILE_TID 32
+#endif
+#else
+#define PROF_MARK(slot) do { } while (0)
+#endif
 
 // ---- the persistent tile kernel ------------------------------------------------------------------
 // CTA c consumes command stream c.  Everything it touches arrives asynchronously and ahead of use:
@@ -523,18 +607,22 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
     Cmd *ring = reinterpret_cast<Cmd *>(I + inter_words);
     uint64_t *bg_full = reinterpret_cast<uint64_t *>(ring + kRing);
     uint64_t *patch_full = bg_full + kTileBufs;
+    // uniform state kept in shared memory to save registers: the current TILE record, the producer's cursor
+    uint32_t *trec2 = reinterpret_cast<uint32_t *>(patch_full + 1);  // 2 x 16 words, by tile parity (the finished
+                                                                     // tile is flushed while the next one begins)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ptid = tid - kProducerTid;  // >= 0: producer warp
     const Cmd *stream = streams + stream_off[blockIdx.x];
 
-    if (tid == 0) {
+    if (tid == kProducerTid) {
         for (int b = 0; b < kTileBufs; ++b) mbar_init(&bg_full[b], 1);
         mbar_init(patch_full, 1);
     }
-    if (tid < 4) {  // ring prologue: records 0 .. kRingAhead-1, one group each
+    if (ptid >= 0 && ptid < 4) {  // ring prologue: records 0 .. kRingAhead-1, one group each
 #pragma unroll
         for (int i = 0; i < kRingAhead; ++i) {
-            cp_async16(reinterpret_cast<uint8_t *>(ring + i) + 16 * tid, reinterpret_cast<const uint8_t *>(stream + i) + 16 * tid);
+            cp_async16(reinterpret_cast<uint8_t *>(ring + i) + 16 * ptid, reinterpret_cast<const uint8_t *>(stream + i) + 16 * ptid);
             cp_async_commit();
         }
     }
@@ -545,12 +633,19 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
     uint32_t pseq = 0;    // patches consumed so far (parity of patch_full)
     int steps_left = 0;
     bool bg_pending = false;
-    int c_tx0 = 0, c_ty0 = 0, c_tw = 0, c_th = 0;
-    uint32_t c_flags = 0, c_canvas = 0;
-    const void *c_out_map = nullptr;
-    // producer state (thread 0)
-    int ppos = 0, ptseq = 0;
-    bool patch_busy = false, p_done = false;
+    uint32_t c_flags = 0;
+#define trec (trec2 + ((ctseq & 1) << 4))
+#define c_tx0 ((int)trec[2])
+#define c_ty0 ((int)trec[3])
+#define c_tw ((int)(trec[4] & 0xffffu))
+#define c_th ((int)(trec[4] >> 16))
+#define c_canvas (trec[7])
+#define c_out_map (reinterpret_cast<const void *>((uint64_t)trec[10] | ((uint64_t)trec[11] << 32)))
+    // producer state (meaningful in the producer thread only)
+    int ppos = 0;             // next record to examine
+    int ptseq = 0;            // tiles whose background has been issued
+    bool patch_busy = false;  // the patch buffer holds (or is receiving) a patch whose H pass has not finished
+    bool p_done = false;      // END seen
 
     auto producer_advance = [&](int limit) {
         while (!p_done && ppos <= limit) {
@@ -588,66 +683,74 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
         }
     };
 
-    // all threads: the tile's pixels are final -> write it out (TMA store, or generic stores)
+    // The tile's pixels are final.  The store itself is issued after the next (A) barrier (flush_tile), so a
+    // finished tile costs no barrier of its own.
+    bool store_pending = false;
     auto finish_tile = [&]() {
-        uint32_t *ct = ctile + (ctseq & (kTileBufs - 1)) * kTileWords;
         if (bg_pending) {
             mbar_wait(&bg_full[ctseq & (kTileBufs - 1)], (uint32_t)(ctseq / kTileBufs) & 1u);
             bg_pending = false;
         }
+        if (c_flags & kTileOutTma) fence_async_smem();  // generic writes to the tile -> visible to the async proxy
+        store_pending = true;
+    };
+    // after a barrier: write the finished tile out (TMA store by thread 0, or generic stores by everyone)
+    auto flush_tile = [&]() {
+        store_pending = false;
+        const uint32_t *ct = ctile + (ctseq & (kTileBufs - 1)) * kTileWords;
         if (c_flags & kTileOutTma) {
-            fence_async_smem();  // generic writes to the tile -> visible to the async proxy
-            __syncthreads();
-            if (tid == 0) {
+            if (tid == kProducerTid) {
                 tma_store_2d(c_out_map, c_tx0, c_ty0, ct);
                 if (c_tw > 32) tma_store_2d(c_out_map, c_tx0 + 32, c_ty0, ct + 1024);
                 bulk_commit();
             }
         } else {
-            __syncthreads();
             const DevCanvas &cv = canvases[c_canvas];
             uint8_t *out = cv.out;
             const int64_t pitch = cv.out_pitch;
             const int xx = tid & (kTileW - 1);
-            if (xx < c_tw)
-                for (int yy = tid / kTileW; yy < c_th; yy += kThreads / kTileW)
+            if (tid < kElemThreads && xx < c_tw)
+                for (int yy = tid / kTileW; yy < c_th; yy += kRowSweep)
                     *reinterpret_cast<uint32_t *>(out + (int64_t)(c_ty0 + yy) * pitch + (int64_t)(c_tx0 + xx) * 4) = ct[ct_off(yy, xx)];
-            if (tid == 0) bulk_commit();  // every tile is one bulk group, so the group counting stays uniform
+            if (tid == kProducerTid) bulk_commit();  // every tile is one bulk group, so the group counting stays uniform
         }
     };
 
+#if B200COMP_PROFILE
+    unsigned long long prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = clock64();
+#endif
     for (;;) {
-        if (tid < 4) {
+        PROF_MARK(0);  // end of the previous record (tile begin / step tail / NOP)
+        if (ptid >= 0 && ptid < 4) {
             cp_async_wait<kRingAhead - 1 - kLook>();  // records <= pos + kLook have landed
-            cp_async16(reinterpret_cast<uint8_t *>(ring + ((pos + kRingAhead) & (kRing - 1))) + 16 * tid,
-                       reinterpret_cast<const uint8_t *>(stream + pos + kRingAhead) + 16 * tid);
+            cp_async16(reinterpret_cast<uint8_t *>(ring + ((pos + kRingAhead) & (kRing - 1))) + 16 * ptid,
+                       reinterpret_cast<const uint8_t *>(stream + pos + kRingAhead) + 16 * ptid);
             cp_async_commit();
         }
         __syncthreads();  // (A) ring visible; every thread is done with the previous record
+        PROF_MARK(1);  // barrier (A)
+        if (store_pending) flush_tile();
         const Cmd &cmd = ring[pos & (kRing - 1)];
         const uint32_t kind = cmd.w[0];
         if (kind == kCmdEnd) break;
-        if (tid == 0) producer_advance(pos + kLook);
+        if (tid == kProducerTid && (kind == kCmdTile || ppos <= pos)) producer_advance(pos + kLook);
         if (kind == kCmdNop) {
             ++pos;
+            PROF_MARK(9);  // NOP record
             continue;
         }
         if (kind == kCmdTile) {
             ++ctseq;
             steps_left = (int)cmd.w[1];
-            c_tx0 = (int)cmd.w[2];
-            c_ty0 = (int)cmd.w[3];
-            c_tw = (int)(cmd.w[4] & 0xffffu);
-            c_th = (int)(cmd.w[4] >> 16);
             c_flags = cmd.w[6];
-            c_canvas = cmd.w[7];
-            c_out_map = reinterpret_cast<const void *>((uint64_t)cmd.w[10] | ((uint64_t)cmd.w[11] << 32));
+            if (tid < 16) trec[tid] = cmd.w[tid];  // read after the next barrier at the earliest
             if (c_flags & kTileBgTma) {
                 bg_pending = true;
             } else {
                 // solid colour, or a background TMA cannot address: fill the buffer here
                 const uint32_t solid = cmd.w[5];
-                if (tid == 0) bulk_wait_read<kTileBufs - 1>();  // the store that last read this buffer is done
+                if (tid == kProducerTid) bulk_wait_read<kTileBufs - 1>();  // the store that last read this buffer is done
                 __syncthreads();
                 uint32_t *ct = ctile + (ctseq & (kTileBufs - 1)) * kTileWords;
                 const int xx = tid & (kTileW - 1);
@@ -655,15 +758,21 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
                     const DevCanvas &cv = canvases[c_canvas];
                     const uint8_t *bg = cv.bg;
                     const int64_t pitch = cv.bg_pitch;
-                    if (xx < c_tw)
-                        for (int yy = tid / kTileW; yy < c_th; yy += kThreads / kTileW)
+                    if (tid < kElemThreads && xx < c_tw)
+                        for (int yy = tid / kTileW; yy < c_th; yy += kRowSweep)
                             ct[ct_off(yy, xx)] = ld_px(bg, (int64_t)(c_ty0 + yy) * pitch + (int64_t)(c_tx0 + xx) * 4);
                 } else {
-                    for (int yy = tid / kTileW; yy < kTileH; yy += kThreads / kTileW) ct[ct_off(yy, xx)] = solid;
+                    if (tid < kElemThreads)
+                        for (int yy = tid / kTileW; yy < kTileH; yy += kRowSweep) ct[ct_off(yy, xx)] = solid;
                 }
                 bg_pending = false;
             }
-            if (steps_left == 0) finish_tile();
+            if (steps_left == 0) {
+                finish_tile();
+                PROF_MARK(8);  // empty tile (waits for its background)
+            } else {
+                PROF_MARK(7);  // tile begin
+            }
             ++pos;
             continue;
         }
@@ -686,9 +795,13 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
             const int IPW = NRQ | 1;
             const int iplane_stride = kTileW * IPW;
             // coefficient rows -> L1 while the patch is in flight
-            if (warp < 2 && warp * 32 + lane < two) prefetch_coeffs(plx, nwx, n_out_x, ox0 + warp * 32 + lane);
-            if (warp == 2 && lane < tho) prefetch_coeffs(ply, nwy, n_out_y, oy0 + lane);
+            if (warp == kComputeWarps) {  // the producer warp's idle lanes do the prefetching
+                for (int jj = lane; jj < two; jj += 32) prefetch_coeffs(plx, nwx, n_out_x, ox0 + jj);
+                if (lane < tho) prefetch_coeffs(ply, nwy, n_out_y, oy0 + lane);
+            }
+            PROF_MARK(2);  // dispatch, decode, producer (thread 0), coefficient prefetch
             mbar_wait(patch_full, pseq & 1u);  // source patch has landed in P
+            PROF_MARK(3);  // wait for the patch
             ++pseq;
             if (nwx == 3)
                 tile_hpass<3>(P, pbw, I, iplane_stride, IPW, NRQ, cw0, ox0, two, scale_x, support_x, plx, n_out_x, nch);
@@ -696,8 +809,10 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
                 tile_hpass<4>(P, pbw, I, iplane_stride, IPW, NRQ, cw0, ox0, two, scale_x, support_x, plx, n_out_x, nch);
             else
                 tile_hpass<5>(P, pbw, I, iplane_stride, IPW, NRQ, cw0, ox0, two, scale_x, support_x, plx, n_out_x, nch);
+            PROF_MARK(4);  // H pass
             __syncthreads();  // (B) H pass done: P is free, I is complete
-            if (tid == 0) {
+            PROF_MARK(5);  // barrier (B)
+            if (tid == kProducerTid) {
                 patch_busy = false;
                 producer_advance(pos + kLook);  // the next patch streams in during this V pass
             }
@@ -705,12 +820,19 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
                 mbar_wait(&bg_full[ctseq & (kTileBufs - 1)], (uint32_t)(ctseq / kTileBufs) & 1u);
                 bg_pending = false;
             }
-            if (nwy == 3)
-                tile_vpass_over<3>(I, iplane_stride, IPW, ct, rw0, oy0, tho, two, dx, dy, scale_y, support_y, ply, n_out_y, nch);
-            else if (nwy == 4)
-                tile_vpass_over<4>(I, iplane_stride, IPW, ct, rw0, oy0, tho, two, dx, dy, scale_y, support_y, ply, n_out_y, nch);
-            else
-                tile_vpass_over<5>(I, iplane_stride, IPW, ct, rw0, oy0, tho, two, dx, dy, scale_y, support_y, ply, n_out_y, nch);
+#define B200_VPASS(NWY, NCH_) \
+    tile_vpass_over<NWY, NCH_>(I, iplane_stride, IPW, ct, rw0, oy0, tho, two, dx, dy, scale_y, support_y, ply, n_out_y)
+            if (nch == 4) {
+                if (nwy == 3) B200_VPASS(3, 4);
+                else if (nwy == 4) B200_VPASS(4, 4);
+                else B200_VPASS(5, 4);
+            } else {
+                if (nwy == 3) B200_VPASS(3, 3);
+                else if (nwy == 4) B200_VPASS(4, 3);
+                else B200_VPASS(5, 3);
+            }
+#undef B200_VPASS
+            PROF_MARK(6);  // V pass (+ background wait, producer on thread 0)
         } else if (kind == kCmdIdentTma) {
             // identity-size overlay: P holds the 64x32 source pixels under this tile (zero outside the overlay)
             mbar_wait(patch_full, pseq & 1u);
@@ -721,13 +843,13 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
             }
             const int xx = tid & (kTileW - 1);
             const int shift = (int)cmd.w[5];
-            if (xx >= dx && xx < dx + two)
-                for (int yy = dy + tid / kTileW; yy < dy + tho; yy += kThreads / kTileW) {
+            if (tid < kElemThreads && xx >= dx && xx < dx + two)
+                for (int yy = dy + tid / kTileW; yy < dy + tho; yy += kRowSweep) {
                     uint32_t *c = ct + ct_off(yy, xx);
                     *c = over_px(*c, P[yy * kOverlayBoxW + xx + shift]);
                 }
             __syncthreads();  // (B) P is free
-            if (tid == 0) {
+            if (tid == kProducerTid) {
                 patch_busy = false;
                 producer_advance(pos + kLook);
             }
@@ -740,8 +862,8 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
             const int64_t spitch = (int64_t)cmd.w[6];
             const int sx0 = (int)cmd.w[3], sy0 = (int)cmd.w[4];
             const int xx = tid & (kTileW - 1);
-            if (xx < two)
-                for (int yy = tid / kTileW; yy < tho; yy += kThreads / kTileW) {
+            if (tid < kElemThreads && xx < two)
+                for (int yy = tid / kTileW; yy < tho; yy += kRowSweep) {
                     const uint32_t s = ld_px(src, (int64_t)(sy0 + yy) * spitch + (int64_t)(sx0 + xx) * 4);
                     uint32_t *c = ct + ct_off(dy + yy, dx + xx);
                     *c = over_px(*c, s);
@@ -750,8 +872,19 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
         if (--steps_left == 0) finish_tile();
         ++pos;
     }
-    if (tid < 4) cp_async_wait<0>();
-    if (tid == 0) bulk_wait_all();  // stores still reading shared memory
+    if (ptid >= 0 && ptid < 4) cp_async_wait<0>();
+    if (tid == kProducerTid) bulk_wait_all();  // stores still reading shared memory
+#if B200COMP_PROFILE
+    if (tid == B200COMP_PROFILE_TID)
+        for (int i = 0; i < 10; ++i) atomicAdd(&g_prof[i], prof_acc[i]);
+#endif
+#undef trec
+#undef c_tx0
+#undef c_ty0
+#undef c_tw
+#undef c_th
+#undef c_canvas
+#undef c_out_map
 }
 
 }  // namespace b200comp

@@ -16,7 +16,7 @@ def main():
     prof = [(r[ix["Source"]].strip(), float(r[ix["Instructions Executed"]] or 0), float(r[ix["# Samples"]] or 0))
             for r in rows[hi + 1:] if len(r) >= len(hdr)]
     lines = open(sass_path).read().split("\n")
-    start = next(i for i, l in enumerate(lines) if l.startswith(".text.") and "composite_tiles_kernel" in l)
+    start = next(i for i, l in enumerate(lines) if l.startswith(".text.") and "composite_stream_kernel" in l)
     cur = ("?", 0)
     sass = []
     for l in lines[start + 1:]:
@@ -33,12 +33,18 @@ def main():
     def find(s):
         return next(i + 1 for i, l in enumerate(src) if s in l)
 
+    kernel = "composite_stream_kernel"
     marks = [(find("void prefetch_l1"), "prefetch"),
              (find("void tile_hpass("), "hpass"), (find("void tile_vpass_over("), "vpass"),
-             (find("struct DevPlacementT"), "main:setup"), (find("z-order walk, kDescCache"), "main:hit list"),
-             (find("identity-size placement: plain over"), "main:identity over"),
-             (find("const Geo g = geometry(d);\n            const int IPW") if False else find("const int IPW = g.NRQ | 1;"), "main:resample glue (TMA wait, syncs)"),
-             (find("write the tile once"), "main:store")]
+             (find("struct DevPlacementT"), "binning (not this kernel)"),
+             (find("composite_stream_kernel(const Cmd"), "main:setup / ring prologue"),
+             (find("auto producer_advance"), "main:producer (TMA issue)"),
+             (find("auto finish_tile"), "main:finish tile (store)"),
+             (find("for (;;) {"), "main:ring + dispatch"),
+             (find("if (kind == kCmdTile) {"), "main:tile begin"),
+             (find("if (kind == kCmdResample) {"), "main:resample glue (decode, waits)"),
+             (find("} else if (kind == kCmdIdentTma) {"), "main:identity over"),
+             (find("if (--steps_left == 0) finish_tile();"), "main:step end")]
 
     def region(f, ln):
         if f != cuh.split("/")[-1] or ln < marks[0][0]:

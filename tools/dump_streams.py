@@ -32,7 +32,9 @@ print("records", n, "streams", ns.value)
 KIND = {0: "TILE", 1: "RESAMPLE", 2: "IDENT_TMA", 3: "IDENT_LDG", 4: "NOP", 5: "END"}
 shown = 0
 for c in range(ns.value):
-    lo, hi = offs[c], offs[c + 1]
+    lo = int(offs[c]); hi = lo
+    while hi < n and recs[hi][0] != 5: hi += 1
+    hi += 1  # streams are stored in allocation order, each ends with END
     if hi - lo <= 1: continue
     if shown >= int(sys.argv[2]) if len(sys.argv) > 2 else shown >= 12: break
     shown += 1
