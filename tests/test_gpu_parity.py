@@ -364,3 +364,154 @@ def test_batch_rejects_bad_arguments(B):
         B.CompositeBatch(pool, [(0, 10)], [[]])
     with pytest.raises(ValueError):
         B.CutoutPool({1: np.zeros((4, 4, 3), np.uint8)})
+
+
+# ------------------------------------------------------------------------------ device-level C ABI, raw buffers
+def _raw_batch(native, canvases, overlays, placements, host_api=False, chunk=0):
+    """b200comp_composite_batch[_host] on caller-owned buffers.
+    canvases: [(bg array or None, solid rgba, W, H, out_pitch)]; overlays: {oid: (array, pitch)};
+    placements: per canvas [(oid, x, y, w, h)].  Returns the output arrays."""
+    mk = (lambda n: torch.zeros(n, dtype=torch.uint8)) if host_api else (lambda n: torch.zeros(n, dtype=torch.uint8, device="cuda"))
+    keep, src = [], {}
+    for oid, (a, pitch) in overlays.items():
+        sh, sw = a.shape[:2]
+        buf = mk(pitch * sh + 64)
+        off = 4  # deliberately only 4-byte aligned
+        view = buf[off:off + pitch * sh].view(sh, pitch)
+        view[:, : sw * 4] = torch.from_numpy(np.ascontiguousarray(a).reshape(sh, sw * 4)).to(buf.device)
+        keep.append(buf)
+        src[oid] = (buf.data_ptr() + off, pitch, sw, sh)
+    cv = (native.Canvas * len(canvases))()
+    recs, outs = [], []
+    for i, (bg, solid, W, H, out_pitch) in enumerate(canvases):
+        out = mk(out_pitch * H + 64)
+        keep.append(out)
+        outs.append(out)
+        bg_ptr, bg_pitch = None, 0
+        if bg is not None:
+            b = mk(W * 4 * H)
+            b[:] = torch.from_numpy(np.ascontiguousarray(bg).reshape(-1)).to(b.device)
+            keep.append(b)
+            bg_ptr, bg_pitch = b.data_ptr(), W * 4
+        first = len(recs)
+        recs.extend(placements[i])
+        r, g, bl, a = solid
+        cv[i] = native.Canvas(out.data_ptr(), out_pitch, bg_ptr, bg_pitch, r | (g << 8) | (bl << 16) | (a << 24), W, H,
+                              first, len(placements[i]), 0)
+    pl = (native.Placement * max(1, len(recs)))()
+    for j, (oid, x, y, w, h) in enumerate(recs):
+        p, pitch, sw, sh = src[oid]
+        pl[j] = native.Placement(p, pitch, sw, sh, x, y, w, h, 0, 0)
+    L = native.lib()
+    if host_api:
+        native.check(L.b200comp_composite_batch_host(cv, len(canvases), pl, len(recs), 4, chunk, 3), "composite_batch_host")
+    else:
+        native.check(L.b200comp_composite_batch(cv, len(canvases), pl, len(recs), None), "composite_batch")
+        torch.cuda.synchronize()
+    res = []
+    for (bg, solid, W, H, out_pitch), out in zip(canvases, outs):
+        res.append(out[: out_pitch * H].view(H, out_pitch)[:, : W * 4].reshape(H, W, 4).cpu().numpy())
+    return res
+
+
+def test_raw_buffers_unaligned_pitches_and_bases():
+    """Sources and canvases TMA cannot address (4-byte aligned bases, pitches that are not multiples of
+    16): the plain-load / plain-store paths of the tile kernel and the scalar path of the prepare kernel."""
+    from image_transformation_b200 import _native
+
+    rng = np.random.default_rng(5)
+    ov = {1: rng.integers(0, 256, (37, 51, 4), dtype=np.uint8), 2: rng.integers(0, 256, (90, 70, 4), dtype=np.uint8)}
+    ov[2][20:60, 10:50, 3] = 255
+    overlays = {1: (ov[1], 51 * 4), 2: (ov[2], 70 * 4 + 4)}
+    W, H = 203, 131
+    bg = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    bg[..., 3] = 255
+    pls = [[(1, 5, 7, 51, 37), (2, 60, 20, 70, 90), (2, 100, -30, 91, 150), (1, 150, 100, 80, 60), (1, -20, 90, 51, 37)],
+           [(2, 0, 0, 70, 90), (1, 30, 30, 25, 19)]]
+    canvases = [(bg, (0, 0, 0, 0), W, H, W * 4 + 4), (None, (9, 8, 7, 255), W, H, W * 4)]
+    outs = _raw_batch(_native, canvases, overlays, pls)
+    for i, o in enumerate(outs):
+        base = bg if i == 0 else np.broadcast_to(np.array([9, 8, 7, 255], np.uint8), (H, W, 4)).copy()
+        ref = oracle.composite(base, ov, [{"object_id": oid, "box": [x, y, x + w, y + h]} for oid, x, y, w, h in pls[i]])
+        assert_same(o, ref, f"raw canvas {i}")
+
+
+def test_host_buffer_batch_sub_ranges():
+    """b200comp_composite_batch_host with several chunks per plan (plan_run_canvases on sub-ranges)."""
+    from image_transformation_b200 import _native, synth
+
+    rng = np.random.default_rng(8)
+    pool = synth.make_pool(5, 30, 160, seed=3)
+    overlays = {k: (v, ((v.shape[1] * 4 + 15) // 16) * 16) for k, v in pool.items()}
+    canvases, pls, bgs = [], [], []
+    for i in range(11):
+        W, H = int(rng.integers(64, 400)), int(rng.integers(40, 300))
+        bg = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+        bg[..., 3] = 255
+        bgs.append(bg)
+        canvases.append((bg, (0, 0, 0, 0), W, H, W * 4))
+        pl = []
+        for _ in range(7):
+            oid = int(rng.integers(1, 6))
+            sh, sw = pool[oid].shape[:2]
+            s = 1.0 if rng.random() < 0.3 else float(rng.uniform(0.5, 1.6))
+            w, h = max(1, round(sw * s)), max(1, round(sh * s))
+            pl.append((oid, int(rng.integers(-w // 2, W)), int(rng.integers(-h // 2, H)), w, h))
+        pls.append(pl)
+    outs = _raw_batch(_native, canvases, overlays, pls, host_api=True, chunk=2)
+    for i, o in enumerate(outs):
+        ref = oracle.composite(bgs[i], pool, [{"object_id": oid, "box": [x, y, x + w, y + h]} for oid, x, y, w, h in pls[i]])
+        assert_same(o, ref, f"host batch canvas {i}")
+
+
+def test_batch_many_placements_per_tile(B):
+    """More placements on one tile than one binning chunk (32) and than the old descriptor cache (64)."""
+    rng = np.random.default_rng(12)
+    pool = {k: rng.integers(0, 256, (int(rng.integers(8, 40)), int(rng.integers(8, 40)), 4), dtype=np.uint8) for k in range(1, 7)}
+    W, H = 150, 90
+    pl = []
+    for _ in range(150):
+        oid = int(rng.integers(1, 7))
+        sh, sw = pool[oid].shape[:2]
+        s = 1.0 if rng.random() < 0.4 else float(rng.uniform(0.6, 1.7))
+        w, h = max(1, round(sw * s)), max(1, round(sh * s))
+        x, y = int(rng.integers(-10, W)), int(rng.integers(-10, H))
+        pl.append({"object_id": oid, "box": [x, y, x + w, y + h]})
+    bg = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    outs, _ = run_batch(B, pool, [(W, H)], [pl], bgs=[bg])
+    assert_same(outs[0], oracle.composite(bg, pool, pl), "150 placements")
+
+
+def test_batch_c4_aspect_sweep_vs_oracle(B):
+    """BASELINE.json configs[3]: one canvas of every aspect ratio of the sweep (4399x1885 has rows TMA cannot
+    address: pitch % 16 != 0), 20 objects each, bit-exact vs the oracle."""
+    from image_transformation_b200 import synth
+
+    pool = synth.make_pool(10, 256, 1536, seed=1234)
+    sizes_by_id = {k: (v.shape[1], v.shape[0]) for k, v in pool.items()}
+    sizes = synth.WORKLOADS["c4_aspect_sweep"]["canvases"]
+    pls = [synth.canvas_placements(sizes_by_id, s, i) for i, s in enumerate(sizes)]
+    outs, info = run_batch(B, pool, sizes, pls, solid=(38, 73, 115, 255))
+    for (W, H), o, pl in zip(sizes, outs, pls):
+        bg = np.empty((H, W, 4), np.uint8)
+        bg[...] = (38, 73, 115, 255)
+        assert_same(o, oracle.composite(bg, pool, pl), f"C4 canvas {W}x{H}")
+
+
+def test_batch_c5_8k_overlapping_with_background_synthesis(B):
+    """BASELINE.json configs[4] (one canvas): fill_solid statistics of a synthetic background -> solid colour
+    -> 7680x4320 canvas with 64 large, heavily overlapping objects, bit-exact vs the oracle."""
+    from image_transformation_b200 import synth
+
+    w = synth.WORKLOADS["c5_8k_64obj"]
+    pool = synth.make_pool(5, 1024, 2048, seed=4321)
+    sizes_by_id = {k: (v.shape[1], v.shape[0]) for k, v in pool.items()}
+    W, H = w["canvas"]
+    bgsrc = synth.synthetic_background(960, 540)
+    colour = B.masked_median_rgb(dev(bgsrc))
+    assert list(colour) == list(oracle.masked_median_rgb(bgsrc))
+    pl = synth.canvas_placements(sizes_by_id, (W, H), 0, n_objects=64, scale_lo=0.6, scale_hi=1.0, layout="uniform")
+    outs, info = run_batch(B, pool, [(W, H)], [pl], solid=(*colour, 255))
+    bg = np.empty((H, W, 4), np.uint8)
+    bg[...] = (*colour, 255)
+    assert_same(outs[0], oracle.composite(bg, pool, pl), "C5 canvas")
