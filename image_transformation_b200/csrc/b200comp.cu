@@ -230,6 +230,7 @@ __global__ void median_from_hist_kernel(const unsigned long long *__restrict__ h
 }  // namespace b200comp
 
 #include "tile_kernel.cuh"
+#include "coeff_kernel.cuh"
 
 namespace b200comp {
 
@@ -395,7 +396,13 @@ struct TableSet {
         }
     }
 
-    void build(int n_threads) {
+    // skip_packed: the packed tables are built on the device (build_packed_on_device); only the legacy
+    // tables of the generic kernels are made here
+    bool has_legacy() const {
+        for (const Key &k : order) if (k.kind == 0) return true;
+        return false;
+    }
+    void build(int n_threads, bool skip_packed = false) {
         host.assign((size_t)total + 4, 0);
         if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
         n_threads = std::max(1, std::min<int>(n_threads, (int)order.size()));
@@ -405,6 +412,7 @@ struct TableSet {
                 const Key &key = order[i];
                 const TableRef &r = refs[key];
                 int32_t *h = host.data();
+                if (skip_packed && key.kind != 0) continue;
                 if (key.kind == 0) {
                     build_lanczos_table(key.in_size, key.out_size, h + r.k_off, h + r.b_off);
                     continue;
@@ -434,6 +442,104 @@ struct TableSet {
         }
     }
 };
+
+// Packed tables on the device (coeff_kernel.cuh): one launch computes every output sample of every table;
+// samples whose fixed-point value sits within the guard band of a rounding boundary come back in a list
+// and are recomputed here with libm, so the result is bit-identical to the host builder.
+// Returns 0, or 1 when the fix-up list overflowed (caller falls back to the host builder).
+static int build_packed_on_device(const TableSet &ts, int32_t *d_tables, cudaStream_t st, int64_t *n_fixed, std::string *err) {
+    std::vector<CoefJob> jobs;
+    int max_out = 1;
+    int64_t samples = 0;
+    for (const TableSet::Key &key : ts.order) {
+        if (key.kind == 0) continue;
+        const TableRef &r = ts.refs.at(key);
+        CoefJob j;
+        j.planes_off = r.b_off;
+        j.in_size = key.in_size;
+        j.out_size = key.out_size;
+        j.nw = r.ks;
+        j.identity = key.kind == 2 ? 1 : 0;
+        jobs.push_back(j);
+        max_out = std::max(max_out, key.out_size);
+        samples += key.out_size;
+    }
+    if (n_fixed) *n_fixed = 0;
+    if (jobs.empty()) return 0;
+    const int fix_cap = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(4096, samples / 64));
+    CoefJob *d_jobs = nullptr;
+    CoefFix *d_fix = nullptr;
+    int *d_count = nullptr;
+    auto fail_cuda = [&](cudaError_t e) {
+        if (err) *err = std::string("device coefficient tables: ") + cudaGetErrorString(e);
+        if (d_jobs) cudaFreeAsync(d_jobs, st);
+        if (d_fix) cudaFreeAsync(d_fix, st);
+        if (d_count) cudaFreeAsync(d_count, st);
+        return -1;
+    };
+    cudaError_t e;
+    if ((e = cudaMallocAsync((void **)&d_jobs, jobs.size() * sizeof(CoefJob), st)) != cudaSuccess) return fail_cuda(e);
+    if ((e = cudaMallocAsync((void **)&d_fix, (size_t)fix_cap * sizeof(CoefFix), st)) != cudaSuccess) return fail_cuda(e);
+    if ((e = cudaMallocAsync((void **)&d_count, sizeof(int), st)) != cudaSuccess) return fail_cuda(e);
+    if ((e = cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(CoefJob), cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail_cuda(e);
+    if ((e = cudaMemsetAsync(d_count, 0, sizeof(int), st)) != cudaSuccess) return fail_cuda(e);
+    const unsigned gx = (unsigned)std::min(16, (max_out + 127) / 128);
+    for (size_t j0 = 0; j0 < jobs.size(); j0 += 65535) {
+        const unsigned ny = (unsigned)std::min<size_t>(65535, jobs.size() - j0);
+        build_packed_tables_kernel<<<dim3(gx, ny), 128, 0, st>>>(d_jobs + j0, (int)j0, reinterpret_cast<uint32_t *>(d_tables), d_fix,
+                                                                 d_count, fix_cap);
+    }
+    int count = 0;
+    if ((e = cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail_cuda(e);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail_cuda(e);
+    int rc = 0;
+    if (count > fix_cap) {
+        rc = 1;  // too many borderline samples for the list: let the host build everything
+    } else if (count > 0) {
+        std::vector<CoefFix> fix((size_t)count);
+        if ((e = cudaMemcpyAsync(fix.data(), d_fix, (size_t)count * sizeof(CoefFix), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail_cuda(e);
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail_cuda(e);
+        std::vector<WordPatch> patches;
+        std::vector<int32_t> row;
+        for (const CoefFix &f : fix) {
+            const CoefJob &job = jobs[(size_t)f.job];
+            row.assign((size_t)lanczos_ksize(job.in_size, job.out_size) + 1, 0);
+            int lo = 0, n = 0;
+            build_lanczos_row(job.in_size, job.out_size, f.j, row.data(), &lo, &n);
+            uint32_t pl[3][5] = {{0}};
+            for (int t = 0; t < n; ++t) {
+                const int pos = (lo & 3) + t, word = pos >> 2, sh = 8 * (pos & 3);
+                if (word >= 5) break;
+                pl[0][word] |= (uint32_t)(row[(size_t)t] & 0xff) << sh;
+                pl[1][word] |= (uint32_t)((row[(size_t)t] >> 8) & 0xff) << sh;
+                pl[2][word] |= (uint32_t)((row[(size_t)t] >> 16) & 0xff) << sh;
+            }
+            for (int p = 0; p < 3; ++p)
+                for (int i = 0; i < job.nw; ++i) {
+                    WordPatch wp;
+                    wp.off = job.planes_off + (int64_t)(p * job.nw + i) * job.out_size + f.j;
+                    wp.value = pl[p][i];
+                    wp.pad_ = 0;
+                    patches.push_back(wp);
+                }
+        }
+        WordPatch *d_patches = nullptr;
+        if ((e = cudaMallocAsync((void **)&d_patches, patches.size() * sizeof(WordPatch), st)) != cudaSuccess) return fail_cuda(e);
+        e = cudaMemcpyAsync(d_patches, patches.data(), patches.size() * sizeof(WordPatch), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            patch_words_kernel<<<(unsigned)((patches.size() + 255) / 256), 256, 0, st>>>(reinterpret_cast<uint32_t *>(d_tables),
+                                                                                        d_patches, (int)patches.size());
+            e = cudaStreamSynchronize(st);  // `patches` is a local
+        }
+        cudaFreeAsync(d_patches, st);
+        if (e != cudaSuccess) return fail_cuda(e);
+        if (n_fixed) *n_fixed = count;
+    }
+    cudaFreeAsync(d_jobs, st);
+    cudaFreeAsync(d_fix, st);
+    cudaFreeAsync(d_count, st);
+    return rc;
+}
 
 // Upper bound of the 4-sample words one tile needs along an axis (see tile_kernel.cuh: cw1 - cw0).
 static int words_bound(int in_size, int out_size, int n_out, int nw) {
@@ -813,8 +919,10 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     }
 
     // ---- build tables on the host threads, upload everything ----
-    ts.build(n_host_threads);
-    const size_t tbytes = ts.host.size() * sizeof(int32_t);
+    // B200COMP_HOST_TABLES=1 builds the packed tables with libm on the host threads instead (validation)
+    static const bool host_tables = std::getenv("B200COMP_HOST_TABLES") != nullptr;
+    bool tables_on_device = !host_tables;
+    const size_t tbytes = ((size_t)ts.total + 4) * sizeof(int32_t);
     auto dev_alloc = [&](void **p, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMallocAsync(p, std::max<size_t>(bytes, 16), st);
         if (e == cudaSuccess) plan->owned.push_back(*p);
@@ -975,7 +1083,22 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         CUDA_TRY(dev_alloc((void **)&plan->d_bin, (size_t)plan->G * (size_t)std::max<int64_t>(1, K) * sizeof(int32_t)));
         CUDA_TRY(dev_alloc((void **)&plan->d_stream_off, (size_t)(plan->G + 1) * sizeof(int64_t)));
     }
-    CUDA_TRY(cudaMemcpyAsync(plan->d_tables, ts.host.data(), tbytes, cudaMemcpyHostToDevice, st));
+    int64_t n_fixed = 0;
+    if (tables_on_device) {
+        if (ts.has_legacy()) {  // legacy tables of the generic kernels: host-built, uploaded with the (still empty) packed regions
+            ts.build(n_host_threads, true);
+            CUDA_TRY(cudaMemcpyAsync(plan->d_tables, ts.host.data(), tbytes, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        std::string err;
+        const int r = build_packed_on_device(ts, plan->d_tables, st, &n_fixed, &err);
+        if (r < 0) return fail(B200COMP_ECUDA, err);
+        if (r > 0) tables_on_device = false;
+    }
+    if (!tables_on_device) {
+        ts.build(n_host_threads);
+        CUDA_TRY(cudaMemcpyAsync(plan->d_tables, ts.host.data(), tbytes, cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(cudaMemcpyAsync(plan->d_placements, hp.data(), hp.size() * sizeof(DevPlacementT), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(plan->d_canvases, hc.data(), hc.size() * sizeof(DevCanvas), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(plan->d_status, 0, sizeof(int), st));
@@ -1091,6 +1214,39 @@ int64_t b200comp_plan_debug_streams_(b200comp_plan *plan, uint32_t *out, int64_t
     const int64_t n = std::min<int64_t>(max_records, std::min<int64_t>(offs[plan->G], plan->stream_capacity));
     cudaMemcpy(out, plan->d_streams, (size_t)n * sizeof(Cmd), cudaMemcpyDeviceToHost);
     return n;
+}
+
+// internal (tests/): packed coefficient tables of the given (in, out) size pairs built on the device (with the
+// libm fix-up) and on the host; returns the number of differing words (0 = bit-identical) or a negative error.
+int64_t b200comp_debug_compare_tables_(const int *in_sizes, const int *out_sizes, int n, int64_t *n_fixed) {
+    TableSet ts;
+    for (int i = 0; i < n; ++i) {
+        if (in_sizes[i] < 1 || out_sizes[i] < 1) return B200COMP_EINVAL;
+        if (in_sizes[i] == out_sizes[i]) { ts.want_packed(in_sizes[i], out_sizes[i], true); continue; }
+        if (packed_words(lanczos_ksize(in_sizes[i], out_sizes[i])) == 0) continue;  // not a fused-path table
+        ts.want_packed(in_sizes[i], out_sizes[i], false);
+    }
+    const size_t tbytes = ((size_t)ts.total + 4) * sizeof(int32_t);
+    int32_t *d = nullptr;
+    if (cudaMalloc((void **)&d, tbytes) != cudaSuccess) return B200COMP_ENOMEM;
+    cudaMemset(d, 0xff, tbytes);
+    std::string err;
+    const int r = build_packed_on_device(ts, d, nullptr, n_fixed, &err);
+    if (r != 0) {
+        cudaFree(d);
+        return r < 0 ? fail(B200COMP_ECUDA, err) : fail(B200COMP_EINTERNAL, "fix-up list overflow");
+    }
+    std::vector<int32_t> got((size_t)ts.total + 4);
+    cudaMemcpy(got.data(), d, tbytes, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    ts.build(0);
+    int64_t bad = 0;
+    for (const TableSet::Key &key : ts.order) {
+        const TableRef &ref = ts.refs.at(key);
+        const int64_t words = (int64_t)3 * ref.ks * key.out_size;
+        for (int64_t w = 0; w < words; ++w) bad += got[(size_t)(ref.b_off + w)] != ts.host[(size_t)(ref.b_off + w)];
+    }
+    return bad;
 }
 
 // internal (tools/): phase cycle counters of a -DB200COMP_PROFILE=1 build; reset after reading

@@ -40,7 +40,7 @@ __device__ __forceinline__ double lanczos3_dev(double x) {
     return 0.0;
 }
 
-__global__ void __launch_bounds__(128) build_packed_tables_kernel(const CoefJob *__restrict__ jobs,
+__global__ void __launch_bounds__(128) build_packed_tables_kernel(const CoefJob *__restrict__ jobs, int job0,
                                                                    uint32_t *__restrict__ tables,
                                                                    CoefFix *__restrict__ fix, int *__restrict__ fix_count,
                                                                    int fix_cap) {
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128) build_packed_tables_kernel(const CoefJob 
         if (uncertain) {
             const int idx = atomicAdd(fix_count, 1);
             if (idx < fix_cap) {
-                fix[idx].job = blockIdx.y;
+                fix[idx].job = job0 + (int)blockIdx.y;
                 fix[idx].j = j;
             }
         }

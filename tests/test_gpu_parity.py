@@ -515,3 +515,23 @@ def test_batch_c5_8k_overlapping_with_background_synthesis(B):
     bg = np.empty((H, W, 4), np.uint8)
     bg[...] = (*colour, 255)
     assert_same(outs[0], oracle.composite(bg, pool, pl), "C5 canvas")
+
+
+def test_device_coefficient_tables_match_libm():
+    """The packed LANCZOS tables built on the device (double arithmetic replayed in the host's operation
+    order, borderline roundings recomputed with libm) are bit-identical to the host builder's."""
+    from image_transformation_b200 import _native
+
+    L = _native.lib()
+    L.b200comp_debug_compare_tables_.restype = ctypes.c_int64
+    L.b200comp_debug_compare_tables_.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    rng = np.random.default_rng(2024)
+    ins = rng.integers(1, 4000, 3000).astype(np.int32)
+    scale = rng.uniform(0.38, 3.0, 3000)
+    outs = np.maximum(1, (ins * scale).astype(np.int32))
+    ins = np.concatenate([ins, np.array([1, 1, 2, 5, 7, 4000, 1536, 1536, 256], np.int32)])
+    outs = np.concatenate([outs, np.array([1, 9, 1, 5, 3, 3999, 768, 1535, 683], np.int32)])
+    fixed = ctypes.c_int64(0)
+    bad = L.b200comp_debug_compare_tables_(ins.ctypes.data, outs.ctypes.data, len(ins), ctypes.byref(fixed))
+    assert bad == 0, f"{bad} coefficient words differ ({_native.last_error()})"
+    assert 0 <= fixed.value < len(ins) * 40  # a handful of borderline samples were recomputed on the host
