@@ -364,7 +364,7 @@ def run_b200(args):
             pls[j] = _native.Placement(tp.data_ptr(), tp.shape[1] * 4, tp.shape[1], tp.shape[0], x, y, w, h, fl, 0)
 
         def e2e_step():
-            rc = L.b200comp_composite_batch_host(cvs, nb, pls, len(recs), host_cores(), 8, 3)
+            rc = L.b200comp_composite_batch_host(cvs, nb, pls, len(recs), host_cores(), 4, 3)
             _native.check(rc, "composite_batch_host")
 
         e2e_step()  # warm-up (also pages the pinned buffers in)

@@ -3,6 +3,9 @@
 // device-level C ABI declared in include/b200comp.h plus CUDA runtime copies.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -19,11 +22,21 @@ namespace {
 
 thread_local std::string g_host_err;
 
+// Device memory from the stream-ordered pool: the pool keeps freed blocks (release threshold raised below),
+// so the staging buffers of repeated host-buffer calls cost a pool lookup, not a cudaMalloc / cudaFree pair.
 struct DevBuf {
     void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, nullptr); }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, std::max<size_t>(bytes, 16), nullptr); }
 };
+
+void keep_pool_memory(int device) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+}
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -54,6 +67,15 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
         return b200comp_set_error_(B200COMP_EINVAL, "composite_batch_host: empty batch or null arrays");
     int device = 0;
     if (cudaGetDevice(&device) != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, "no CUDA device");
+    keep_pool_memory(device);
+    // B200COMP_TRACE=1: host-side timeline of the pipeline on stderr
+    static const bool trace = std::getenv("B200COMP_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto stamp = [&](const char *what, int idx) {
+        if (!trace) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+        std::fprintf(stderr, "[b200comp host] %8.2f ms  %s %d\n", ms, what, idx);
+    };
     if (n_host_threads <= 0) n_host_threads = std::max(1u, std::thread::hardware_concurrency());
     if (chunk_canvases <= 0) chunk_canvases = 8;
     // super-chunk: about a quarter of the batch (so the pipeline has depth), between 2 and 16 sub-chunks
@@ -92,39 +114,44 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
     max_canvas_bytes = align_up(max_canvas_bytes, 256);
 
     // ---- device resources ----
-    const int n_buf = n_super > 1 ? 2 : 1;
-    DevBuf pool, d_out[2], d_bg[2];
+    // three staging sets: while the host waits for the oldest super-chunk, two more are queued on the copy
+    // streams, so neither PCIe direction idles
+    constexpr int kBufs = 3;
+    const int n_buf = std::min(n_super, kBufs);
+    DevBuf pool, d_out[kBufs], d_bg[kBufs];
     if (pool.alloc(pool_bytes) != cudaSuccess) return b200comp_set_error_(B200COMP_ENOMEM, "cutout pool allocation failed");
     for (int b = 0; b < n_buf; ++b)
         if (d_out[b].alloc(max_canvas_bytes * super_canvases) != cudaSuccess ||
             (any_bg && d_bg[b].alloc(max_canvas_bytes * super_canvases) != cudaSuccess))
             return b200comp_set_error_(B200COMP_ENOMEM, "canvas staging allocation failed");
-    cudaStream_t s_in = nullptr, s_exec = nullptr, s_out = nullptr, s_plan = nullptr;
+    cudaStreamSynchronize(nullptr);  // the allocations above are ordered on the default stream
+    stamp("staging allocated", 0);
+    cudaStream_t s_in = nullptr, s_exec = nullptr, s_out = nullptr, s_plan = nullptr, s_chk = nullptr;
     struct StreamGuard {
-        cudaStream_t *s[4];
+        cudaStream_t *s[5];
         ~StreamGuard() { for (auto p : s) if (*p) cudaStreamDestroy(*p); }
-    } sguard{{&s_in, &s_exec, &s_out, &s_plan}};
+    } sguard{{&s_in, &s_exec, &s_out, &s_plan, &s_chk}};
     if (cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s_exec, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&s_plan, cudaStreamNonBlocking) != cudaSuccess)
+        cudaStreamCreateWithFlags(&s_plan, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s_chk, cudaStreamNonBlocking) != cudaSuccess)
         return b200comp_set_error_(B200COMP_ECUDA, "stream creation failed");
     const int max_sub = (super_canvases + chunk_canvases - 1) / chunk_canvases;
-    std::vector<cudaEvent_t> ev_in((size_t)max_sub * 2), ev_exec((size_t)max_sub * 2);  // one set per staging buffer
+    std::vector<cudaEvent_t> ev_in((size_t)max_sub * 3), ev_exec((size_t)max_sub * 3);  // one set per staging buffer
     struct EventGuard {
         std::vector<cudaEvent_t> *a, *b;
         ~EventGuard() { for (auto e : *a) if (e) cudaEventDestroy(e); for (auto e : *b) if (e) cudaEventDestroy(e); }
     } eguard{&ev_in, &ev_exec};
     for (auto &e : ev_in) e = nullptr;
     for (auto &e : ev_exec) e = nullptr;
-    cudaEvent_t ev_pool = nullptr, ev_done[2] = {nullptr, nullptr};
-    for (int i = 0; i < 2 * max_sub; ++i)
+    cudaEvent_t ev_pool = nullptr, ev_done[kBufs] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < 3 * max_sub; ++i)
         if (cudaEventCreateWithFlags(&ev_in[(size_t)i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&ev_exec[(size_t)i], cudaEventDisableTiming) != cudaSuccess)
             return b200comp_set_error_(B200COMP_ECUDA, "event creation failed");
     cudaEventCreateWithFlags(&ev_pool, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_done[0], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_done[1], cudaEventDisableTiming);
+    for (int b = 0; b < kBufs; ++b) cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming);
 
     // cutouts: each distinct host cutout once, 16-byte aligned pitch (copy-in stream)
     for (const SrcKey &k : src_order) {
@@ -173,7 +200,7 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
 
     int rc = 0;
     std::string err;
-    SuperPlan live[2];  // plans of the super-chunks in flight, by staging buffer
+    SuperPlan live[kBufs];  // plans of the super-chunks in flight, by staging buffer
     SuperPlan built;    // plan being resolved by the helper thread
     auto retire = [&](int buf) {  // wait for the super-chunk that used `buf`, check it, free its plan
         if (!live[buf].plan) return;
@@ -184,7 +211,9 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
             err = cudaGetErrorString(e);
         }
         if (rc == 0) {
-            const int c = b200comp_plan_check(live[buf].plan, s_exec);
+            // the plan's kernels are complete (ev_done): read its status word on a stream of its own, NOT on
+            // s_exec, whose queue already holds the next super-chunks
+            const int c = b200comp_plan_check(live[buf].plan, s_chk);
             if (c) {
                 rc = c;
                 err = b200comp_last_error();
@@ -201,6 +230,7 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
         const int n_sub = (c_hi - c_lo + chunk_canvases - 1) / chunk_canvases;
         cudaEvent_t *e_in = ev_in.data() + (size_t)buf * max_sub, *e_exec = ev_exec.data() + (size_t)buf * max_sub;
         retire(buf);  // the previous user of this staging buffer (two super-chunks ago)
+        stamp("staging buffer free", si);
         if (rc) break;
         // copy-in of the backgrounds overlaps the helper thread's table building
         for (int j = 0; j < n_sub; ++j) {
@@ -213,7 +243,9 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
             }
             cudaEventRecord(e_in[j], s_in);
         }
+        stamp("copy-in enqueued, waiting for plan", si);
         helper.join();  // plan of this super-chunk
+        stamp("plan ready", si);
         live[buf] = std::move(built);
         built = SuperPlan();
         if (live[buf].rc) {
@@ -242,6 +274,7 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
             }
         }
         cudaEventRecord(ev_done[buf], s_out);
+        stamp("super-chunk enqueued", si);
         if (rc) {
             err = b200comp_last_error();
             break;
@@ -255,16 +288,16 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
     {
         const int keep_rc = rc;
         const std::string keep_err = err;
-        for (int b = 0; b < 2; ++b) retire(b);
+        for (int b = 0; b < kBufs; ++b) retire(b);
         if (keep_rc) {
             rc = keep_rc;
             err = keep_err;
         }
     }
     cudaDeviceSynchronize();
+    stamp("all done", 0);
     if (ev_pool) cudaEventDestroy(ev_pool);
-    if (ev_done[0]) cudaEventDestroy(ev_done[0]);
-    if (ev_done[1]) cudaEventDestroy(ev_done[1]);
+    for (int b = 0; b < kBufs; ++b) if (ev_done[b]) cudaEventDestroy(ev_done[b]);
     if (rc) return b200comp_set_error_(rc, err.c_str());
     return 0;
 }
