@@ -590,6 +590,8 @@ struct b200comp_plan {
     int32_t *d_bin = nullptr;        // [G][K] per-tile slot counts, scanned in place
     int64_t *d_stream_off = nullptr; // [G + 1]
     uint8_t *d_maps = nullptr;       // every CUtensorMap of the plan (placements, overlays, canvases)
+    uint32_t *d_masks = nullptr;     // [tiles][mask_chunks][2] keep / opaque masks from the count kernel
+    int mask_chunks = 1;             // ceil(max placements per canvas / 32)
     std::vector<int64_t> tiles_before;  // prefix sum of tiles per canvas (n_canvases + 1)
     std::vector<void *> owned;  // device allocations freed with the plan
 };
@@ -1082,6 +1084,10 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         CUDA_TRY(dev_alloc((void **)&plan->d_streams, (size_t)(plan->stream_capacity + kRing) * sizeof(Cmd)));
         CUDA_TRY(dev_alloc((void **)&plan->d_bin, (size_t)plan->G * (size_t)std::max<int64_t>(1, K) * sizeof(int32_t)));
         CUDA_TRY(dev_alloc((void **)&plan->d_stream_off, (size_t)(plan->G + 1) * sizeof(int64_t)));
+        int max_count = 1;
+        for (int c = 0; c < n_canvases; ++c) max_count = std::max(max_count, canvases[c].n_placements);
+        plan->mask_chunks = (max_count + 31) / 32;
+        CUDA_TRY(dev_alloc((void **)&plan->d_masks, (size_t)std::max<int64_t>(1, tiles) * plan->mask_chunks * 2 * sizeof(uint32_t)));
     }
     int64_t n_fixed = 0;
     if (tables_on_device) {
@@ -1161,8 +1167,7 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
     const int64_t n_tiles = plan->tiles_before[(size_t)first + count] - tile0;
     const int G = plan->G;
     const int K = (int)((n_tiles + G - 1) / G);
-    const unsigned gx = (unsigned)((plan->max_tiles + 127) / 128);
-    const unsigned gxf = (unsigned)((plan->max_tiles + kFillWarps - 1) / kFillWarps);
+    const unsigned gx = (unsigned)((plan->max_tiles + kBinWarps - 1) / kBinWarps);  // warp = tile
     unsigned long long *cursor = reinterpret_cast<unsigned long long *>(plan->d_stream_off + G);  // record allocator
     // B200COMP_DEBUG_SYNC=1: synchronise after every launch so a device fault names its kernel
     static const bool debug_sync = std::getenv("B200COMP_DEBUG_SYNC") != nullptr;
@@ -1175,8 +1180,9 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
     };
     for (int c0 = first; c0 < first + count; c0 += 65535) {  // grid.y is limited to 65535 canvases per launch
         const int nc = std::min(65535, first + count - c0);
-        bin_count_kernel<<<dim3(gx, (unsigned)nc), 128, 0, st>>>(plan->d_canvases + c0, plan->d_placements, tile0, G, K, plan->d_bin,
-                                                                 c0 == first ? cursor : nullptr);
+        bin_count_kernel<<<dim3(gx, (unsigned)nc), kBinWarps * 32, 0, st>>>(
+            plan->d_canvases + c0, plan->d_placements, tile0, G, K, plan->d_bin, plan->d_masks, plan->mask_chunks,
+            plan->patch_words, plan->inter_words, c0 == first ? cursor : nullptr, plan->d_status);
     }
     if (int rc = checkpoint("bin_count_kernel")) return rc;
     bin_scan_kernel<<<(unsigned)((G + 7) / 8), 256, 0, st>>>(plan->d_bin, G, K, n_tiles, plan->d_stream_off, cursor,
@@ -1184,10 +1190,10 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
     if (int rc = checkpoint("bin_scan_kernel")) return rc;
     for (int c0 = first; c0 < first + count; c0 += 65535) {
         const int nc = std::min(65535, first + count - c0);
-        bin_fill_kernel<<<dim3(gxf, (unsigned)nc), kFillWarps * 32, 0, st>>>(
-            plan->d_canvases + c0, c0, plan->d_placements, tile0, G, K, plan->d_bin, plan->d_stream_off, plan->d_streams,
-            plan->stream_capacity, plan->d_maps, reinterpret_cast<const uint32_t *>(plan->d_tables), plan->patch_words,
-            plan->inter_words, plan->d_status);
+        bin_fill_kernel<<<dim3(gx, (unsigned)nc), kBinWarps * 32, 0, st>>>(
+            plan->d_canvases + c0, c0, plan->d_placements, tile0, G, K, plan->d_bin, plan->d_masks, plan->mask_chunks,
+            plan->d_stream_off, plan->d_streams, plan->stream_capacity, plan->d_maps,
+            reinterpret_cast<const uint32_t *>(plan->d_tables));
     }
     if (int rc = checkpoint("bin_fill_kernel")) return rc;
     composite_stream_kernel<<<(unsigned)G, kThreads, plan->smem_bytes, st>>>(

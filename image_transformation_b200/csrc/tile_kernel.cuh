@@ -347,29 +347,106 @@ struct DevPlacementT {
 };
 static_assert(sizeof(DevPlacementT) == 128, "DevPlacementT layout");
 
+// Geometry of a resampled placement on a tile (identical doubles to the host table builder).
+struct Geo {
+    int ix0, iy0, two, tho, ox0, oy0, cw0, rw0, NRQ, bq0, bq1;
+};
+__device__ __forceinline__ Geo tile_geometry(const DevPlacementT &d, int tx0, int ty0, int tx1, int ty1) {
+    Geo g;
+    g.ix0 = max(tx0, d.x);
+    g.iy0 = max(ty0, d.y);
+    const int ix1 = min(tx1, d.x + d.w), iy1 = min(ty1, d.y + d.h);
+    g.two = ix1 - g.ix0;
+    g.tho = iy1 - g.iy0;
+    g.ox0 = g.ix0 - d.x;
+    g.oy0 = g.iy0 - d.y;
+    const int w_first = first_tap(g.ox0, d.scale_x, d.support_x) >> 2;
+    const int w_last = (first_tap(ix1 - 1 - d.x, d.scale_x, d.support_x) >> 2) + d.nwx - 1;
+    g.bq0 = w_first >> 2;  // alpha summary blocks (4 words) the patch touches
+    g.bq1 = min(w_last >> 2, d.wq - 1);
+    g.cw0 = w_first & ~3;  // TMA boxes start on 16-byte boundaries
+    g.rw0 = first_tap(g.oy0, d.scale_y, d.support_y) >> 2;
+    g.NRQ = (first_tap(iy1 - 1 - d.y, d.scale_y, d.support_y) >> 2) + d.nwy - g.rw0;
+    return g;
+}
+
+__device__ __forceinline__ void store_cmd(Cmd *dst, const uint32_t (&w)[16]) {
+    uint4 *q = reinterpret_cast<uint4 *>(dst);
+    q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    q[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    q[3] = make_uint4(w[12], w[13], w[14], w[15]);
+}
+
 // ---- binning: (canvases, placements) -> one command stream per persistent CTA -----------------------
 // Tile t (numbered over the canvases of the run) belongs to CTA t % G and is its (t / G)-th tile.
-// count: slots each tile needs (1 + placements whose box touches it), stored stream-major so that the
-// scan kernel walks one contiguous row per stream.
-__global__ void __launch_bounds__(128)
+//
+// count: warp = tile, lane = placement (32 at a time).  Decides which placements become steps of the tile:
+// the box must touch it and, for resampled placements, the OR of the alpha summary over the source patch
+// must have some non-zero alpha (the whole warp reads the summary rectangle of each candidate).  The keep /
+// opaque masks go to `masks` for the fill kernel; the tile's slot count (1 + steps, or 0 for a tile nothing
+// is drawn on -- such tiles never enter a stream) is stored stream-major for the scan.
+constexpr int kBinWarps = 4;
+__global__ void __launch_bounds__(kBinWarps * 32)
 bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__restrict__ placements,
-                 int64_t run_tile_base, int G, int K, int32_t *__restrict__ cnt,
-                 unsigned long long *__restrict__ cursor) {
+                 int64_t run_tile_base, int G, int K, int32_t *__restrict__ cnt, uint32_t *__restrict__ masks,
+                 int mask_chunks, int patch_words, int inter_words, unsigned long long *__restrict__ cursor,
+                 int *__restrict__ status) {
     if (cursor && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *cursor = 0ull;  // first launch of a run
     const DevCanvas &cv = canvases[blockIdx.y];
-    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int local = blockIdx.x * kBinWarps + (threadIdx.x >> 5);
     if (local >= cv.tiles_x * cv.tiles_y) return;
     const int ty = local / cv.tiles_x, tx = local - ty * cv.tiles_x;
     const int tx0 = tx * kTileW, ty0 = ty * kTileH;
     const int tx1 = min(cv.W, tx0 + kTileW), ty1 = min(cv.H, ty0 + kTileH);
-    int n = 1;
-    for (int i = 0; i < cv.count; ++i) {
-        const DevPlacementT &d = placements[cv.first + i];
-        const int x = __ldg(&d.x), y = __ldg(&d.y), w = __ldg(&d.w), h = __ldg(&d.h);
-        n += (max(tx0, x) < min(tx1, x + w) && max(ty0, y) < min(ty1, y + h)) ? 1 : 0;
-    }
     const int64_t t = cv.tile_base - run_tile_base + local;
-    cnt[(t % G) * K + t / G] = n;
+    uint32_t *mk = masks + t * (int64_t)mask_chunks * 2;
+    int n = 0;
+    for (int chunk = 0; chunk < mask_chunks; ++chunk) {
+        const int i = chunk * 32 + lane;
+        if (chunk * 32 >= cv.count) {  // canvases with fewer placements than the widest one of the plan
+            if (lane == 0) mk[2 * chunk] = mk[2 * chunk + 1] = 0u;
+            continue;
+        }
+        const DevPlacementT &d = placements[cv.first + min(i, cv.count - 1)];
+        const bool hit = i < cv.count && max(tx0, d.x) < min(tx1, d.x + d.w) && max(ty0, d.y) < min(ty1, d.y + d.h);
+        Geo g = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        bool fits = false;
+        if (hit && d.mode != 0) {
+            g = tile_geometry(d, tx0, ty0, tx1, ty1);
+            fits = d.pbw * d.nrbox <= patch_words && 4 * kTileW * (g.NRQ | 1) <= inter_words && 4 * g.NRQ <= d.nrbox &&
+                   g.cw0 < 65536 && g.rw0 < 65536;
+            if (!fits) atomicOr(status, kStatusPatchOverflow);  // host sizing bug: flagged, step dropped
+        }
+        uint32_t my_bits = 0u;
+        for (uint32_t mr = __ballot_sync(0xffffffffu, fits); mr; mr &= mr - 1u) {
+            const int b = __ffs((int)mr) - 1;
+            const unsigned long long fp = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(d.flags), b);
+            const int wq = __shfl_sync(0xffffffffu, d.wq, b), bq0 = __shfl_sync(0xffffffffu, g.bq0, b);
+            const int nbw = __shfl_sync(0xffffffffu, g.bq1 - g.bq0 + 1, b);
+            const int r0 = __shfl_sync(0xffffffffu, g.rw0, b), r1 = __shfl_sync(0xffffffffu, min(g.rw0 + g.NRQ, d.sh4), b);
+            const uint32_t *fl = reinterpret_cast<const uint32_t *>((uintptr_t)fp);
+            const int nb = nbw * (r1 - r0);
+            uint32_t bits = 0u;
+            for (int q = lane; q < nb; q += 32) {
+                const int br = q / nbw, bc = q - br * nbw;
+                bits |= __ldg(fl + (int64_t)(r0 + br) * wq + bq0 + bc);
+            }
+            bits = __reduce_or_sync(0xffffffffu, bits);
+            if (lane == b) my_bits = bits;
+        }
+        // keep: identity overlays always; resampled ones unless nothing but alpha 0 lies under the tile
+        const bool keep = hit && (d.mode == 0 || (fits && (my_bits & 1u)));
+        const uint32_t km = __ballot_sync(0xffffffffu, keep);
+        const uint32_t om = __ballot_sync(0xffffffffu, keep && d.mode != 0 && !(my_bits & 2u));  // every alpha 255
+        if (lane == 0) {
+            mk[2 * chunk] = km;
+            mk[2 * chunk + 1] = om;
+        }
+        n += __popc(km);
+    }
+    if (lane == 0) cnt[(t % G) * K + t / G] = n ? n + 1 : 0;
 }
 
 // exclusive scan of every stream's row (in place), one warp per stream; the stream's region of the record
@@ -404,98 +481,58 @@ bin_scan_kernel(int32_t *__restrict__ cnt, int G, int K, int64_t n_tiles, int64_
     }
 }
 
-// Geometry of a resampled placement on a tile (identical doubles to the host table builder).
-struct Geo {
-    int ix0, iy0, two, tho, ox0, oy0, cw0, rw0, NRQ, bq0, bq1;
-};
-__device__ __forceinline__ Geo tile_geometry(const DevPlacementT &d, int tx0, int ty0, int tx1, int ty1) {
-    Geo g;
-    g.ix0 = max(tx0, d.x);
-    g.iy0 = max(ty0, d.y);
-    const int ix1 = min(tx1, d.x + d.w), iy1 = min(ty1, d.y + d.h);
-    g.two = ix1 - g.ix0;
-    g.tho = iy1 - g.iy0;
-    g.ox0 = g.ix0 - d.x;
-    g.oy0 = g.iy0 - d.y;
-    const int w_first = first_tap(g.ox0, d.scale_x, d.support_x) >> 2;
-    const int w_last = (first_tap(ix1 - 1 - d.x, d.scale_x, d.support_x) >> 2) + d.nwx - 1;
-    g.bq0 = w_first >> 2;  // alpha summary blocks (4 words) the patch touches
-    g.bq1 = min(w_last >> 2, d.wq - 1);
-    g.cw0 = w_first & ~3;  // TMA boxes start on 16-byte boundaries
-    g.rw0 = first_tap(g.oy0, d.scale_y, d.support_y) >> 2;
-    g.NRQ = (first_tap(iy1 - 1 - d.y, d.scale_y, d.support_y) >> 2) + d.nwy - g.rw0;
-    return g;
-}
-
-__device__ __forceinline__ void store_cmd(Cmd *dst, const uint32_t (&w)[16]) {
-    uint4 *q = reinterpret_cast<uint4 *>(dst);
-    q[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    q[1] = make_uint4(w[4], w[5], w[6], w[7]);
-    q[2] = make_uint4(w[8], w[9], w[10], w[11]);
-    q[3] = make_uint4(w[12], w[13], w[14], w[15]);
-}
-
-// fill: warp = tile, lane = placement (32 at a time, z-order kept by ballot ranks).  Writes the TILE record
-// and one record per touching placement: resample steps carry the tile geometry and the OR of the alpha
-// summary over the source patch (fully transparent patches become NOPs, fully opaque ones skip the alpha
-// plane in the tile kernel).
-constexpr int kFillWarps = 4;
-__global__ void __launch_bounds__(kFillWarps * 32)
+// fill: warp = tile, lane = placement.  Tiles without steps are finished right here (background or solid
+// colour copied to the output: they never reach the tile kernel); the others get their TILE record and one
+// record per kept placement, in z-order (ballot ranks).
+__global__ void __launch_bounds__(kBinWarps * 32)
 bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPlacementT *__restrict__ placements,
-                int64_t run_tile_base, int G, int K, const int32_t *__restrict__ scan,
-                const int64_t *__restrict__ stream_off, Cmd *__restrict__ streams, int64_t capacity,
-                const uint8_t *__restrict__ maps_base, const uint32_t *__restrict__ tables_base, int patch_words,
-                int inter_words, int *__restrict__ status) {
+                int64_t run_tile_base, int G, int K, const int32_t *__restrict__ scan, const uint32_t *__restrict__ masks,
+                int mask_chunks, const int64_t *__restrict__ stream_off, Cmd *__restrict__ streams, int64_t capacity,
+                const uint8_t *__restrict__ maps_base, const uint32_t *__restrict__ tables_base) {
     const DevCanvas &cv = canvases[blockIdx.y];
     const int lane = threadIdx.x & 31;
-    const int local = blockIdx.x * kFillWarps + (threadIdx.x >> 5);
+    const int local = blockIdx.x * kBinWarps + (threadIdx.x >> 5);
     if (local >= cv.tiles_x * cv.tiles_y) return;
     const int ty = local / cv.tiles_x, tx = local - ty * cv.tiles_x;
     const int tx0 = tx * kTileW, ty0 = ty * kTileH;
     const int tx1 = min(cv.W, tx0 + kTileW), ty1 = min(cv.H, ty0 + kTileH);
     const int64_t t = cv.tile_base - run_tile_base + local;
-    const int64_t base = stream_off[t % G] + scan[(t % G) * K + t / G];
-    int n_slots = 0, n_steps = 0;
-    uint32_t w[16];
-    for (int i0 = 0; i0 < cv.count; i0 += 32) {
-        const int i = i0 + lane;
-        bool hit = false;
-        const DevPlacementT &d = placements[cv.first + min(i, cv.count - 1)];
-        if (i < cv.count) hit = max(tx0, d.x) < min(tx1, d.x + d.w) && max(ty0, d.y) < min(ty1, d.y + d.h);
-        const uint32_t m = __ballot_sync(0xffffffffu, hit);
-        // resampled placements: tile geometry per lane, then the alpha summary of each patch is ORed by the
-        // whole warp (the rectangle of lane b is broadcast, every lane reads a slice of it)
-        Geo g = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        bool fits = false;
-        if (hit && d.mode != 0) {
-            g = tile_geometry(d, tx0, ty0, tx1, ty1);
-            fits = d.pbw * d.nrbox <= patch_words && 4 * kTileW * (g.NRQ | 1) <= inter_words && 4 * g.NRQ <= d.nrbox &&
-                   g.cw0 < 65536 && g.rw0 < 65536;
-            if (!fits) atomicOr(status, kStatusPatchOverflow);  // host sizing bug: flagged, step dropped
-        }
-        uint32_t my_bits = 0u;
-        for (uint32_t mr = __ballot_sync(0xffffffffu, fits); mr; mr &= mr - 1u) {
-            const int b = __ffs((int)mr) - 1;
-            const unsigned long long fp = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(d.flags), b);
-            const int wq = __shfl_sync(0xffffffffu, d.wq, b), bq0 = __shfl_sync(0xffffffffu, g.bq0, b);
-            const int nbw = __shfl_sync(0xffffffffu, g.bq1 - g.bq0 + 1, b);
-            const int r0 = __shfl_sync(0xffffffffu, g.rw0, b), r1 = __shfl_sync(0xffffffffu, min(g.rw0 + g.NRQ, d.sh4), b);
-            const uint32_t *fl = reinterpret_cast<const uint32_t *>((uintptr_t)fp);
-            const int nb = nbw * (r1 - r0);
-            uint32_t bits = 0u;
-            for (int q = lane; q < nb; q += 32) {
-                const int br = q / nbw, bc = q - br * nbw;
-                bits |= __ldg(fl + (int64_t)(r0 + br) * wq + bq0 + bc);
+    const uint32_t *mk = masks + t * (int64_t)mask_chunks * 2;
+    int n_steps = 0;
+    for (int c = 0; c < mask_chunks; ++c) n_steps += __popc(mk[2 * c]);
+    if (n_steps == 0) {
+        // nothing is drawn on this tile: out = background (or the solid colour)
+        const int tw = tx1 - tx0, th = ty1 - ty0;
+        const bool vec = tw == kTileW && ((reinterpret_cast<uintptr_t>(cv.out) | (uintptr_t)cv.out_pitch) & 15u) == 0 &&
+                         (!cv.bg || ((reinterpret_cast<uintptr_t>(cv.bg) | (uintptr_t)cv.bg_pitch) & 15u) == 0);
+        if (vec) {  // 16 lanes x 16 bytes per row, two rows per sweep
+            const int x4 = (lane & 15) * 4;
+            const uint4 sv = make_uint4(cv.solid, cv.solid, cv.solid, cv.solid);
+            for (int yy = lane >> 4; yy < th; yy += 2) {
+                const int64_t px = (int64_t)(tx0 + x4) * 4;
+                const uint4 v = cv.bg ? __ldg(reinterpret_cast<const uint4 *>(cv.bg + (int64_t)(ty0 + yy) * cv.bg_pitch + px)) : sv;
+                *reinterpret_cast<uint4 *>(cv.out + (int64_t)(ty0 + yy) * cv.out_pitch + px) = v;
             }
-            bits = __reduce_or_sync(0xffffffffu, bits);
-            if (lane == b) my_bits = bits;
+        } else {
+            for (int yy = 0; yy < th; ++yy)
+                for (int xx = lane; xx < tw; xx += 32) {
+                    const int64_t px = (int64_t)(tx0 + xx) * 4;
+                    const uint32_t v = cv.bg ? ld_px(cv.bg, (int64_t)(ty0 + yy) * cv.bg_pitch + px) : cv.solid;
+                    *reinterpret_cast<uint32_t *>(cv.out + (int64_t)(ty0 + yy) * cv.out_pitch + px) = v;
+                }
         }
-        bool step = false;
-        if (hit) {
-            const int64_t at = base + 1 + n_slots + __popc(m & ((1u << lane) - 1u));
+        return;
+    }
+    const int64_t base = stream_off[t % G] + scan[(t % G) * K + t / G];
+    int n_slots = 0;
+    uint32_t w[16];
+    for (int i0 = 0, chunk = 0; i0 < cv.count && chunk < mask_chunks; i0 += 32, ++chunk) {
+        const uint32_t km = mk[2 * chunk], om = mk[2 * chunk + 1];
+        if ((km >> lane) & 1u) {
+            const DevPlacementT &d = placements[cv.first + i0 + lane];
+            const int64_t at = base + 1 + n_slots + __popc(km & ((1u << lane) - 1u));
 #pragma unroll
             for (int k = 0; k < 16; ++k) w[k] = 0u;
-            w[0] = kCmdNop;
             if (d.mode == 0) {
                 const int ix0 = max(tx0, d.x), iy0 = max(ty0, d.y);
                 const int two = min(tx1, d.x + d.w) - ix0, tho = min(ty1, d.y + d.h) - iy0;
@@ -518,34 +555,27 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
                     w[12] = (uint32_t)p;
                     w[13] = (uint32_t)(p >> 32);
                 }
-                step = true;
             } else {
-                if (fits) {
-                    const uint32_t bits = my_bits;
-                    if (bits & 1u) {  // otherwise nothing but alpha 0: the canvas does not change
-                        w[0] = kCmdResample;
-                        w[1] = (uint32_t)d.nwx | ((uint32_t)d.nwy << 8) | ((bits & 2u) ? (4u << 16) : (3u << 16)) | ((uint32_t)g.NRQ << 24);
-                        w[2] = (uint32_t)(g.ix0 - tx0) | ((uint32_t)(g.iy0 - ty0) << 8) | ((uint32_t)g.two << 16) | ((uint32_t)g.tho << 24);
-                        w[3] = (uint32_t)g.ox0;
-                        w[4] = (uint32_t)g.oy0;
-                        w[5] = (uint32_t)g.cw0 | ((uint32_t)g.rw0 << 16);
-                        w[6] = (uint32_t)d.w;
-                        w[7] = (uint32_t)d.h;
-                        w[8] = (uint32_t)((reinterpret_cast<const uint8_t *>(d.tmap) - maps_base) >> 7);
-                        w[9] = (uint32_t)(d.plx - tables_base);
-                        w[10] = (uint32_t)(d.ply - tables_base);
-                        w[11] = (uint32_t)d.pbw | ((uint32_t)d.nrbox << 16);
-                        const uint64_t sx = (uint64_t)__double_as_longlong(d.scale_x), sy = (uint64_t)__double_as_longlong(d.scale_y);
-                        w[12] = (uint32_t)sx; w[13] = (uint32_t)(sx >> 32);
-                        w[14] = (uint32_t)sy; w[15] = (uint32_t)(sy >> 32);
-                        step = true;
-                    }
-                }
+                const Geo g = tile_geometry(d, tx0, ty0, tx1, ty1);
+                w[0] = kCmdResample;
+                w[1] = (uint32_t)d.nwx | ((uint32_t)d.nwy << 8) | (((om >> lane) & 1u) ? (3u << 16) : (4u << 16)) | ((uint32_t)g.NRQ << 24);
+                w[2] = (uint32_t)(g.ix0 - tx0) | ((uint32_t)(g.iy0 - ty0) << 8) | ((uint32_t)g.two << 16) | ((uint32_t)g.tho << 24);
+                w[3] = (uint32_t)g.ox0;
+                w[4] = (uint32_t)g.oy0;
+                w[5] = (uint32_t)g.cw0 | ((uint32_t)g.rw0 << 16);
+                w[6] = (uint32_t)d.w;
+                w[7] = (uint32_t)d.h;
+                w[8] = (uint32_t)((reinterpret_cast<const uint8_t *>(d.tmap) - maps_base) >> 7);
+                w[9] = (uint32_t)(d.plx - tables_base);
+                w[10] = (uint32_t)(d.ply - tables_base);
+                w[11] = (uint32_t)d.pbw | ((uint32_t)d.nrbox << 16);
+                const uint64_t sx = (uint64_t)__double_as_longlong(d.scale_x), sy = (uint64_t)__double_as_longlong(d.scale_y);
+                w[12] = (uint32_t)sx; w[13] = (uint32_t)(sx >> 32);
+                w[14] = (uint32_t)sy; w[15] = (uint32_t)(sy >> 32);
             }
             if (at < capacity) store_cmd(streams + at, w);  // overflow is flagged by the scan kernel
         }
-        n_slots += __popc(m);
-        n_steps += __popc(__ballot_sync(0xffffffffu, step));
+        n_slots += __popc(km);
     }
     if (lane != 0 || base >= capacity) return;
 #pragma unroll
@@ -619,13 +649,7 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
         for (int b = 0; b < kTileBufs; ++b) mbar_init(&bg_full[b], 1);
         mbar_init(patch_full, 1);
     }
-    if (ptid >= 0 && ptid < 4) {  // ring prologue: records 0 .. kRingAhead-1, one group each
-#pragma unroll
-        for (int i = 0; i < kRingAhead; ++i) {
-            cp_async16(reinterpret_cast<uint8_t *>(ring + i) + 16 * ptid, reinterpret_cast<const uint8_t *>(stream + i) + 16 * ptid);
-            cp_async_commit();
-        }
-    }
+    int fetched = 0;  // records whose copy into the ring has been issued (one cp.async group each)
 
     // consumer state (uniform across the CTA)
     int pos = 0;          // record being consumed
@@ -723,36 +747,36 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
     for (;;) {
         PROF_MARK(0);  // end of the previous record (tile begin / step tail / NOP)
         if (ptid >= 0 && ptid < 4) {
-            cp_async_wait<kRingAhead - 1 - kLook>();  // records <= pos + kLook have landed
-            cp_async16(reinterpret_cast<uint8_t *>(ring + ((pos + kRingAhead) & (kRing - 1))) + 16 * ptid,
-                       reinterpret_cast<const uint8_t *>(stream + pos + kRingAhead) + 16 * ptid);
-            cp_async_commit();
+            // top the ring up to record pos + kRingAhead - 1 (an iteration consumes one or two records), then
+            // wait until all but the newest kRingAhead - 1 - kLook copies have landed: records <= pos + kLook
+            for (; fetched < pos + kRingAhead; ++fetched) {
+                cp_async16(reinterpret_cast<uint8_t *>(ring + (fetched & (kRing - 1))) + 16 * ptid,
+                           reinterpret_cast<const uint8_t *>(stream + fetched) + 16 * ptid);
+                cp_async_commit();
+            }
+            cp_async_wait<kRingAhead - 1 - kLook>();
         }
         __syncthreads();  // (A) ring visible; every thread is done with the previous record
         PROF_MARK(1);  // barrier (A)
         if (store_pending) flush_tile();
-        const Cmd &cmd = ring[pos & (kRing - 1)];
-        const uint32_t kind = cmd.w[0];
-        if (kind == kCmdEnd) break;
-        if (tid == kProducerTid && (kind == kCmdTile || ppos <= pos)) producer_advance(pos + kLook);
-        if (kind == kCmdNop) {
-            ++pos;
-            PROF_MARK(9);  // NOP record
-            continue;
-        }
-        if (kind == kCmdTile) {
+        if (ring[pos & (kRing - 1)].w[0] == kCmdEnd) break;
+        const int limit = pos + kLook;  // last record the ring is guaranteed to hold during this iteration
+        if (tid == kProducerTid && (ring[pos & (kRing - 1)].w[0] == kCmdTile || ppos <= pos)) producer_advance(limit);
+        if (ring[pos & (kRing - 1)].w[0] == kCmdTile) {
+            // a TILE record is always followed by its first step: both are consumed in this iteration
+            const Cmd &tc = ring[pos & (kRing - 1)];
             ++ctseq;
-            steps_left = (int)cmd.w[1];
-            c_flags = cmd.w[6];
-            if (tid < 16) trec[tid] = cmd.w[tid];  // read after the next barrier at the earliest
+            steps_left = (int)tc.w[1];
+            c_flags = tc.w[6];
+            if (tid < 16) trec[tid] = tc.w[tid];  // read after the next barrier at the earliest
             if (c_flags & kTileBgTma) {
                 bg_pending = true;
             } else {
                 // solid colour, or a background TMA cannot address: fill the buffer here
-                const uint32_t solid = cmd.w[5];
+                const uint32_t solid = tc.w[5];
                 if (tid == kProducerTid) bulk_wait_read<kTileBufs - 1>();  // the store that last read this buffer is done
                 __syncthreads();
-                uint32_t *ct = ctile + (ctseq & (kTileBufs - 1)) * kTileWords;
+                uint32_t *ctb = ctile + (ctseq & (kTileBufs - 1)) * kTileWords;
                 const int xx = tid & (kTileW - 1);
                 if (c_flags & kTileHasBg) {
                     const DevCanvas &cv = canvases[c_canvas];
@@ -760,22 +784,19 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
                     const int64_t pitch = cv.bg_pitch;
                     if (tid < kElemThreads && xx < c_tw)
                         for (int yy = tid / kTileW; yy < c_th; yy += kRowSweep)
-                            ct[ct_off(yy, xx)] = ld_px(bg, (int64_t)(c_ty0 + yy) * pitch + (int64_t)(c_tx0 + xx) * 4);
+                            ctb[ct_off(yy, xx)] = ld_px(bg, (int64_t)(c_ty0 + yy) * pitch + (int64_t)(c_tx0 + xx) * 4);
                 } else {
                     if (tid < kElemThreads)
-                        for (int yy = tid / kTileW; yy < kTileH; yy += kRowSweep) ct[ct_off(yy, xx)] = solid;
+                        for (int yy = tid / kTileW; yy < kTileH; yy += kRowSweep) ctb[ct_off(yy, xx)] = solid;
                 }
+                __syncthreads();  // the tile's first step (same iteration) may composite right away
                 bg_pending = false;
             }
-            if (steps_left == 0) {
-                finish_tile();
-                PROF_MARK(8);  // empty tile (waits for its background)
-            } else {
-                PROF_MARK(7);  // tile begin
-            }
+            PROF_MARK(7);  // tile begin
             ++pos;
-            continue;
         }
+        const Cmd &cmd = ring[pos & (kRing - 1)];
+        const uint32_t kind = cmd.w[0];
         uint32_t *ct = ctile + (ctseq & (kTileBufs - 1)) * kTileWords;
         const int dx = (int)(cmd.w[2] & 0xffu), dy = (int)((cmd.w[2] >> 8) & 0xffu);
         const int two = (int)((cmd.w[2] >> 16) & 0xffu), tho = (int)(cmd.w[2] >> 24);
@@ -814,7 +835,7 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
             PROF_MARK(5);  // barrier (B)
             if (tid == kProducerTid) {
                 patch_busy = false;
-                producer_advance(pos + kLook);  // the next patch streams in during this V pass
+                producer_advance(limit);  // the next patch streams in during this V pass
             }
             if (bg_pending) {
                 mbar_wait(&bg_full[ctseq & (kTileBufs - 1)], (uint32_t)(ctseq / kTileBufs) & 1u);
@@ -851,7 +872,7 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
             __syncthreads();  // (B) P is free
             if (tid == kProducerTid) {
                 patch_busy = false;
-                producer_advance(pos + kLook);
+                producer_advance(limit);
             }
         } else {  // kCmdIdentLdg: overlay read with plain loads (source not addressable by TMA)
             if (bg_pending) {
