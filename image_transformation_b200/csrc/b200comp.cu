@@ -591,6 +591,7 @@ struct b200comp_plan {
     int64_t *d_stream_off = nullptr; // [G + 1]
     uint8_t *d_maps = nullptr;       // every CUtensorMap of the plan (placements, overlays, canvases)
     uint32_t *d_masks = nullptr;     // [tiles][mask_chunks][2] keep / opaque masks from the count kernel
+    int4 *d_boxes = nullptr;         // destination boxes (x, y, w, h) of the placements: the binning hit test
     int mask_chunks = 1;             // ceil(max placements per canvas / 32)
     std::vector<int64_t> tiles_before;  // prefix sum of tiles per canvas (n_canvases + 1)
     std::vector<void *> owned;  // device allocations freed with the plan
@@ -1106,6 +1107,10 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         CUDA_TRY(cudaMemcpyAsync(plan->d_tables, ts.host.data(), tbytes, cudaMemcpyHostToDevice, st));
     }
     CUDA_TRY(cudaMemcpyAsync(plan->d_placements, hp.data(), hp.size() * sizeof(DevPlacementT), cudaMemcpyHostToDevice, st));
+    std::vector<int4> hboxes(hp.size());
+    for (size_t i = 0; i < hp.size(); ++i) hboxes[i] = make_int4(hp[i].x, hp[i].y, hp[i].w, hp[i].h);
+    CUDA_TRY(dev_alloc((void **)&plan->d_boxes, hboxes.size() * sizeof(int4)));
+    CUDA_TRY(cudaMemcpyAsync(plan->d_boxes, hboxes.data(), hboxes.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(plan->d_canvases, hc.data(), hc.size() * sizeof(DevCanvas), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(plan->d_status, 0, sizeof(int), st));
     CUDA_TRY(cudaStreamSynchronize(st));  // host staging vectors die with this scope
@@ -1181,8 +1186,8 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
     for (int c0 = first; c0 < first + count; c0 += 65535) {  // grid.y is limited to 65535 canvases per launch
         const int nc = std::min(65535, first + count - c0);
         bin_count_kernel<<<dim3(gx, (unsigned)nc), kBinWarps * 32, 0, st>>>(
-            plan->d_canvases + c0, plan->d_placements, tile0, G, K, plan->d_bin, plan->d_masks, plan->mask_chunks,
-            plan->patch_words, plan->inter_words, c0 == first ? cursor : nullptr, plan->d_status);
+            plan->d_canvases + c0, plan->d_placements, plan->d_boxes, tile0, G, K, plan->d_bin, plan->d_masks,
+            plan->mask_chunks, plan->patch_words, plan->inter_words, c0 == first ? cursor : nullptr, plan->d_status);
     }
     if (int rc = checkpoint("bin_count_kernel")) return rc;
     bin_scan_kernel<<<(unsigned)((G + 7) / 8), 256, 0, st>>>(plan->d_bin, G, K, n_tiles, plan->d_stream_off, cursor,

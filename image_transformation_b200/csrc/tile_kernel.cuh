@@ -389,7 +389,7 @@ __device__ __forceinline__ void store_cmd(Cmd *dst, const uint32_t (&w)[16]) {
 constexpr int kBinWarps = 4;
 __global__ void __launch_bounds__(kBinWarps * 32)
 bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__restrict__ placements,
-                 int64_t run_tile_base, int G, int K, int32_t *__restrict__ cnt, uint32_t *__restrict__ masks,
+                 const int4 *__restrict__ boxes, int64_t run_tile_base, int G, int K, int32_t *__restrict__ cnt, uint32_t *__restrict__ masks,
                  int mask_chunks, int patch_words, int inter_words, unsigned long long *__restrict__ cursor,
                  int *__restrict__ status) {
     if (cursor && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *cursor = 0ull;  // first launch of a run
@@ -410,10 +410,12 @@ bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__
             continue;
         }
         const DevPlacementT &d = placements[cv.first + min(i, cv.count - 1)];
-        const bool hit = i < cv.count && max(tx0, d.x) < min(tx1, d.x + d.w) && max(ty0, d.y) < min(ty1, d.y + d.h);
+        const int4 bx = __ldg(boxes + cv.first + min(i, cv.count - 1));  // (x, y, w, h): one 16-byte load per lane
+        const bool hit = i < cv.count && max(tx0, bx.x) < min(tx1, bx.x + bx.z) && max(ty0, bx.y) < min(ty1, bx.y + bx.w);
         Geo g = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         bool fits = false;
-        if (hit && d.mode != 0) {
+        const int mode = hit ? d.mode : 0;
+        if (hit && mode != 0) {
             g = tile_geometry(d, tx0, ty0, tx1, ty1);
             fits = d.pbw * d.nrbox <= patch_words && 4 * kTileW * (g.NRQ | 1) <= inter_words && 4 * g.NRQ <= d.nrbox &&
                    g.cw0 < 65536 && g.rw0 < 65536;
@@ -437,9 +439,9 @@ bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__
             if (lane == b) my_bits = bits;
         }
         // keep: identity overlays always; resampled ones unless nothing but alpha 0 lies under the tile
-        const bool keep = hit && (d.mode == 0 || (fits && (my_bits & 1u)));
+        const bool keep = hit && (mode == 0 || (fits && (my_bits & 1u)));
         const uint32_t km = __ballot_sync(0xffffffffu, keep);
-        const uint32_t om = __ballot_sync(0xffffffffu, keep && d.mode != 0 && !(my_bits & 2u));  // every alpha 255
+        const uint32_t om = __ballot_sync(0xffffffffu, keep && mode != 0 && !(my_bits & 2u));  // every alpha 255
         if (lane == 0) {
             mk[2 * chunk] = km;
             mk[2 * chunk + 1] = om;
