@@ -171,6 +171,18 @@ class CompositeBatch:
         with torch.cuda.device(self.pool.device):
             _native.check(_native.lib().b200comp_plan_check(self._plan, _stream_handle(stream)), "CompositeBatch.check")
 
+    def profile(self, enable: bool = True) -> None:
+        """Bracket the phases of every following run() with CUDA events on the launching stream."""
+        _native.check(_native.lib().b200comp_plan_profile(self._plan, int(bool(enable))), "CompositeBatch.profile")
+
+    def profile_read(self) -> dict:
+        """Summed phase durations (ms) of the runs since profile(True); synchronises the stream."""
+        ms = (ctypes.c_double * 3)()
+        runs = ctypes.c_int(0)
+        with torch.cuda.device(self.pool.device):
+            _native.check(_native.lib().b200comp_plan_profile_read(self._plan, ms, ctypes.byref(runs)), "CompositeBatch.profile_read")
+        return {"runs": int(runs.value), "prepare_ms": float(ms[0]), "binning_ms": float(ms[1]), "tile_kernel_ms": float(ms[2])}
+
     def output(self, i: int) -> torch.Tensor:
         w, h = self.sizes[i]
         o = self._out_off[i]

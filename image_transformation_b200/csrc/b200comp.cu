@@ -594,6 +594,13 @@ struct b200comp_plan {
     int4 *d_boxes = nullptr;         // destination boxes (x, y, w, h) of the placements: the binning hit test
     int mask_chunks = 1;             // ceil(max placements per canvas / 32)
     std::vector<int64_t> tiles_before;  // prefix sum of tiles per canvas (n_canvases + 1)
+    // b200comp_plan_profile: events around the phases of every run (4 per run: before prepare, before
+    // binning, before the tile kernel, after it); a prepare without a run contributes nothing
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;
+    cudaEvent_t prof_prepare[2] = {nullptr, nullptr};
+    bool prof_prepare_valid = false;
+    int prof_runs = 0;
     std::vector<void *> owned;  // device allocations freed with the plan
 };
 
@@ -769,6 +776,8 @@ int b200comp_plan_destroy(b200comp_plan *plan) {
     cudaGetDevice(&cur);
     if (cur != plan->device) cudaSetDevice(plan->device);
     for (void *p : plan->owned) cudaFreeAsync(p, plan->create_stream);
+    for (cudaEvent_t e : plan->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : plan->prof_prepare) if (e) cudaEventDestroy(e);
     if (cur != plan->device) cudaSetDevice(cur);
     delete plan;
     return 0;
@@ -1140,6 +1149,10 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
 int b200comp_plan_prepare(b200comp_plan *plan, void *stream) {
     if (!plan) return fail(B200COMP_EINVAL, "plan_prepare: null plan");
     cudaStream_t st = S(stream);
+    if (plan->profile) {
+        for (auto &e : plan->prof_prepare) if (!e) CUDA_TRY(cudaEventCreate(&e));
+        CUDA_TRY(cudaEventRecord(plan->prof_prepare[0], st));
+    }
     for (auto &pr : plan->pre) {
         const int32_t *t = plan->d_tables;
         int rc = resample_two_pass(pr.src, pr.sw, pr.sh, pr.sp, pr.dst, pr.w, pr.h, (int64_t)((pr.w * 4 + 15) & ~15), t + pr.tx.k_off,
@@ -1156,6 +1169,10 @@ int b200comp_plan_prepare(b200comp_plan *plan, void *stream) {
             prepare_cutouts_kernel<<<dim3((unsigned)plan->prep_blocks_x, (unsigned)np), 256, 0, st>>>(plan->d_prep + p0);
         }
         CUDA_TRY(cudaGetLastError());
+    }
+    if (plan->profile) {
+        CUDA_TRY(cudaEventRecord(plan->prof_prepare[1], st));
+        plan->prof_prepare_valid = true;
     }
     return 0;
 }
@@ -1174,6 +1191,14 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
     const int K = (int)((n_tiles + G - 1) / G);
     const unsigned gx = (unsigned)((plan->max_tiles + kBinWarps - 1) / kBinWarps);  // warp = tile
     unsigned long long *cursor = reinterpret_cast<unsigned long long *>(plan->d_stream_off + G);  // record allocator
+    cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
+    if (plan->profile) {
+        for (auto &e : pe) {
+            CUDA_TRY(cudaEventCreate(&e));
+            plan->prof_events.push_back(e);
+        }
+        CUDA_TRY(cudaEventRecord(pe[0], st));
+    }
     // B200COMP_DEBUG_SYNC=1: synchronise after every launch so a device fault names its kernel
     static const bool debug_sync = std::getenv("B200COMP_DEBUG_SYNC") != nullptr;
     auto checkpoint = [&](const char *what) -> int {
@@ -1201,10 +1226,15 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
             reinterpret_cast<const uint32_t *>(plan->d_tables));
     }
     if (int rc = checkpoint("bin_fill_kernel")) return rc;
+    if (pe[1]) CUDA_TRY(cudaEventRecord(pe[1], st));
     composite_stream_kernel<<<(unsigned)G, kThreads, plan->smem_bytes, st>>>(
         plan->d_streams, plan->d_stream_off, plan->d_canvases, plan->d_maps,
         reinterpret_cast<const uint32_t *>(plan->d_tables), plan->patch_words, plan->inter_words);
     CUDA_TRY(cudaGetLastError());
+    if (pe[2]) {
+        CUDA_TRY(cudaEventRecord(pe[2], st));
+        ++plan->prof_runs;
+    }
     if (int rc = checkpoint("composite_stream_kernel")) return rc;
     return 0;
 }
@@ -1272,6 +1302,37 @@ int b200comp_debug_profile_(unsigned long long *out16) {
     (void)out16;
     return B200COMP_EINVAL;
 #endif
+}
+
+int b200comp_plan_profile(b200comp_plan *plan, int enable) {
+    if (!plan) return fail(B200COMP_EINVAL, "plan_profile: null plan");
+    plan->profile = enable != 0;
+    return 0;
+}
+
+int b200comp_plan_profile_read(b200comp_plan *plan, double ms[3], int *runs) {
+    if (!plan || !ms) return fail(B200COMP_EINVAL, "plan_profile_read: null argument");
+    ms[0] = ms[1] = ms[2] = 0.0;
+    if (runs) *runs = plan->prof_runs;
+    if (!plan->prof_events.empty()) CUDA_TRY(cudaEventSynchronize(plan->prof_events.back()));
+    for (size_t i = 0; i + 2 < plan->prof_events.size(); i += 3) {
+        float a = 0.f, b = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&a, plan->prof_events[i], plan->prof_events[i + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&b, plan->prof_events[i + 1], plan->prof_events[i + 2]));
+        ms[1] += a;
+        ms[2] += b;
+    }
+    // the prepare kernel runs once per b200comp_plan_run; only the last one is still bracketed
+    if (plan->prof_prepare_valid && plan->prof_runs > 0) {
+        float p = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&p, plan->prof_prepare[0], plan->prof_prepare[1]));
+        ms[0] = (double)p * plan->prof_runs;
+    }
+    for (cudaEvent_t e : plan->prof_events) cudaEventDestroy(e);
+    plan->prof_events.clear();
+    plan->prof_runs = 0;
+    plan->prof_prepare_valid = false;
+    return 0;
 }
 
 int b200comp_plan_info(const b200comp_plan *plan, int64_t *info) {

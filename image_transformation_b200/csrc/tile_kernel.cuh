@@ -386,7 +386,7 @@ __device__ __forceinline__ void store_cmd(Cmd *dst, const uint32_t (&w)[16]) {
 // must have some non-zero alpha (the whole warp reads the summary rectangle of each candidate).  The keep /
 // opaque masks go to `masks` for the fill kernel; the tile's slot count (1 + steps, or 0 for a tile nothing
 // is drawn on -- such tiles never enter a stream) is stored stream-major for the scan.
-constexpr int kBinWarps = 4;
+constexpr int kBinWarps = 4;  // tiles per block (16 measured slower: uneven tiles hold block slots)
 __global__ void __launch_bounds__(kBinWarps * 32)
 bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__restrict__ placements,
                  const int4 *__restrict__ boxes, int64_t run_tile_base, int G, int K, int32_t *__restrict__ cnt, uint32_t *__restrict__ masks,

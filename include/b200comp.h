@@ -149,6 +149,13 @@ int b200comp_plan_info(const b200comp_plan *plan, int64_t *info /* [B200COMP_INF
 /* Synchronise `stream` and read the kernel's status word: fails with B200COMP_EINTERNAL if a
  * tile needed more shared memory than the plan sized (never silently wrong pixels). */
 int b200comp_plan_check(b200comp_plan *plan, void *stream);
+/* Measurement aid (bench.py): with profiling enabled every b200comp_plan_run[_canvases] brackets the
+ * prepare kernel, the three binning kernels and the tile kernel with CUDA events on the launching
+ * stream.  b200comp_plan_profile_read synchronises the stream of the last run and returns the summed
+ * durations in milliseconds: ms[0] prepare, ms[1] binning, ms[2] tile kernel; *runs = runs measured;
+ * the counters are reset. */
+int b200comp_plan_profile(b200comp_plan *plan, int enable);
+int b200comp_plan_profile_read(b200comp_plan *plan, double ms[3], int *runs);
 
 /* create + run + destroy */
 int b200comp_composite_batch(const b200comp_canvas *canvases, int n_canvases, const b200comp_placement *placements,

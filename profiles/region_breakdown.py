@@ -34,15 +34,18 @@ def main():
         return next(i + 1 for i, l in enumerate(src) if s in l)
 
     kernel = "composite_stream_kernel"
-    marks = [(find("void prefetch_l1"), "prefetch"),
+    marks = [(find("void mbar_init"), "mbarrier waits (patch / background landed)"),
+             (find("void tma_load_patch"), "TMA / bulk-group issue helpers"),
+             (find("void prefetch_l1"), "prefetch"),
              (find("void tile_hpass("), "hpass"), (find("void tile_vpass_over("), "vpass"),
              (find("struct DevPlacementT"), "binning (not this kernel)"),
              (find("composite_stream_kernel(const Cmd"), "main:setup / ring prologue"),
              (find("auto producer_advance"), "main:producer (TMA issue)"),
              (find("auto finish_tile"), "main:finish tile (store)"),
              (find("for (;;) {"), "main:ring + dispatch"),
-             (find("if (kind == kCmdTile) {"), "main:tile begin"),
+             (find("if (ring[pos & (kRing - 1)].w[0] == kCmdTile) {"), "main:tile begin"),
              (find("if (kind == kCmdResample) {"), "main:resample glue (decode, waits)"),
+             (find("__syncthreads();  // (B) H pass done"), "main:barrier (B) + V pass call"),
              (find("} else if (kind == kCmdIdentTma) {"), "main:identity over"),
              (find("if (--steps_left == 0) finish_tile();"), "main:step end")]
 
