@@ -20,6 +20,7 @@ EXPORTED = (
     "b200comp_build_coeffs", "b200comp_resize_rgba_lanczos", "b200comp_resample_rgba", "b200comp_alpha_over",
     "b200comp_plan_create", "b200comp_plan_run", "b200comp_plan_prepare", "b200comp_plan_run_canvases",
     "b200comp_plan_destroy", "b200comp_plan_info", "b200comp_plan_profile", "b200comp_plan_profile_read",
+    "b200comp_plan_last_records",
     "b200comp_plan_check", "b200comp_composite_batch", "b200comp_composite_batch_host",
     "b200comp_composite_host", "b200comp_host_alloc", "b200comp_host_free", "b200comp_masked_median_rgb",
     "b200comp_fill_rgba", "b200comp_fill_gradient", "b200comp_masked_median_rgb_host",
@@ -84,6 +85,7 @@ def _load() -> ctypes.CDLL:
     L.b200comp_plan_destroy.argtypes = [vp]
     L.b200comp_plan_info.argtypes = [vp, POINTER(c_int64)]
     L.b200comp_plan_check.argtypes = [vp, vp]
+    L.b200comp_plan_last_records.argtypes = [vp, vp, POINTER(c_int64)]
     L.b200comp_plan_profile.argtypes = [vp, c_int]
     L.b200comp_plan_profile_read.argtypes = [vp, POINTER(ctypes.c_double), POINTER(c_int)]
     L.b200comp_composite_batch.argtypes = [POINTER(Canvas), c_int, POINTER(Placement), c_int, vp]

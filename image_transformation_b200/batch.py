@@ -171,6 +171,14 @@ class CompositeBatch:
         with torch.cuda.device(self.pool.device):
             _native.check(_native.lib().b200comp_plan_check(self._plan, _stream_handle(stream)), "CompositeBatch.check")
 
+    def last_records(self, stream: Optional[torch.cuda.Stream] = None) -> int:
+        """Command records written by the binning pass of the last run (tiles + surviving steps + one END per CTA)."""
+        n = ctypes.c_int64(0)
+        with torch.cuda.device(self.pool.device):
+            _native.check(_native.lib().b200comp_plan_last_records(self._plan, _stream_handle(stream), ctypes.byref(n)),
+                          "CompositeBatch.last_records")
+        return int(n.value)
+
     def profile(self, enable: bool = True) -> None:
         """Bracket the phases of every following run() with CUDA events on the launching stream."""
         _native.check(_native.lib().b200comp_plan_profile(self._plan, int(bool(enable))), "CompositeBatch.profile")

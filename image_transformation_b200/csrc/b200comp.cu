@@ -1208,11 +1208,14 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
         if (e != cudaSuccess) return fail(B200COMP_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
         return 0;
     };
+    // B200COMP_NO_CULL=1 keeps the steps an opaque, tile-covering later placement hides (A/B parity tests)
+    const char *no_cull = std::getenv("B200COMP_NO_CULL");
+    const int cull = !(no_cull && no_cull[0] == '1');
     for (int c0 = first; c0 < first + count; c0 += 65535) {  // grid.y is limited to 65535 canvases per launch
         const int nc = std::min(65535, first + count - c0);
         bin_count_kernel<<<dim3(gx, (unsigned)nc), kBinWarps * 32, 0, st>>>(
             plan->d_canvases + c0, plan->d_placements, plan->d_boxes, tile0, G, K, plan->d_bin, plan->d_masks,
-            plan->mask_chunks, plan->patch_words, plan->inter_words, c0 == first ? cursor : nullptr, plan->d_status);
+            plan->mask_chunks, plan->patch_words, plan->inter_words, c0 == first ? cursor : nullptr, plan->d_status, cull);
     }
     if (int rc = checkpoint("bin_count_kernel")) return rc;
     bin_scan_kernel<<<(unsigned)((G + 7) / 8), 256, 0, st>>>(plan->d_bin, G, K, n_tiles, plan->d_stream_off, cursor,
@@ -1348,6 +1351,15 @@ int b200comp_plan_check(b200comp_plan *plan, void *stream) {
     CUDA_TRY(cudaMemcpyAsync(&h, plan->d_status, sizeof h, cudaMemcpyDeviceToHost, S(stream)));
     CUDA_TRY(cudaStreamSynchronize(S(stream)));
     if (h != 0) return fail(B200COMP_EINTERNAL, "binning reported a sizing violation (status " + std::to_string(h) + ")");
+    return 0;
+}
+
+int b200comp_plan_last_records(b200comp_plan *plan, void *stream, int64_t *records) {
+    if (!plan || !records) return fail(B200COMP_EINVAL, "plan_last_records: null argument");
+    unsigned long long h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, plan->d_stream_off + plan->G, sizeof h, cudaMemcpyDeviceToHost, S(stream)));
+    CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    *records = (int64_t)h;
     return 0;
 }
 

@@ -63,7 +63,7 @@ struct __align__(16) Cmd {
 };
 static_assert(sizeof(Cmd) == 64, "Cmd layout");
 enum : uint32_t { kCmdTile = 0, kCmdResample = 1, kCmdIdentTma = 2, kCmdIdentLdg = 3, kCmdNop = 4, kCmdEnd = 5 };
-enum : uint32_t { kTileBgTma = 1, kTileOutTma = 2, kTileHasBg = 4 };
+enum : uint32_t { kTileBgTma = 1, kTileOutTma = 2, kTileHasBg = 4, kTileNoBg = 8 };
 constexpr int kRing = 8;       // command ring slots in shared memory
 constexpr int kRingAhead = 6;  // records fetched ahead of the consumer
 constexpr int kLook = 3;       // records the producer may run ahead of the consumer

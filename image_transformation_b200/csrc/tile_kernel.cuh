@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kBinWarps * 32)
 bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__restrict__ placements,
                  const int4 *__restrict__ boxes, int64_t run_tile_base, int G, int K, int32_t *__restrict__ cnt, uint32_t *__restrict__ masks,
                  int mask_chunks, int patch_words, int inter_words, unsigned long long *__restrict__ cursor,
-                 int *__restrict__ status) {
+                 int *__restrict__ status, int cull) {
     if (cursor && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *cursor = 0ull;  // first launch of a run
     const DevCanvas &cv = canvases[blockIdx.y];
     const int lane = threadIdx.x & 31;
@@ -403,6 +403,7 @@ bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__
     const int64_t t = cv.tile_base - run_tile_base + local;
     uint32_t *mk = masks + t * (int64_t)mask_chunks * 2;
     int n = 0;
+    int occ_chunk = -1, occ_top = 0;  // last placement that hides everything under it on this tile
     for (int chunk = 0; chunk < mask_chunks; ++chunk) {
         const int i = chunk * 32 + lane;
         if (chunk * 32 >= cv.count) {  // canvases with fewer placements than the widest one of the plan
@@ -441,14 +442,32 @@ bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__
         // keep: identity overlays always; resampled ones unless nothing but alpha 0 lies under the tile
         const bool keep = hit && (mode == 0 || (fits && (my_bits & 1u)));
         const uint32_t km = __ballot_sync(0xffffffffu, keep);
-        const uint32_t om = __ballot_sync(0xffffffffu, keep && mode != 0 && !(my_bits & 2u));  // every alpha 255
+        const bool opaque = keep && mode != 0 && !(my_bits & 2u);  // every alpha 255
+        const uint32_t om = __ballot_sync(0xffffffffu, opaque);
+        // Occlusion: an opaque placement whose box covers the whole tile replaces every pixel of it (the V pass
+        // stores its pixels without reading the canvas), so nothing drawn earlier -- earlier placements and
+        // the background -- can show.  Those steps are dropped; the result is unchanged bit for bit.
+        const uint32_t cm = __ballot_sync(0xffffffffu, cull && opaque && g.two == tx1 - tx0 && g.tho == ty1 - ty0);
         if (lane == 0) {
             mk[2 * chunk] = km;
             mk[2 * chunk + 1] = om;
         }
-        n += __popc(km);
+        if (cm) {
+            occ_chunk = chunk;
+            occ_top = 31 - __clz((int)cm);
+            n = __popc(km >> occ_top);
+        } else {
+            n += __popc(km);
+        }
     }
-    if (lane == 0) cnt[(t % G) * K + t / G] = n ? n + 1 : 0;
+    if (lane == 0) {
+        if (occ_chunk >= 0) {
+            for (int c = 0; c < occ_chunk; ++c) mk[2 * c] = mk[2 * c + 1] = 0u;
+            mk[2 * occ_chunk] &= ~((1u << occ_top) - 1u);
+            mk[2 * occ_chunk + 1] &= ~((1u << occ_top) - 1u);
+        }
+        cnt[(t % G) * K + t / G] = n ? n + 1 : 0;
+    }
 }
 
 // exclusive scan of every stream's row (in place), one warp per stream; the stream's region of the record
@@ -528,8 +547,11 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
     const int64_t base = stream_off[t % G] + scan[(t % G) * K + t / G];
     int n_slots = 0;
     uint32_t w[16];
+    bool first_seen = false;
+    uint32_t nobg = 0u;  // the tile's first step replaces every pixel: the background is never read
     for (int i0 = 0, chunk = 0; i0 < cv.count && chunk < mask_chunks; i0 += 32, ++chunk) {
         const uint32_t km = mk[2 * chunk], om = mk[2 * chunk + 1];
+        bool occludes = false;
         if ((km >> lane) & 1u) {
             const DevPlacementT &d = placements[cv.first + i0 + lane];
             const int64_t at = base + 1 + n_slots + __popc(km & ((1u << lane) - 1u));
@@ -559,6 +581,7 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
                 }
             } else {
                 const Geo g = tile_geometry(d, tx0, ty0, tx1, ty1);
+                occludes = ((om >> lane) & 1u) && g.two == tx1 - tx0 && g.tho == ty1 - ty0;
                 w[0] = kCmdResample;
                 w[1] = (uint32_t)d.nwx | ((uint32_t)d.nwy << 8) | (((om >> lane) & 1u) ? (3u << 16) : (4u << 16)) | ((uint32_t)g.NRQ << 24);
                 w[2] = (uint32_t)(g.ix0 - tx0) | ((uint32_t)(g.iy0 - ty0) << 8) | ((uint32_t)g.two << 16) | ((uint32_t)g.tho << 24);
@@ -577,6 +600,10 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
             }
             if (at < capacity) store_cmd(streams + at, w);  // overflow is flagged by the scan kernel
         }
+        if (!first_seen && km) {
+            first_seen = true;
+            nobg = (__ballot_sync(0xffffffffu, occludes) >> (__ffs((int)km) - 1)) & 1u;
+        }
         n_slots += __popc(km);
     }
     if (lane != 0 || base >= capacity) return;
@@ -588,7 +615,8 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
     w[3] = (uint32_t)ty0;
     w[4] = (uint32_t)(tx1 - tx0) | ((uint32_t)(ty1 - ty0) << 16);
     w[5] = cv.solid;
-    w[6] = (cv.bg ? kTileHasBg : 0u) | (cv.bg && cv.bg_map ? kTileBgTma : 0u) | (cv.out_map ? kTileOutTma : 0u);
+    w[6] = nobg ? (kTileNoBg | (cv.out_map ? kTileOutTma : 0u))
+                : ((cv.bg ? kTileHasBg : 0u) | (cv.bg && cv.bg_map ? kTileBgTma : 0u) | (cv.out_map ? kTileOutTma : 0u));
     w[7] = (uint32_t)(canvas0 + (int)blockIdx.y);
     const uint64_t bm = reinterpret_cast<uint64_t>(cv.bg_map), om = reinterpret_cast<uint64_t>(cv.out_map);
     w[8] = (uint32_t)bm; w[9] = (uint32_t)(bm >> 32);
@@ -688,6 +716,8 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
                     mbar_expect_tx(&bg_full[b], tw > 32 ? 8192u : 4096u);
                     tma_load_2d(ctile + b * kTileWords, map, (int)c.w[2], (int)c.w[3], &bg_full[b]);
                     if (tw > 32) tma_load_2d(ctile + b * kTileWords + 1024, map, (int)c.w[2] + 32, (int)c.w[3], &bg_full[b]);
+                } else if (c.w[6] & kTileNoBg) {
+                    bulk_wait_read<1>();  // nothing to load, but the buffer must be free before the first step writes it
                 }
                 ++ptseq;
             } else if (kind == kCmdResample) {
@@ -711,11 +741,20 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
 
     // The tile's pixels are final.  The store itself is issued after the next (A) barrier (flush_tile), so a
     // finished tile costs no barrier of its own.
+    // Background loads complete phases of bg_full[b] one by one, but only tiles that HAVE a TMA background use
+    // one (solid-colour, generically loaded and fully occluded tiles do not): the parity to wait for is counted
+    // per buffer, not derived from the tile sequence number.
+    uint32_t bg_phase = 0u;  // bit b = parity of the next phase of bg_full[b]
+    auto wait_bg = [&]() {
+        const int b = ctseq & (kTileBufs - 1);
+        mbar_wait(&bg_full[b], (bg_phase >> b) & 1u);
+        bg_phase ^= 1u << b;
+        bg_pending = false;
+    };
     bool store_pending = false;
     auto finish_tile = [&]() {
         if (bg_pending) {
-            mbar_wait(&bg_full[ctseq & (kTileBufs - 1)], (uint32_t)(ctseq / kTileBufs) & 1u);
-            bg_pending = false;
+            wait_bg();
         }
         if (c_flags & kTileOutTma) fence_async_smem();  // generic writes to the tile -> visible to the async proxy
         store_pending = true;
@@ -773,6 +812,10 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
             if (tid < 16) trec[tid] = tc.w[tid];  // read after the next barrier at the earliest
             if (c_flags & kTileBgTma) {
                 bg_pending = true;
+            } else if (c_flags & kTileNoBg) {
+                // the first step is an opaque placement over the whole tile: it stores every pixel (after barrier
+                // (B), i.e. after the producer has seen this record and waited for the buffer's last store)
+                bg_pending = false;
             } else {
                 // solid colour, or a background TMA cannot address: fill the buffer here
                 const uint32_t solid = tc.w[5];
@@ -840,8 +883,7 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
                 producer_advance(limit);  // the next patch streams in during this V pass
             }
             if (bg_pending) {
-                mbar_wait(&bg_full[ctseq & (kTileBufs - 1)], (uint32_t)(ctseq / kTileBufs) & 1u);
-                bg_pending = false;
+                wait_bg();
             }
 #define B200_VPASS(NWY, NCH_) \
     tile_vpass_over<NWY, NCH_>(I, iplane_stride, IPW, ct, rw0, oy0, tho, two, dx, dy, scale_y, support_y, ply, n_out_y)
@@ -861,8 +903,7 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
             mbar_wait(patch_full, pseq & 1u);
             ++pseq;
             if (bg_pending) {
-                mbar_wait(&bg_full[ctseq & (kTileBufs - 1)], (uint32_t)(ctseq / kTileBufs) & 1u);
-                bg_pending = false;
+                wait_bg();
             }
             const int xx = tid & (kTileW - 1);
             const int shift = (int)cmd.w[5];
@@ -878,8 +919,7 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
             }
         } else {  // kCmdIdentLdg: overlay read with plain loads (source not addressable by TMA)
             if (bg_pending) {
-                mbar_wait(&bg_full[ctseq & (kTileBufs - 1)], (uint32_t)(ctseq / kTileBufs) & 1u);
-                bg_pending = false;
+                wait_bg();
             }
             const uint8_t *src = reinterpret_cast<const uint8_t *>((uint64_t)cmd.w[12] | ((uint64_t)cmd.w[13] << 32));
             const int64_t spitch = (int64_t)cmd.w[6];

@@ -149,6 +149,10 @@ int b200comp_plan_info(const b200comp_plan *plan, int64_t *info /* [B200COMP_INF
 /* Synchronise `stream` and read the kernel's status word: fails with B200COMP_EINTERNAL if a
  * tile needed more shared memory than the plan sized (never silently wrong pixels). */
 int b200comp_plan_check(b200comp_plan *plan, void *stream);
+/* Synchronise `stream` and return the number of command records the binning pass of the last
+ * b200comp_plan_run[_canvases] wrote: one per tile something is drawn on, one per (tile, placement)
+ * step that survived the transparency and occlusion tests, one END per persistent CTA. */
+int b200comp_plan_last_records(b200comp_plan *plan, void *stream, int64_t *records);
 /* Measurement aid (bench.py): with profiling enabled every b200comp_plan_run[_canvases] brackets the
  * prepare kernel, the three binning kernels and the tile kernel with CUDA events on the launching
  * stream.  b200comp_plan_profile_read synchronises the stream of the last run and returns the summed

@@ -235,7 +235,8 @@ def run_batch(B, pool_arrays, sizes, placements, bgs=None, solid=None):
     cb.run()
     cb.check()
     outs = [host(o) for o in cb.outputs()]
-    info = cb.info
+    info = dict(cb.info)
+    info["records"] = cb.last_records()
     cb.close()
     return outs, info
 
@@ -480,6 +481,62 @@ def test_batch_many_placements_per_tile(B):
     bg = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
     outs, _ = run_batch(B, pool, [(W, H)], [pl], bgs=[bg])
     assert_same(outs[0], oracle.composite(bg, pool, pl), "150 placements")
+
+
+def test_batch_occlusion_culling(B, monkeypatch):
+    """Steps hidden by a later opaque placement that covers the whole tile are dropped by the binning pass
+    (and the tile's background is never loaded).  Opaque and soft-edged cutouts stacked 70 deep (occluders in
+    the second and third binning chunk hide the first), semi-transparent random background: bit-exact vs the
+    oracle, identical with culling switched off, and the culled run really has fewer steps."""
+    rng = np.random.default_rng(77)
+    from image_transformation_b200 import synth
+
+    pool = {}
+    for k in range(1, 5):  # fully opaque rectangles: every interior tile is an occluder
+        a = rng.integers(0, 256, (int(rng.integers(150, 400)), int(rng.integers(150, 400)), 4), dtype=np.uint8)
+        a[..., 3] = 255
+        pool[k] = a
+    for k in range(5, 9):  # soft-edged masks: occluders in the interior only
+        pool[k] = synth.make_cutout(rng, int(rng.integers(150, 400)), int(rng.integers(150, 400)))
+    W, H = 700, 500
+    pl = []
+    for _ in range(70):
+        oid = int(rng.integers(1, 9))
+        sh, sw = pool[oid].shape[:2]
+        s = 1.0 if rng.random() < 0.15 else float(rng.uniform(0.5, 1.6))
+        w, h = max(1, round(sw * s)), max(1, round(sh * s))
+        x, y = int(rng.integers(-w // 3, W - w // 2)), int(rng.integers(-h // 3, H - h // 2))
+        pl.append({"object_id": oid, "box": [x, y, x + w, y + h]})
+    bg = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    exp = oracle.composite(bg, pool, pl)
+    outs, info = run_batch(B, pool, [(W, H)], [pl], bgs=[bg])
+    assert_same(outs[0], exp, "culled")
+    monkeypatch.setenv("B200COMP_NO_CULL", "1")
+    outs2, info2 = run_batch(B, pool, [(W, H)], [pl], bgs=[bg])
+    assert_same(outs2[0], exp, "not culled")
+    assert info["records"] < 0.7 * info2["records"], (info["records"], info2["records"])
+    monkeypatch.delenv("B200COMP_NO_CULL")
+    # several tiles per persistent CTA, occluded tiles (no background load) interleaved with ordinary ones: the
+    # background barriers' phases must be counted per buffer
+    W2, H2 = 2432, 1500
+    pl2 = []
+    for _ in range(40):
+        oid = int(rng.integers(1, 9))
+        sh, sw = pool[oid].shape[:2]
+        s = float(rng.uniform(1.0, 2.4))
+        w, h = round(sw * s), round(sh * s)
+        x, y = int(rng.integers(-w // 3, W2 - w // 2)), int(rng.integers(-h // 3, H2 - h // 2))
+        pl2.append({"object_id": oid, "box": [x, y, x + w, y + h]})
+    bg2 = rng.integers(0, 256, (H2, W2, 4), dtype=np.uint8)
+    outs4, _ = run_batch(B, pool, [(W2, H2), (W, H)], [pl2, pl], bgs=[bg2, None], solid=[(0, 0, 0, 0), (1, 2, 3, 255)])
+    assert_same(outs4[0], oracle.composite(bg2, pool, pl2), "large canvas, mixed tiles")
+    # solid-colour canvases take the same path (no background buffer at all)
+    outs3, _ = run_batch(B, pool, [(W, H), (333, 257)], [pl, pl], solid=(9, 8, 7, 200))
+    for o in outs3:
+        hh, ww = o.shape[:2]
+        sbg = np.empty((hh, ww, 4), np.uint8)
+        sbg[...] = (9, 8, 7, 200)
+        assert_same(o, oracle.composite(sbg, pool, pl), f"solid {ww}x{hh}")
 
 
 def test_batch_c4_aspect_sweep_vs_oracle(B):
