@@ -926,7 +926,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device);
-        plan->G = std::max(1, std::min(1024, 2 * sms));
+        plan->G = std::max(1, std::min(1024, kCtasPerSm * sms));
         plan->stream_capacity = tiles + step_records + plan->G;
     }
 

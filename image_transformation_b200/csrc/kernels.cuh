@@ -29,7 +29,11 @@ constexpr int kTileH = 32;
 #ifndef B200COMP_THREADS
 #define B200COMP_THREADS 384
 #endif
-constexpr int kThreads = B200COMP_THREADS;  // warps per CTA x 32; two CTAs per SM
+#ifndef B200COMP_CTAS_PER_SM
+#define B200COMP_CTAS_PER_SM 2
+#endif
+constexpr int kThreads = B200COMP_THREADS;  // warps per CTA x 32
+constexpr int kCtasPerSm = B200COMP_CTAS_PER_SM;  // persistent CTAs resident per SM (registers and shared memory permitting)
 constexpr int kWarps = kThreads / 32;
 // The last warp is the producer: its lane 0 issues every asynchronous copy (command ring, TMA loads and stores)
 // and does no pass work, so that bookkeeping never delays the compute warps at a barrier.
@@ -87,13 +91,25 @@ __device__ __forceinline__ uint32_t premultiply_px(uint32_t p) {
     return r | (g << 8) | (b << 16) | (a << 24);
 }
 
+// 255 * c / a for c, a < 256 without a division: with m = ceil(2^24 / a), (255 * c * m) >> 24 is the exact
+// truncated quotient (n = 255 * c < 2^16, a < 2^8: the round-up error n * (m * a - 2^24) / (a * 2^24) stays below
+// 1 / a; checked exhaustively by tests/test_host_logic.py).  One table lookup serves the three colour channels.
+struct UnpremulMagic {
+    uint32_t m[256];
+    constexpr UnpremulMagic() : m() {
+        for (uint32_t a = 1; a < 256; ++a) m[a] = ((1u << 24) + a - 1u) / a;
+    }
+};
+__device__ const UnpremulMagic g_unpremul_magic = UnpremulMagic();
+
 // Convert.c rgba2rgbA: RGBa -> RGBA, truncating divide, clip
 __device__ __forceinline__ uint32_t unpremultiply_px(uint32_t p) {
     const uint32_t a = p >> 24;
     if (a == 255u || a == 0u) return p;
-    const uint32_t r = min(255u, (255u * (p & 0xffu)) / a);
-    const uint32_t g = min(255u, (255u * ((p >> 8) & 0xffu)) / a);
-    const uint32_t b = min(255u, (255u * ((p >> 16) & 0xffu)) / a);
+    const uint32_t m = __ldg(&g_unpremul_magic.m[a]);
+    const uint32_t r = min(255u, __umulhi((p & 0xffu) * 65280u, m));  // (255 * c << 8) * m >> 32
+    const uint32_t g = min(255u, __umulhi(((p >> 8) & 0xffu) * 65280u, m));
+    const uint32_t b = min(255u, __umulhi(((p >> 16) & 0xffu) * 65280u, m));
     return r | (g << 8) | (b << 16) | (a << 24);
 }
 

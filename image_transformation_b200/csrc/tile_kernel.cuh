@@ -166,6 +166,8 @@ __device__ __forceinline__ void tma_load_patch(void *smem_dst, const void *tmap,
         ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(word), "r"(0), "r"(row), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // pull the coefficient rows this lane will need into L1 while the patch is being staged
@@ -213,7 +215,7 @@ __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int P
                                            const uint32_t *__restrict__ plx, int n_out, int nch) {
     // nch = 3 when every source alpha in the patch is 255: the alpha plane is then 255 after both passes
     // (255 * sum(k) + 2^21 >> 22 == 255 because |sum(k) - 2^22| <= taps) and is not computed
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler: row offsets go to uniform registers
     if (warp >= kComputeWarps) return;
     // two column groups of 32: the first (kComputeWarps + 1) / 2 warps take columns 0..31, the rest 32..63
     constexpr int kHalf = (kComputeWarps + 1) / 2;
@@ -288,9 +290,12 @@ __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, 
                                                 uint32_t *__restrict__ ctile, int rw0, int oy0, int tho, int two,
                                                 int tile_dx, int tile_dy, double scale, double support,
                                                 const uint32_t *__restrict__ ply, int n_out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane >= tho || warp >= kComputeWarps) return;
-    const int y = oy0 + lane;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    if (warp >= kComputeWarps) return;
+    // Lanes past the tile's last row redo the last row (same loads, same value stored to the same address): the
+    // warp stays converged, which lets the compiler keep the column / plane offsets in uniform registers.
+    const int lrow = min(lane, tho - 1);
+    const int y = oy0 + lrow;
     const int wbase = (first_tap(y, scale, support) >> 2) - rw0;
     uint32_t k0[NW], k1[NW], k2[NW];
 #pragma unroll
@@ -299,7 +304,7 @@ __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, 
         k1[i] = __ldg(ply + (int64_t)(1 * NW + i) * n_out + y);
         k2[i] = __ldg(ply + (int64_t)(2 * NW + i) * n_out + y);
     }
-    const int r = tile_dy + lane;
+    const int r = tile_dy + lrow;
     uint32_t *crow = ctile + (r << 5);
     for (int x = warp; x < two; x += kComputeWarps) {
         const uint32_t *col = I + x * IPW + wbase;
@@ -311,19 +316,22 @@ __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, 
             for (int i = 0; i < NW; ++i) wd[i] = col[c * iplane_stride + i];
             acc[c] = tap_sum<NW>(wd, k0, k1, k2);
         }
-        const int X = tile_dx + x;
-        uint32_t *cpx = crow + (((X & 32) << 5) | ((((X >> 2) ^ r) & 7) << 2) | (X & 3));
+        const int X = tile_dx + x;  // warp-uniform
+        uint32_t *cpx = crow + (((X & 32) << 5) | (X & 3)) + ((((X >> 2) ^ r) & 7) << 2);
+        // bytes packed with PRMT (the shift-and-or form compiles to IMAD.SHL on the FMA-heavy pipe)
+        const uint32_t rg = __byte_perm(clip8i(acc[0]), clip8i(acc[1]), 0x1140);
         if (NCH == 3) {  // every source alpha is 255: the pixel replaces the canvas pixel
-            *cpx = clip8i(acc[0]) | (clip8i(acc[1]) << 8) | (clip8i(acc[2]) << 16) | 0xff000000u;
-            continue;
+            *cpx = __byte_perm(rg, clip8i(acc[2]), 0x5410) | 0xff000000u;
+        } else {
+            // Alpha tests on the raw accumulator (clip8(acc) == 0 / == 255).  Do NOT test the clamped value:
+            // CUDA 12.9 ptxas folds `clamp(x) == 255` into VIMNMX.RELU's predicate output with the wrong
+            // sense on sm_100a (partially transparent pixels took the opaque branch).
+            if (acc[3] >= (1 << kPrecisionBits)) {  // else transparent: canvas pixel unchanged
+                const bool opaque = acc[3] >= (255 << kPrecisionBits);
+                const uint32_t s = __byte_perm(rg, __byte_perm(clip8i(acc[2]), clip8i(acc[3]), 0x1140), 0x5410);
+                *cpx = opaque ? s : over_px(*cpx, unpremultiply_px(s));
+            }
         }
-        // Alpha tests on the raw accumulator (clip8(acc) == 0 / == 255).  Do NOT test the clamped value:
-        // CUDA 12.9 ptxas folds `clamp(x) == 255` into VIMNMX.RELU's predicate output with the wrong
-        // sense on sm_100a (partially transparent pixels took the opaque branch).
-        if (acc[3] < (1 << kPrecisionBits)) continue;  // transparent: canvas pixel unchanged
-        const bool opaque = acc[3] >= (255 << kPrecisionBits);
-        const uint32_t s = clip8i(acc[0]) | (clip8i(acc[1]) << 8) | (clip8i(acc[2]) << 16) | (clip8i(acc[3]) << 24);
-        *cpx = opaque ? s : over_px(*cpx, unpremultiply_px(s));
     }
 }
 
@@ -654,7 +662,7 @@ __device__ unsigned long long g_prof[16];
 //   * source patches: one TMA box per step, issued as soon as the previous step's horizontal pass has
 //     released the patch buffer -- also across tile boundaries
 // Thread 0 is the producer (it only issues copies; it never waits for data on behalf of others).
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict__ stream_off,
                         const DevCanvas *__restrict__ canvases, const uint8_t *__restrict__ maps,
                         const uint32_t *__restrict__ tables, int patch_words, int inter_words) {
@@ -843,16 +851,22 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
         const Cmd &cmd = ring[pos & (kRing - 1)];
         const uint32_t kind = cmd.w[0];
         uint32_t *ct = ctile + (ctseq & (kTileBufs - 1)) * kTileWords;
-        const int dx = (int)(cmd.w[2] & 0xffu), dy = (int)((cmd.w[2] >> 8) & 0xffu);
-        const int two = (int)((cmd.w[2] >> 16) & 0xffu), tho = (int)(cmd.w[2] >> 24);
+        // Record fields are the same for every thread, but the compiler cannot know that of a shared-memory load:
+        // broadcasting them from lane 0 marks them warp-uniform, so the passes' row / column / plane offsets are
+        // computed once per warp on the uniform datapath (LDS [R + UR + imm]) instead of per lane with IMADs that
+        // compete with dp4a for the FMA-heavy pipe.
+        const uint32_t w1 = uni(cmd.w[1]), w2 = uni(cmd.w[2]);
+        const int dx = (int)(w2 & 0xffu), dy = (int)((w2 >> 8) & 0xffu);
+        const int two = (int)((w2 >> 16) & 0xffu), tho = (int)(w2 >> 24);
         if (kind == kCmdResample) {
-            const int nwx = (int)(cmd.w[1] & 0xffu), nwy = (int)((cmd.w[1] >> 8) & 0xffu);
-            const int nch = (int)((cmd.w[1] >> 16) & 0xffu), NRQ = (int)(cmd.w[1] >> 24);
-            const int ox0 = (int)cmd.w[3], oy0 = (int)cmd.w[4];
-            const int cw0 = (int)(cmd.w[5] & 0xffffu), rw0 = (int)(cmd.w[5] >> 16);
-            const int n_out_x = (int)cmd.w[6], n_out_y = (int)cmd.w[7];
-            const uint32_t *plx = tables + cmd.w[9], *ply = tables + cmd.w[10];
-            const int pbw = (int)(cmd.w[11] & 0xffffu);
+            const int nwx = (int)(w1 & 0xffu), nwy = (int)((w1 >> 8) & 0xffu);
+            const int nch = (int)((w1 >> 16) & 0xffu), NRQ = (int)(w1 >> 24);
+            const uint32_t w5 = uni(cmd.w[5]);
+            const int ox0 = (int)uni(cmd.w[3]), oy0 = (int)uni(cmd.w[4]);
+            const int cw0 = (int)(w5 & 0xffffu), rw0 = (int)(w5 >> 16);
+            const int n_out_x = (int)uni(cmd.w[6]), n_out_y = (int)uni(cmd.w[7]);
+            const uint32_t *plx = tables + uni(cmd.w[9]), *ply = tables + uni(cmd.w[10]);
+            const int pbw = (int)(uni(cmd.w[11]) & 0xffffu);
             const double scale_x = __longlong_as_double((long long)((uint64_t)cmd.w[12] | ((uint64_t)cmd.w[13] << 32)));
             const double scale_y = __longlong_as_double((long long)((uint64_t)cmd.w[14] | ((uint64_t)cmd.w[15] << 32)));
             // a skipped pass is the 1-tap identity: scale 1, support 1 -> first tap = the sample itself

@@ -166,6 +166,9 @@ WORKLOADS = {
     # BASELINE.json configs[2]: synthetic 4K canvases, 20 RGBA objects each, batch 1024
     "c3_4k_20obj": dict(canvas=(3840, 2160), n_objects=20, pool_n=64, pool_lo=256, pool_hi=1536,
                         scale_lo=0.5, scale_hi=1.0, layout="flex", batch=1024),
+    # kernel-tuning variant of C3: scales 0.75..1.0 only (smaller source patches, 9-tap windows)
+    "c3_s75": dict(canvas=(3840, 2160), n_objects=20, pool_n=64, pool_lo=256, pool_hi=1536,
+                   scale_lo=0.75, scale_hi=1.0, layout="flex", batch=1024),
     # configs[3]: aspect sweep at the same 8.29 MP budget
     "c4_aspect_sweep": dict(canvases=[(2160, 3840), (2880, 2880), (3840, 2160), (4399, 1885)], n_objects=20,
                             pool_n=64, pool_lo=256, pool_hi=1536, scale_lo=0.5, scale_hi=1.0, layout="flex",

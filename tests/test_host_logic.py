@@ -104,3 +104,13 @@ def test_synthetic_workload_is_deterministic_and_in_spec():
     assert len(u) == 64
     st = synth.alpha_stats(synth.make_pool(4, 64, 128))
     assert 0.2 < st["transparent"] < 0.4 and 0.5 < st["opaque"] < 0.75
+
+
+def test_unpremultiply_magic_division_is_exact():
+    """kernels.cuh unpremultiply_px replaces 255 * c / a (Convert.c rgba2rgbA) by a multiply-high with
+    m = ceil(2^24 / a): (255 * c << 8) * m >> 32 must be the truncated quotient for every (c, a)."""
+    for a in range(1, 256):
+        m = ((1 << 24) + a - 1) // a
+        assert m <= 1 << 24
+        for c in range(256):
+            assert ((c * 65280) * m) >> 32 == (255 * c) // a, (c, a)
