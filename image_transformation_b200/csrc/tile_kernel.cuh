@@ -1,18 +1,19 @@
-// Fused resample + alpha-over tile kernel (sm_100a), the hot kernel of the path.
+// Fused resample + alpha-over tile kernel (sm_100a), the hot kernel of the path, and the binning pass
+// that feeds it.
 //
-// One CTA owns one 64x32 tile of one output canvas.  The tile lives in shared memory while the
-// CTA walks the canvas' placements in z-order (compositor.py:12-21).  For every placement that
-// touches the tile:
-//   1. stage   the needed source patch: 128-bit loads of RGBA pixels, premultiply (Convert.c
-//              rgbA2rgba), byte-transpose into four channel planes (4 consecutive pixels of one
-//              channel per 32-bit word)
-//   2. H pass  lane <-> output column; Pillow's 22-bit fixed-point taps are held as three byte
-//              planes (k = b0 + 256*b1 + 65536*b2, b2 signed) so four taps cost three dp4a and no
-//              byte unpacking; result rounded + clipped to uint8 (ImagingResampleHorizontal_8bpc)
-//              and written transposed (4 consecutive ROWS of one channel per word)
-//   3. V pass  lane <-> output row, same dp4a scheme (ImagingResampleVertical_8bpc), then
-//              un-premultiply (rgba2rgbA) and alpha-over (AlphaComposite.c) onto the resident tile
-// The tile is written to HBM once.  Arithmetic is integer-exact: dp4a partial sums wrap modulo
+// The kernel is persistent: CTA c walks the 64x32 canvas tiles of command stream c (written by the binning
+// kernels below).  A tile lives in shared memory while the placements that touch it are composited in z-order
+// (compositor.py:12-21); the binning pass has already dropped the placements that cannot show (transparent
+// source patch, or hidden by a later opaque placement that covers the tile).  Per resampled placement:
+//   1. patch   one TMA box (words x 4 channel planes x rows) of the PREPARED cutout: premultiplied
+//              (Convert.c rgbA2rgba), channel-planar, 4 consecutive pixels of one channel per 32-bit word
+//   2. H pass  lane <-> output column; Pillow's 22-bit fixed-point taps are held as three byte planes
+//              (k = b0 + 256*b1 + 65536*b2, b2 signed) so four taps cost three dp4a and no byte unpacking;
+//              result rounded + clipped to uint8 (ImagingResampleHorizontal_8bpc) and written transposed
+//              (4 consecutive ROWS of one channel per word)
+//   3. V pass  lane <-> output row, same dp4a scheme (ImagingResampleVertical_8bpc), then un-premultiply
+//              (rgba2rgbA) and alpha-over (AlphaComposite.c) onto the resident tile
+// The tile is written to HBM once (TMA store).  Arithmetic is integer-exact: dp4a partial sums wrap modulo
 // 2^32 and the true accumulator fits in int32, exactly as Pillow's int accumulator.
 #pragma once
 #include "kernels.cuh"

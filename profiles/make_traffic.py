@@ -1,0 +1,44 @@
+#!/usr/bin/env python3
+"""profiles/ncu_traffic.json from an ncu launch list of `bench.py --batch N --steps 2 --warmup 3 --no-e2e
+--no-cpu-baseline` (metrics gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum).
+
+usage: make_traffic.py <launches.csv> <bench json of the same command> <out json>
+
+The LAST step of the run is used: the launches from the last prepare_cutouts_kernel to the last
+composite_stream_kernel (prepare + 3 binning kernels + tile kernel = one b200comp_plan_run)."""
+import csv
+import json
+import sys
+
+
+def main():
+    src, bench_json, out = sys.argv[1:4]
+    rows = [r for r in csv.reader(open(src)) if len(r) > 14 and r[0].isdigit()]
+    launches = {}
+    for r in rows:
+        d = launches.setdefault(int(r[0]), {"name": r[4].split("(")[0]})
+        d[r[12]] = float(r[14].replace(",", ""))
+    ids = sorted(launches)
+    last_tile = max(i for i in ids if launches[i]["name"].startswith("composite_stream_kernel"))
+    first = max(i for i in ids if i < last_tile and launches[i]["name"].startswith("prepare_cutouts_kernel"))
+    step = [launches[i] for i in ids if first <= i <= last_tile]
+    dram = sum(l["dram__bytes_read.sum"] + l["dram__bytes_write.sum"] for l in step)
+    t = sum(l["gpu__time_duration.sum"] for l in step)
+    tile = launches[last_tile]
+    bench = json.loads(open(bench_json).read().strip().splitlines()[-1])
+    res = {
+        "source": f"profiles/{src.split('/')[-1]} (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
+                  f"--clock-control none; last step of bench.py --batch {bench['config']['canvases_per_gpu_per_step']}: "
+                  + " + ".join(l["name"] for l in step) + ")",
+        "dram_bytes_per_launch": dram,
+        "algorithmic_bytes_per_launch": bench["roofline"]["algorithmic_bytes_per_launch"],
+        "tile_kernel_dram_bytes": tile["dram__bytes_read.sum"] + tile["dram__bytes_write.sum"],
+        "tile_kernel_share_of_step_time": tile["gpu__time_duration.sum"] / t,
+        "launch_ns": {l["name"]: l["gpu__time_duration.sum"] for l in step},
+    }
+    json.dump(res, open(out, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()
