@@ -18,10 +18,6 @@
 #pragma once
 #include "kernels.cuh"
 
-#ifndef B200COMP_HSPLIT
-#define B200COMP_HSPLIT 0  // horizontal pass work unit: 1 = (row quad, channel), 0 = row quad (measured faster)
-#endif
-
 namespace b200comp {
 
 __device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
@@ -225,6 +221,7 @@ __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int P
     const int wfirst = cg ? warp - kHalf : warp;                                     // this warp's index in its group
     const int rstep = two_groups ? (cg ? kComputeWarps - kHalf : kHalf) : kComputeWarps;  // warps in the group
     const int jj = cg * 32 + lane;
+    const unsigned act = __ballot_sync(0xffffffffu, jj < two);  // lanes of this warp that own an output column
     if (jj >= two) return;
     const int j = ox0 + jj;
     const int wbase = (first_tap(j, scale, support) >> 2) - cw0;
@@ -235,36 +232,39 @@ __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int P
         k1[i] = __ldg(plx + (int64_t)(1 * NW + i) * n_out + j);
         k2[i] = __ldg(plx + (int64_t)(2 * NW + i) * n_out + j);
     }
-#if B200COMP_HSPLIT
-    // unit = (row quad, channel): 4 rows x 32 columns of one channel plane.  NRQ * nch units spread evenly
-    // over the warps of this column group (a unit per row quad would leave warps idle at the barrier).
-    const int n_units = NRQ * nch;
-    const int plane = PBW >> 2;
-    for (int u = wfirst; u < n_units; u += rstep) {
-        const int rq = nch == 4 ? (u >> 2) : (int)(((uint32_t)u * 43691u) >> 17);  // u / 3 for u < 98304
-        const int c = u - rq * nch;
-        const uint32_t *row = P + (rq * 4) * PBW + c * plane + wbase;
-        uint32_t o = 0u;
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            uint32_t wd[NW];
-#pragma unroll
-            for (int i = 0; i < NW; ++i) wd[i] = row[rr * PBW + i];
-            const uint32_t v = clip8i(tap_sum<NW>(wd, k0, k1, k2));
-            if (rr == 0) o = v;
-            else if (rr == 1) o = __byte_perm(o, v, 0x3240);
-            else if (rr == 2) o = __byte_perm(o, v, 0x3410);
-            else o = __byte_perm(o, v, 0x4210);
-        }
-        I[c * iplane_stride + jj * IPW + rq] = o;
-    }
-#else
-    // unit = row quad: 4 rows x 32 columns x all channel planes
+    // unit = row quad: 4 source rows x 32 output columns x all channel planes.  With an alpha plane (nch == 4) that
+    // plane goes first: if every alpha the warp read for this unit is 0, the premultiplied colours are 0 as well
+    // (rgbA2rgba) and so are their sums -- the three colour planes are stored as zeros without being computed
+    // (about a quarter of the units of tiles that straddle a cutout's edge).
     const int plane = PBW >> 2;
     for (int rq = wfirst; rq < NRQ; rq += rstep) {
         const uint32_t *row = P + (rq * 4) * PBW + wbase;
         uint32_t *d = I + jj * IPW + rq;
-        for (int c = 0; c < nch; ++c) {
+        if (nch == 4) {
+            uint32_t o = 0u, nz = 0u;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                uint32_t wd[NW];
+#pragma unroll
+                for (int i = 0; i < NW; ++i) {
+                    wd[i] = row[3 * plane + rr * PBW + i];
+                    nz |= wd[i];
+                }
+                const uint32_t v = clip8i(tap_sum<NW>(wd, k0, k1, k2));
+                if (rr == 0) o = v;
+                else if (rr == 1) o = __byte_perm(o, v, 0x3240);
+                else if (rr == 2) o = __byte_perm(o, v, 0x3410);
+                else o = __byte_perm(o, v, 0x4210);
+            }
+            d[3 * iplane_stride] = o;
+            if (!__any_sync(act, nz != 0u)) {
+                d[0] = 0u;
+                d[iplane_stride] = 0u;
+                d[2 * iplane_stride] = 0u;
+                continue;
+            }
+        }
+        for (int c = 0; c < 3; ++c) {
             uint32_t o = 0u;
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
@@ -282,19 +282,52 @@ __device__ __forceinline__ void tile_hpass(const uint32_t *__restrict__ P, int P
             d += iplane_stride;
         }
     }
-#endif
 }
 
 // ---- V pass + un-premultiply + over -------------------------------------------------------------
+// One output column of the tile (lane <-> output row): NCH channel sums, then the pixel goes onto the
+// resident tile.  NCH == 3: every source alpha of the column is 255 -- the alpha plane is not computed and
+// the pixel replaces the canvas pixel.
 template <int NW, int NCH>
-__device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, int iplane_stride, int IPW,
+__device__ __forceinline__ void vpass_column(const uint32_t *__restrict__ col, int iplane_stride, uint32_t *__restrict__ cpx,
+                                             const uint32_t (&k0)[NW], const uint32_t (&k1)[NW], const uint32_t (&k2)[NW]) {
+    int32_t acc[4];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        uint32_t wd[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) wd[i] = col[c * iplane_stride + i];
+        acc[c] = tap_sum<NW>(wd, k0, k1, k2);
+    }
+    // bytes packed with PRMT (the shift-and-or form compiles to IMAD.SHL on the FMA-heavy pipe)
+    const uint32_t rg = __byte_perm(clip8i(acc[0]), clip8i(acc[1]), 0x1140);
+    if (NCH == 3) {
+        *cpx = __byte_perm(rg, clip8i(acc[2]), 0x5410) | 0xff000000u;
+    } else {
+        // Alpha tests on the raw accumulator (clip8(acc) == 0 / == 255).  Do NOT test the clamped value:
+        // CUDA 12.9 ptxas folds `clamp(x) == 255` into VIMNMX.RELU's predicate output with the wrong
+        // sense on sm_100a (partially transparent pixels took the opaque branch).
+        if (acc[3] >= (1 << kPrecisionBits)) {  // else transparent: canvas pixel unchanged
+            const bool opaque = acc[3] >= (255 << kPrecisionBits);
+            const uint32_t s = __byte_perm(rg, __byte_perm(clip8i(acc[2]), clip8i(acc[3]), 0x1140), 0x5410);
+            *cpx = opaque ? s : over_px(*cpx, unpremultiply_px(s));
+        }
+    }
+}
+
+// NCH == 3: the whole source patch is opaque (alpha summary).  NCH == 4: each column is classified first from
+// the alpha plane of the intermediate (one word per lane, two warp reductions): all zero -> nothing to draw,
+// the column is skipped; all 255 -> the 3-channel path; on tiles that straddle a cutout's edge about a fifth of
+// the columns fall in either class.
+template <int NW, int NCH>
+__device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, int iplane_stride, int IPW, int NRQ,
                                                 uint32_t *__restrict__ ctile, int rw0, int oy0, int tho, int two,
                                                 int tile_dx, int tile_dy, double scale, double support,
                                                 const uint32_t *__restrict__ ply, int n_out) {
     const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     if (warp >= kComputeWarps) return;
     // Lanes past the tile's last row redo the last row (same loads, same value stored to the same address): the
-    // warp stays converged, which lets the compiler keep the column / plane offsets in uniform registers.
+    // warp stays converged (the column classification below is a warp-wide reduction).
     const int lrow = min(lane, tho - 1);
     const int y = oy0 + lrow;
     const int wbase = (first_tap(y, scale, support) >> 2) - rw0;
@@ -309,29 +342,23 @@ __device__ __forceinline__ void tile_vpass_over(const uint32_t *__restrict__ I, 
     uint32_t *crow = ctile + (r << 5);
     for (int x = warp; x < two; x += kComputeWarps) {
         const uint32_t *col = I + x * IPW + wbase;
-        int32_t acc[4];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            uint32_t wd[NW];
-#pragma unroll
-            for (int i = 0; i < NW; ++i) wd[i] = col[c * iplane_stride + i];
-            acc[c] = tap_sum<NW>(wd, k0, k1, k2);
-        }
         const int X = tile_dx + x;  // warp-uniform
         uint32_t *cpx = crow + (((X & 32) << 5) | (X & 3)) + ((((X >> 2) ^ r) & 7) << 2);
-        // bytes packed with PRMT (the shift-and-or form compiles to IMAD.SHL on the FMA-heavy pipe)
-        const uint32_t rg = __byte_perm(clip8i(acc[0]), clip8i(acc[1]), 0x1140);
-        if (NCH == 3) {  // every source alpha is 255: the pixel replaces the canvas pixel
-            *cpx = __byte_perm(rg, clip8i(acc[2]), 0x5410) | 0xff000000u;
+        if (NCH == 3) {
+            vpass_column<NW, 3>(col, iplane_stride, cpx, k0, k1, k2);
         } else {
-            // Alpha tests on the raw accumulator (clip8(acc) == 0 / == 255).  Do NOT test the clamped value:
-            // CUDA 12.9 ptxas folds `clamp(x) == 255` into VIMNMX.RELU's predicate output with the wrong
-            // sense on sm_100a (partially transparent pixels took the opaque branch).
-            if (acc[3] >= (1 << kPrecisionBits)) {  // else transparent: canvas pixel unchanged
-                const bool opaque = acc[3] >= (255 << kPrecisionBits);
-                const uint32_t s = __byte_perm(rg, __byte_perm(clip8i(acc[2]), clip8i(acc[3]), 0x1140), 0x5410);
-                *cpx = opaque ? s : over_px(*cpx, unpremultiply_px(s));
+            const uint32_t *acol = I + 3 * iplane_stride + x * IPW;
+            uint32_t any = 0u, all = 0xffffffffu;
+            for (int q = lane; q < NRQ; q += 32) {
+                const uint32_t a = acol[q];
+                any |= a;
+                all &= a;
             }
+            any = __reduce_or_sync(0xffffffffu, any);
+            all = __reduce_and_sync(0xffffffffu, all);
+            if (any == 0u) continue;  // every source alpha under this column is 0
+            if (all == 0xffffffffu) vpass_column<NW, 3>(col, iplane_stride, cpx, k0, k1, k2);
+            else vpass_column<NW, 4>(col, iplane_stride, cpx, k0, k1, k2);
         }
     }
 }
@@ -901,7 +928,7 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
                 wait_bg();
             }
 #define B200_VPASS(NWY, NCH_) \
-    tile_vpass_over<NWY, NCH_>(I, iplane_stride, IPW, ct, rw0, oy0, tho, two, dx, dy, scale_y, support_y, ply, n_out_y)
+    tile_vpass_over<NWY, NCH_>(I, iplane_stride, IPW, NRQ, ct, rw0, oy0, tho, two, dx, dy, scale_y, support_y, ply, n_out_y)
             if (nch == 4) {
                 if (nwy == 3) B200_VPASS(3, 4);
                 else if (nwy == 4) B200_VPASS(4, 4);
