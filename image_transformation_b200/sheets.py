@@ -10,6 +10,7 @@ Reference interfaces mirrored (file:line in /root/reference):
   * ``_compose_candidates_grid``      macro_placement_test.py:1332-1345
         up to four drafts resized to the first one's size, 2 x 2 grid on white
   * ``_prepare_image_b64_for_api``    api_client.py:97-112   (the RGB LANCZOS downscale; JPEG/base64 stay host)
+  * the agentic compositor node's raster loop  agentic/nodes/compositor.py:36-43  (native-size overlays only)
 
 ``Image.thumbnail`` on a plain RGBA image is a LANCZOS ``resize`` to the aspect-preserving size
 (PIL Image.py: ``preserve_aspect_ratio``; ``draft`` only applies to JPEG files and the RGBA branch of
@@ -200,3 +201,23 @@ def compose_candidates_grid(image_paths: List[Path], out_path: Path) -> None:
     grid = candidates_grid(imgs)
     if grid is not None:
         grid.save(out_path)
+
+
+# ---------------------------------------------------------------------------- agentic compositor node
+def composite_native_size(background_img: Image.Image, object_images, placements) -> Image.Image:
+    """The raster loop of the agentic compositor node (agentic/nodes/compositor.py:36-43): every overlay must
+    already have its placement's size -- ``ValueError("Placement size mismatch; scaling objects is not
+    permitted")`` otherwise -- and is alpha-composited at (x, y) in list order.  ``placements`` are
+    ``{object_id, box}`` records (the node builds exactly these, :22-34) or objects with
+    ``object_id / x / y / width / height`` attributes.  One fused launch instead of one pass per overlay."""
+    recs = []
+    for p in placements:
+        if isinstance(p, dict):
+            oid, (x1, y1, x2, y2) = p["object_id"], p["box"]
+            x, y, w, h = x1, y1, x2 - x1, y2 - y1
+        else:
+            oid, x, y, w, h = p.object_id, p.x, p.y, p.width, p.height
+        if object_images[oid].size != (w, h):
+            raise ValueError("Placement size mismatch; scaling objects is not permitted")
+        recs.append({"object_id": oid, "box": [x, y, x + w, y + h]})
+    return _compositor.composite(background_img, object_images, recs)

@@ -7,6 +7,7 @@ UNMODIFIED reference in the build container:
   contact/<bundle>      macro_placement_test._build_labeled_contact_sheet (:162-242) on the bundle as shipped
   grid                  macro_placement_test._compose_candidates_grid (:1332-1345) on four drafts of different sizes
   api/<name>            the RGB downscale of api_client._prepare_image_b64_for_api (:97-108), before its JPEG encode
+  flow/<case>           layout_constraints.pack_flow (:273-327) boxes of scaled objects -> fill_solid -> composite
 """
 from __future__ import annotations
 
@@ -78,6 +79,35 @@ def main():
             out[f"api/{name}/{max_side}"] = np.array(small, dtype=np.uint8)
             man["api"][f"{name}/{max_side}"] = {"sha256": sha(np.array(small)), "size": list(small.size)}
         out[f"api/{name}/in"] = np.array(im, dtype=np.uint8)
+    # pack_flow (layout_constraints.py:273-327): the in-tree producer of boxes whose size differs from the cutout's
+    import compositor as ref_comp
+    import background_resizing as ref_bg
+    import layout_constraints as ref_lc
+
+    man["flow"] = {}
+    for bundle, ratio, scales, params in (
+            ("squarespace", "9:16", {1: 1.3, 2: 0.8, 3: 0.66, 4: 2.0}, {"align": "center", "orientation": "auto"}),
+            ("squarespace", "16:9", {1: 0.5, 2: 0.45, 3: 0.7, 4: 1.0}, {"align": "left", "orientation": "horizontal",
+                                                                       "global_margin_px": 7, "global_spacing_px": 11}),
+            ("audio_book", "1:1", {1: 0.9, 2: 0.75, 3: 1.5}, {"align": "center", "orientation": "vertical",
+                                                             "global_spacing_px": 3})):
+        rj = f"{REF}/output/{bundle}/results.json"
+        objs = ref_comp.load_object_images(rj)
+        items = json.load(open(rj))
+        meta = {int(it["object_id"]): ref_lc.ObjectMeta(int(it["object_id"]), it.get("label", ""), it["filename"],
+                                                        objs[int(it["object_id"])].width, objs[int(it["object_id"])].height)
+                for it in items}
+        scaled = [ref_lc.ObjectMeta(m.object_id, m.label, m.file, max(1, int(m.width * scales[m.object_id])),
+                                    max(1, int(m.height * scales[m.object_id]))) for m in meta.values()]
+        canvas_size = ref_lc.compute_canvas_size((970, 250), ratio)
+        pls, _ = ref_lc.pack_flow(scaled, canvas_size, params, meta)
+        layout = ref_lc.layout_final_json(pls, canvas_size, 0.0, params["align"])
+        bg = ref_bg.fill_solid(f"{REF}/output/{bundle}/background.png", canvas_size)
+        res = ref_comp.composite(bg, objs, layout["placements"])
+        key = f"{bundle}_{ratio.replace(':', 'x')}"
+        out[f"flow/{key}"] = np.array(res, dtype=np.uint8)
+        man["flow"][key] = {"bundle": bundle, "canvas": list(canvas_size), "placements": layout["placements"],
+                            "sha256": sha(np.array(res))}
     np.savez_compressed(os.path.join(HERE, "sheets.npz"), **out)
     json.dump(man, open(os.path.join(HERE, "sheets_manifest.json"), "w"), indent=1)
     print({k: v.shape for k, v in out.items()})

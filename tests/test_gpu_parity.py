@@ -437,6 +437,31 @@ def test_raw_buffers_unaligned_pitches_and_bases():
         assert_same(o, ref, f"raw canvas {i}")
 
 
+def test_raw_buffers_unaligned_with_occluders():
+    """Occlusion culling on canvases TMA cannot address: fully opaque overlays enlarged over several tiles of a
+    canvas with a 4-byte-aligned pitch (generic background loads / stores), translucent background, more tiles
+    than persistent CTAs so every CTA mixes occluded and ordinary tiles."""
+    from image_transformation_b200 import _native
+
+    rng = np.random.default_rng(15)
+    ov = {1: rng.integers(0, 256, (120, 160, 4), dtype=np.uint8), 2: rng.integers(0, 256, (90, 70, 4), dtype=np.uint8),
+          3: rng.integers(0, 256, (64, 64, 4), dtype=np.uint8)}
+    ov[1][..., 3] = 255
+    ov[3][..., 3] = 255
+    overlays = {1: (ov[1], 160 * 4), 2: (ov[2], 70 * 4 + 4), 3: (ov[3], 64 * 4 + 12)}
+    W, H = 1531, 1203  # 24 x 38 tiles
+    bg = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    pls = [[(2, 100, 100, 500, 400), (1, 50, 60, 900, 700), (2, 300, 200, 260, 300), (3, 700, 500, 700, 650),
+            (1, 900, 20, 600, 420), (2, -40, 900, 700, 400), (3, 1000, 800, 64, 64), (1, 400, 850, 160, 120)],
+           [(1, 0, 0, 1531, 1203), (3, 200, 200, 300, 300), (2, 250, 250, 400, 400)]]
+    canvases = [(bg, (0, 0, 0, 0), W, H, W * 4 + 4), (None, (9, 8, 7, 100), W, H, W * 4)]
+    outs = _raw_batch(_native, canvases, overlays, pls)
+    for i, o in enumerate(outs):
+        base = bg if i == 0 else np.broadcast_to(np.array([9, 8, 7, 100], np.uint8), (H, W, 4)).copy()
+        ref = oracle.composite(base, ov, [{"object_id": oid, "box": [x, y, x + w, y + h]} for oid, x, y, w, h in pls[i]])
+        assert_same(o, ref, f"raw canvas {i}")
+
+
 def test_host_buffer_batch_sub_ranges():
     """b200comp_composite_batch_host with several chunks per plan (plan_run_canvases on sub-ranges)."""
     from image_transformation_b200 import _native, synth

@@ -87,7 +87,48 @@ def test_oracle_rgb_downscale_matches_reference(key):
     assert np.array_equal(got[..., :3], exp) and (got[..., 3] == 255).all()
 
 
+@pytest.mark.parametrize("key", sorted(MAN["flow"]))
+def test_oracle_pack_flow_composite_matches_reference(key):
+    c = MAN["flow"][key]
+    _, objs = G.bundle(c["bundle"])
+    W, H = c["canvas"]
+    bg = np.zeros((H, W, 4), np.uint8)
+    bg[...] = tuple(G.manifest()["bundles"][c["bundle"]]["median_color"]) + (255,)
+    exp = Z[f"flow/{key}"]
+    assert G.sha(exp) == c["sha256"]
+    assert np.array_equal(oracle.composite(bg, objs, c["placements"]), exp)
+
+
 # ------------------------------------------------------------------------------ GPU: the mirrored functions
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", sorted(MAN["flow"]))
+def test_pack_flow_layouts_through_dropin(key):
+    """Boxes from the reference's pack_flow (scaled objects: the in-tree producer of non-identity boxes)."""
+    from image_transformation_b200 import compositor
+
+    c = MAN["flow"][key]
+    _, objs = G.bundle(c["bundle"])
+    W, H = c["canvas"]
+    bg = Image.new("RGBA", (W, H), tuple(G.manifest()["bundles"][c["bundle"]]["median_color"]) + (255,))
+    out = compositor.composite(bg, {k: Image.fromarray(v, "RGBA") for k, v in objs.items()}, c["placements"])
+    assert np.array_equal(np.asarray(out), Z[f"flow/{key}"])
+
+
+@pytest.mark.gpu
+def test_agentic_native_size_loop():
+    _, objs = G.bundle("audio_book")
+    imgs = {k: Image.fromarray(v, "RGBA") for k, v in objs.items()}
+    bg = Image.new("RGBA", (657, 369), (38, 73, 115, 255))
+    pl = [{"object_id": k, "box": [20 + 90 * i, 10 + 30 * i, 20 + 90 * i + im.width, 10 + 30 * i + im.height]}
+          for i, (k, im) in enumerate(sorted(imgs.items()))]
+    exp = bg.copy()
+    for p in pl:
+        exp.alpha_composite(imgs[p["object_id"]], dest=(p["box"][0], p["box"][1]))
+    assert np.array_equal(np.asarray(sheets.composite_native_size(bg, imgs, pl)), np.asarray(exp))
+    pl[1]["box"][2] += 1
+    with pytest.raises(ValueError, match="Placement size mismatch"):
+        sheets.composite_native_size(bg, imgs, pl)
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("bundle", ["squarespace", "audio_book"])
 def test_build_labeled_contact_sheet(bundle, tmp_path):
