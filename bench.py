@@ -378,9 +378,14 @@ def run_b200(args):
             used_pool.add(oid)
             pls[j] = _native.Placement(tp.data_ptr(), tp.shape[1] * 4, tp.shape[1], tp.shape[0], x, y, w, h, fl, 0)
 
+        n_threads = max(1, host_cores() // max(1, world))  # the ranks of one box share its host cores
+
         def e2e_step():
-            rc = L.b200comp_composite_batch_host(cvs, nb, pls, len(recs), host_cores(), 4, 3)
+            t_call = time.perf_counter()
+            rc = L.b200comp_composite_batch_host(cvs, nb, pls, len(recs), n_threads, 4, 3)
             _native.check(rc, "composite_batch_host")
+            if os.environ.get("B200COMP_TRACE"):
+                print(f"[bench] composite_batch_host call took {(time.perf_counter() - t_call) * 1e3:.2f} ms", file=sys.stderr)
 
         e2e_step()  # warm-up (also pages the pinned buffers in)
         barrier()

@@ -298,6 +298,7 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
     stamp("all done", 0);
     if (ev_pool) cudaEventDestroy(ev_pool);
     for (int b = 0; b < kBufs; ++b) if (ev_done[b]) cudaEventDestroy(ev_done[b]);
+    stamp("events destroyed", 0);
     if (rc) return b200comp_set_error_(rc, err.c_str());
     return 0;
 }
