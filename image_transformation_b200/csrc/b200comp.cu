@@ -113,92 +113,103 @@ __global__ void gradient_lut_kernel(uint32_t *__restrict__ lut, int n, int c1r, 
     lut[i] = r | (g << 8) | (bl << 16) | 0xff000000u;
 }
 
-__global__ void gradient_fill_kernel(uint8_t *__restrict__ dst, int W, int H, int64_t pitch,
-                                     const uint32_t *__restrict__ lut, int horizontal) {
-    const int y = blockIdx.y;
-    uint32_t *row = reinterpret_cast<uint32_t *>(dst + (int64_t)y * pitch);
-    const uint32_t rowv = horizontal ? 0u : __ldg(lut + y);
-    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x)
-        row[x] = horizontal ? __ldg(lut + x) : rowv;
-    (void)H;
+// work item = (row, chunk of 1024 pixels), one warp per item (grid-stride); 128-bit stores when the canvas rows
+// are 16-byte aligned (the LUT always is: it comes from the allocator)
+__global__ void __launch_bounds__(256)
+gradient_fill_kernel(uint8_t *__restrict__ dst, int W, int H, int64_t pitch, const uint32_t *__restrict__ lut,
+                     int horizontal, int vec_ok) {
+    const int lane = threadIdx.x & 31;
+    const int n_chunk = (W + 1023) >> 10;
+    const int64_t n_items = (int64_t)H * n_chunk;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n_items; it += n_warps) {
+        const int y = (int)(it / n_chunk), xb = (int)(it - (int64_t)y * n_chunk) << 10;
+        const int xe = min(W, xb + 1024);
+        uint8_t *row = dst + (int64_t)y * pitch;
+        const uint32_t rowv = horizontal ? 0u : __ldg(lut + y);
+        int x = xb;
+        if (vec_ok) {
+            for (x = xb + lane * 4; x + 3 < xe; x += 128) {
+                const uint4 v = horizontal ? __ldg(reinterpret_cast<const uint4 *>(lut + x)) : make_uint4(rowv, rowv, rowv, rowv);
+                *reinterpret_cast<uint4 *>(row + (int64_t)x * 4) = v;
+            }
+            x = xb + ((xe - xb) & ~3);  // pixels left over after the last whole group of four
+        }
+        for (x += lane; x < xe; x += 32)
+            *reinterpret_cast<uint32_t *>(row + (int64_t)x * 4) = horizontal ? __ldg(lut + x) : rowv;
+    }
 }
 
 // ---- masked RGB histogram + median -----------------------------------------------------
 // hist layout: [2][3][256] uint64: set 0 = pixels with alpha > 0, set 1 = all pixels; counts[2].
-__global__ void hist_rgb_kernel(const uint8_t *__restrict__ img, int64_t pitch, int x0, int y0, int x1, int y1,
-                                unsigned long long *__restrict__ hist, unsigned long long *__restrict__ counts) {
-    __shared__ unsigned int sh[2 * 3 * 256];
-    __shared__ unsigned int scount[2];
-    for (int i = threadIdx.x; i < 2 * 3 * 256; i += blockDim.x) sh[i] = 0;
-    if (threadIdx.x < 2) scount[threadIdx.x] = 0;
+// One launch per set: `all_pixels == 0` fills set 0; `all_pixels == 1` fills set 1 and returns at once unless
+// set 0 came out empty (background_resizing.py:15-19 falls back to every pixel only then).
+//
+// Warp = (row, 1024-pixel chunk) (grid-stride), lane = pixel: coalesced 4-byte loads.  Runs of equal neighbouring pixels inside a
+// warp load (flat backgrounds are the common case) are merged with one shuffle + one ballot, so the first lane
+// of a run adds its length to the three bins instead of 32 lanes serialising on them; every warp has a private
+// histogram in shared memory.
+constexpr int kHistWarps = 8;
+__global__ void __launch_bounds__(kHistWarps * 32)
+hist_rgb_kernel(const uint8_t *__restrict__ img, int64_t pitch, int x0, int y0, int x1, int y1,
+                unsigned long long *__restrict__ hist, unsigned long long *__restrict__ counts, int all_pixels) {
+    if (all_pixels && counts[0] != 0ull) return;
+    __shared__ unsigned int sh[kHistWarps][3 * 256];
+    __shared__ unsigned int scount;
+    for (int i = threadIdx.x; i < kHistWarps * 3 * 256; i += blockDim.x) (&sh[0][0])[i] = 0u;
+    if (threadIdx.x == 0) scount = 0u;
     __syncthreads();
-    const int rw = x1 - x0;
-    const int64_t total = (int64_t)rw * (y1 - y0);
-    // each thread walks runs of 8 consecutive pixels and merges equal neighbours before the
-    // shared-memory atomics (flat backgrounds would otherwise serialise on one bin)
-    constexpr int RUN = 8;
-    const int64_t n_runs = (total + RUN - 1) / RUN;
-    unsigned int cnt_m = 0, cnt_a = 0;
-    for (int64_t run = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; run < n_runs;
-         run += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t prev = 0;
-        unsigned int len = 0;
-        bool have = false;
-        for (int i = 0; i < RUN; ++i) {
-            const int64_t idx = run * RUN + i;
-            if (idx >= total) break;
-            const int yy = (int)(idx / rw), xx = (int)(idx - (int64_t)yy * rw);
-            const uint32_t p = ld_px(img, (int64_t)(y0 + yy) * pitch + (int64_t)(x0 + xx) * 4);
-            // key merges pixels with equal rgb and equal "masked" state
-            const uint32_t key = (p & 0x00ffffffu) | ((p >> 24) ? 0x01000000u : 0u);
-            if (have && key == prev) {
-                ++len;
-            } else {
-                if (have) {
-                    const int set0 = (prev >> 24) & 1;
-                    atomicAdd(&sh[768 + (prev & 0xff)], len);
-                    atomicAdd(&sh[768 + 256 + ((prev >> 8) & 0xff)], len);
-                    atomicAdd(&sh[768 + 512 + ((prev >> 16) & 0xff)], len);
-                    cnt_a += len;
-                    if (set0) {
-                        atomicAdd(&sh[prev & 0xff], len);
-                        atomicAdd(&sh[256 + ((prev >> 8) & 0xff)], len);
-                        atomicAdd(&sh[512 + ((prev >> 16) & 0xff)], len);
-                        cnt_m += len;
-                    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int *h = sh[warp];
+    const int rw = x1 - x0, nrows = y1 - y0;
+    unsigned int cnt = 0;  // pixels counted by this warp (kept by every lane: the ballots are warp-wide)
+    // work item = (row, chunk of 1024 pixels), one warp per item; 8 coalesced loads per lane are in flight before
+    // the first one is consumed (the kernel is latency bound otherwise: ~30 KB per SM must be in flight)
+    constexpr int kChunk = 1024, kUnroll = 8;
+    const int n_chunk = (rw + kChunk - 1) / kChunk;
+    const int64_t n_items = (int64_t)nrows * n_chunk;
+    for (int64_t it = (int64_t)blockIdx.x * kHistWarps + warp; it < n_items; it += (int64_t)gridDim.x * kHistWarps) {
+        const int row = (int)(it / n_chunk), c0 = (int)(it - (int64_t)row * n_chunk) * kChunk;
+        const int c1 = min(rw, c0 + kChunk);
+        const uint8_t *rp = img + (int64_t)(y0 + row) * pitch + (int64_t)x0 * 4;
+        for (int xb = c0; xb < c1; xb += 32 * kUnroll) {
+            uint32_t px[kUnroll];
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
+                const int x = xb + j * 32 + lane;
+                px[j] = x < c1 ? ld_px(rp, (int64_t)x * 4) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
+                if (xb + j * 32 >= c1) break;  // warp-uniform
+                const uint32_t p = px[j];
+                const bool valid = xb + j * 32 + lane < c1 && (all_pixels || (p >> 24) != 0u);
+                cnt += __popc(__ballot_sync(0xffffffffu, valid));
+                // runs of equal neighbouring pixels inside the warp's 32: the first lane of a run adds its length
+                const uint32_t key = valid ? (p & 0x00ffffffu) : 0xffffffffu;
+                const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+                const bool lead = lane == 0 || key != prev;
+                const unsigned leads = __ballot_sync(0xffffffffu, lead);
+                if (lead && valid) {
+                    const unsigned above = leads & ~((2u << lane) - 1u);  // run starts after this lane
+                    const unsigned int n = (unsigned int)((above ? __ffs((int)above) - 1 : 32) - lane);
+                    atomicAdd(&h[key & 0xffu], n);
+                    atomicAdd(&h[256 + ((key >> 8) & 0xffu)], n);
+                    atomicAdd(&h[512 + (key >> 16)], n);
                 }
-                prev = key;
-                len = 1;
-                have = true;
-            }
-        }
-        if (have) {
-            const int set0 = (prev >> 24) & 1;
-            atomicAdd(&sh[768 + (prev & 0xff)], len);
-            atomicAdd(&sh[768 + 256 + ((prev >> 8) & 0xff)], len);
-            atomicAdd(&sh[768 + 512 + ((prev >> 16) & 0xff)], len);
-            cnt_a += len;
-            if (set0) {
-                atomicAdd(&sh[prev & 0xff], len);
-                atomicAdd(&sh[256 + ((prev >> 8) & 0xff)], len);
-                atomicAdd(&sh[512 + ((prev >> 16) & 0xff)], len);
-                cnt_m += len;
             }
         }
     }
-    // warp-shuffle reduction of the two pixel counts, one shared atomic per warp
-    for (int o = 16; o > 0; o >>= 1) {
-        cnt_m += __shfl_xor_sync(0xffffffffu, cnt_m, o);
-        cnt_a += __shfl_xor_sync(0xffffffffu, cnt_a, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&scount[0], cnt_m);
-        atomicAdd(&scount[1], cnt_a);
-    }
+    if (lane == 0 && cnt) atomicAdd(&scount, cnt);
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * 3 * 256; i += blockDim.x)
-        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
-    if (threadIdx.x < 2 && scount[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)scount[threadIdx.x]);
+    unsigned long long *out = hist + (all_pixels ? 768 : 0);
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+        unsigned int v = 0;
+#pragma unroll
+        for (int w = 0; w < kHistWarps; ++w) v += sh[w][i];
+        if (v) atomicAdd(&out[i], (unsigned long long)v);
+    }
+    if (threadIdx.x == 0 && scount) atomicAdd(&counts[all_pixels ? 1 : 0], (unsigned long long)scount);
 }
 
 // np.median semantics: (v[(N-1)/2] + v[N/2]) / 2 per channel; masked set if it has pixels, else all pixels
@@ -604,6 +615,27 @@ struct b200comp_plan {
     std::vector<void *> owned;  // device allocations freed with the plan
 };
 
+// Every entry point that takes scratch memory from the stream-ordered pool calls this first: scratch buffers
+// and plans come and go (one plan per chunk in the host-buffer pipeline), and with the default release threshold
+// (0) the pool hands its memory back to the driver at every synchronisation, so each call would pay a fresh
+// device allocation (about a millisecond) instead of a pool lookup.
+static void keep_pool_memory(int device) {
+    static std::mutex mu;
+    static std::vector<int> tuned;
+    std::lock_guard<std::mutex> lock(mu);
+    if (std::find(tuned.begin(), tuned.end(), device) != tuned.end()) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    tuned.push_back(device);
+}
+static void keep_pool_memory() {
+    int device = 0;
+    if (cudaGetDevice(&device) == cudaSuccess) keep_pool_memory(device);
+}
+
 static const size_t kMaxSmemBytes = 200 * 1024;    // opt-in dynamic shared memory limit we request
 static const size_t kFusedSmemCap = 112 * 1024;    // placements needing more go through the generic kernels
 // dynamic shared memory of the tile kernel: alignment slack + resident tiles + patch + intermediate +
@@ -665,11 +697,12 @@ int b200comp_resize_rgba_lanczos(const uint8_t *src, int sw, int sh, size_t src_
     if (w == sw && h == sh)
         return resample_two_pass(src, sw, sh, (int64_t)src_pitch, dst, w, h, (int64_t)dst_pitch, nullptr, nullptr, 0,
                                  nullptr, nullptr, 0, nullptr, flags, st);
+    keep_pool_memory();
     TableSet ts;
     TableRef tx, ty;
     if (w != sw) tx = ts.want_legacy(sw, w);
     if (h != sh) ty = ts.want_legacy(sh, h);
-    ts.build(1);
+    ts.build((int64_t)w + h > 1024 ? 2 : 1);  // the two tables (double + libm) on two threads when they are large
     const size_t tbytes = ts.host.size() * sizeof(int32_t);
     const size_t sbytes = (size_t)std::max((int64_t)sh * w, (int64_t)h * sw) * 4;
     uint8_t *d_mem = nullptr;
@@ -726,12 +759,15 @@ int b200comp_fill_gradient(uint8_t *dst, int W, int H, size_t pitch, int horizon
     if (!dst || W < 1 || H < 1 || !c1 || !c2) return fail(B200COMP_EINVAL, "fill_gradient: bad argument");
     if (!aligned4(dst, (int64_t)pitch)) return fail(B200COMP_EINVAL, "fill_gradient: buffer must be 4-byte aligned");
     cudaStream_t st = S(stream);
+    keep_pool_memory();
     const int n = horizontal ? W : H;
     uint32_t *lut = nullptr;
     CUDA_TRY(cudaMallocAsync((void **)&lut, (size_t)n * 4, st));
     gradient_lut_kernel<<<(n + 255) / 256, 256, 0, st>>>(lut, n, c1[0], c1[1], c1[2], c2[0], c2[1], c2[2]);
-    dim3 grd((unsigned)std::min(16, (W + 255) / 256), (unsigned)H);
-    gradient_fill_kernel<<<grd, 256, 0, st>>>(dst, W, H, (int64_t)pitch, lut, horizontal ? 1 : 0);
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)pitch) & 15u) == 0;
+    const int64_t items = (int64_t)H * ((W + 1023) / 1024);
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((items + 7) / 8, 148 * 8));
+    gradient_fill_kernel<<<blocks, 256, 0, st>>>(dst, W, H, (int64_t)pitch, lut, horizontal ? 1 : 0, vec_ok);
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(lut, st);
     if (e != cudaSuccess) return fail(B200COMP_ECUDA, cudaGetErrorString(e));
@@ -745,16 +781,18 @@ int b200comp_masked_median_rgb(const uint8_t *img, int W, int H, size_t pitch, i
         return fail(B200COMP_EINVAL, "median: rectangle outside the image or empty");
     if (!aligned4(img, (int64_t)pitch)) return fail(B200COMP_EINVAL, "median: buffer must be 4-byte aligned");
     cudaStream_t st = S(stream);
+    keep_pool_memory();
     unsigned long long *d = nullptr;  // [2*3*256] hist + [2] counts + 3 int32 result
     const size_t bytes = (2 * 3 * 256 + 2) * sizeof(unsigned long long) + 4 * sizeof(int32_t);
     CUDA_TRY(cudaMallocAsync((void **)&d, bytes, st));
     cudaError_t e = cudaMemsetAsync(d, 0, bytes, st);
-    const int64_t total = (int64_t)(x1 - x0) * (y1 - y0);
-    const int64_t n_runs = (total + 7) / 8;
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_runs + 255) / 256, 148 * 8));
+    const int64_t items = (int64_t)(y1 - y0) * ((x1 - x0 + 1023) / 1024);  // warp = (row, 1024-pixel chunk)
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((items + kHistWarps - 1) / kHistWarps, 148 * 8));
     int32_t *d_out = reinterpret_cast<int32_t *>(d + 2 * 3 * 256 + 2);
     if (e == cudaSuccess) {
-        hist_rgb_kernel<<<blocks, 256, 0, st>>>(img, (int64_t)pitch, x0, y0, x1, y1, d, d + 2 * 3 * 256);
+        // masked set first; the all-pixel launch returns immediately unless no pixel had alpha > 0
+        hist_rgb_kernel<<<blocks, kHistWarps * 32, 0, st>>>(img, (int64_t)pitch, x0, y0, x1, y1, d, d + 2 * 3 * 256, 0);
+        hist_rgb_kernel<<<blocks, kHistWarps * 32, 0, st>>>(img, (int64_t)pitch, x0, y0, x1, y1, d, d + 2 * 3 * 256, 1);
         median_from_hist_kernel<<<1, 32, 0, st>>>(d, d + 2 * 3 * 256, d_out);
         e = cudaGetLastError();
     }
@@ -796,21 +834,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         ~Guard() { if (p) b200comp_plan_destroy(p); }
     } guard{plan};
     CUDA_TRY(cudaGetDevice(&plan->device));
-    {
-        // plans come and go (one per chunk in the host-buffer pipeline): keep freed blocks in the
-        // stream-ordered pool instead of returning them to the driver at every synchronisation
-        static std::mutex mu;
-        static std::vector<int> tuned;
-        std::lock_guard<std::mutex> lock(mu);
-        if (std::find(tuned.begin(), tuned.end(), plan->device) == tuned.end()) {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, plan->device) == cudaSuccess) {
-                uint64_t keep = UINT64_MAX;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            tuned.push_back(plan->device);
-        }
-    }
+    keep_pool_memory(plan->device);
     plan->create_stream = st;
     plan->n_canvases = n_canvases;
 
