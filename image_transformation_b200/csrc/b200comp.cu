@@ -1211,6 +1211,7 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
     // Runs of one plan share its command-stream buffers: they must be ordered on the stream.
     const int64_t tile0 = plan->tiles_before[(size_t)first];
     const int64_t n_tiles = plan->tiles_before[(size_t)first + count] - tile0;
+    if (n_tiles >= (int64_t)1 << 31) return fail(B200COMP_EINVAL, "plan_run_canvases: more than 2^31 tiles in one run");
     const int G = plan->G;
     const int K = (int)((n_tiles + G - 1) / G);
     const unsigned gx = (unsigned)((plan->max_tiles + kBinWarps - 1) / kBinWarps);  // warp = tile

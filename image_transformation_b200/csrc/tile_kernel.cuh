@@ -471,6 +471,7 @@ bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__
     const int tx0 = tx * kTileW, ty0 = ty * kTileH;
     const int tx1 = min(cv.W, tx0 + kTileW), ty1 = min(cv.H, ty0 + kTileH);
     const int64_t t = cv.tile_base - run_tile_base + local;
+    const unsigned tu = (unsigned)t;  // tiles of a run fit 31 bits (checked by the host): 32-bit division below
     uint32_t *mk = masks + t * (int64_t)mask_chunks * 2;
     int n = 0;
     int occ_chunk = -1, occ_top = 0;  // last placement that hides everything under it on this tile
@@ -536,7 +537,7 @@ bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__
             mk[2 * occ_chunk] &= ~((1u << occ_top) - 1u);
             mk[2 * occ_chunk + 1] &= ~((1u << occ_top) - 1u);
         }
-        cnt[(t % G) * K + t / G] = n ? n + 1 : 0;
+        cnt[(int64_t)(tu % (unsigned)G) * K + tu / (unsigned)G] = n ? n + 1 : 0;
     }
 }
 
@@ -596,13 +597,25 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
         const int tw = tx1 - tx0, th = ty1 - ty0;
         const bool vec = tw == kTileW && ((reinterpret_cast<uintptr_t>(cv.out) | (uintptr_t)cv.out_pitch) & 15u) == 0 &&
                          (!cv.bg || ((reinterpret_cast<uintptr_t>(cv.bg) | (uintptr_t)cv.bg_pitch) & 15u) == 0);
-        if (vec) {  // 16 lanes x 16 bytes per row, two rows per sweep
+        if (vec) {  // 16 lanes x 16 bytes per row, two rows per sweep, eight sweeps of loads in flight before the stores
             const int x4 = (lane & 15) * 4;
             const uint4 sv = make_uint4(cv.solid, cv.solid, cv.solid, cv.solid);
-            for (int yy = lane >> 4; yy < th; yy += 2) {
-                const int64_t px = (int64_t)(tx0 + x4) * 4;
-                const uint4 v = cv.bg ? __ldg(reinterpret_cast<const uint4 *>(cv.bg + (int64_t)(ty0 + yy) * cv.bg_pitch + px)) : sv;
-                *reinterpret_cast<uint4 *>(cv.out + (int64_t)(ty0 + yy) * cv.out_pitch + px) = v;
+            const uint8_t *bg = cv.bg;
+            uint8_t *out = cv.out;
+            const int64_t bgp = cv.bg_pitch, outp = cv.out_pitch;
+            const int64_t px = (int64_t)(tx0 + x4) * 4;
+            for (int y0 = lane >> 4; y0 < th; y0 += 16) {
+                uint4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int yy = y0 + 2 * k;
+                    v[k] = (bg && yy < th) ? __ldg(reinterpret_cast<const uint4 *>(bg + (int64_t)(ty0 + yy) * bgp + px)) : sv;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int yy = y0 + 2 * k;
+                    if (yy < th) *reinterpret_cast<uint4 *>(out + (int64_t)(ty0 + yy) * outp + px) = v[k];
+                }
             }
         } else {
             for (int yy = 0; yy < th; ++yy)
@@ -614,7 +627,8 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
         }
         return;
     }
-    const int64_t base = stream_off[t % G] + scan[(t % G) * K + t / G];
+    const unsigned tu = (unsigned)t;  // tiles of a run fit 31 bits (checked by the host): 32-bit division
+    const int64_t base = stream_off[tu % (unsigned)G] + scan[(int64_t)(tu % (unsigned)G) * K + tu / (unsigned)G];
     int n_slots = 0;
     uint32_t w[16];
     bool first_seen = false;
