@@ -1021,13 +1021,41 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             }
             pending.push_back(PendingMap{i, it->second});
         }
+        // overlays composited as they are (identity size, or pre-resampled into a plan-owned temporary) only need
+        // the alpha summary: it lets the binning pass drop transparent tile steps and use opaque ones as occluders
+        std::map<SrcKey, int> flags_only_index;
+        std::vector<int> flags_only_of((size_t)std::max(1, n_placements), -1);
+        for (int i = 0; i < n_placements; ++i) {
+            if (hp[i].mode != 0) continue;
+            SrcKey key(hp[i].src, hp[i].sw, hp[i].sh, (int64_t)hp[i].src_pitch);
+            auto it = flags_only_index.find(key);
+            if (it == flags_only_index.end()) {
+                PrepDesc pd;
+                std::memset(&pd, 0, sizeof pd);
+                pd.src = hp[i].src;
+                pd.src_pitch = hp[i].src_pitch;
+                pd.sw = hp[i].sw;
+                pd.sh = hp[i].sh;
+                pd.w4p = ((pd.sw + 3) / 4 + 3) & ~3;
+                pd.vec_ok = ((reinterpret_cast<uintptr_t>(pd.src) & 15u) == 0 && (pd.src_pitch & 15) == 0) ? 1 : 0;
+                prep_off.push_back(0);  // no prepared copy: dst stays null
+                flag_off.push_back(flag_words);
+                flag_words += (int64_t)((pd.sh + 3) / 4) * (pd.w4p / 4);
+                max_words = std::max<int64_t>(max_words, (int64_t)pd.w4p * pd.sh);
+                it = flags_only_index.emplace(key, (int)hprep.size()).first;
+                hprep.push_back(pd);
+            }
+            flags_only_of[i] = it->second;
+        }
+        const size_t n_full_prep = prep_index.size();
         EncodeTiledFn enc = encode_tiled_fn();
         if (!enc) return fail(B200COMP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
         const cuuint32_t estride[3] = {1, 1, 1};
         if (!hprep.empty()) {
             uint8_t *d_prepared = nullptr;  // one allocation for every prepared cutout of the plan
-            CUDA_TRY(dev_alloc((void **)&d_prepared, prep_bytes));
-            for (size_t j = 0; j < hprep.size(); ++j) hprep[j].dst = reinterpret_cast<uint32_t *>(d_prepared + prep_off[j]);
+            CUDA_TRY(dev_alloc((void **)&d_prepared, std::max<size_t>(prep_bytes, 16)));
+            for (size_t j = 0; j < n_full_prep; ++j)  // the descriptors after these only produce the alpha summary
+                hprep[j].dst = reinterpret_cast<uint32_t *>(d_prepared + prep_off[j]);
             for (const PendingMap &pm : pending) {
                 const int i = pm.placement;
                 const PrepDesc &pd = hprep[(size_t)pm.prep];
@@ -1100,8 +1128,9 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         CUDA_TRY(cudaStreamSynchronize(st));  // hmaps / hprep are locals
         for (int i = 0; i < n_placements; ++i) {
             if (map_of[i] >= 0) hp[i].tmap = plan->d_maps + (size_t)map_of[i] * sizeof(CUtensorMap);
-            if (prep_of[i] >= 0) {
-                const PrepDesc &pd = hprep[(size_t)prep_of[i]];
+            const int pi = prep_of[i] >= 0 ? prep_of[i] : flags_only_of[i];
+            if (pi >= 0) {
+                const PrepDesc &pd = hprep[(size_t)pi];
                 hp[i].flags = pd.flags;
                 hp[i].wq = pd.w4p / 4;
                 hp[i].sh4 = (pd.sh + 3) / 4;

@@ -95,7 +95,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // does no per-pixel work before the horizontal pass.  Pixels past the row end are zero.
 struct PrepDesc {
     const uint8_t *src;
-    uint32_t *dst;    // [sh][4][w4p]
+    uint32_t *dst;    // [sh][4][w4p]; null: only the alpha summary is produced (overlays composited as they are)
     uint32_t *flags;  // [ceil(sh/4)][w4p/4] alpha summary of each 4-row x 16-pixel block (zeroed before the launch):
                       // bit 0 = some alpha != 0, bit 1 = some alpha != 255
     int64_t src_pitch;
@@ -110,9 +110,9 @@ __global__ void __launch_bounds__(256) prepare_cutouts_kernel(const PrepDesc *__
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / d.w4p), g = (int)(i - (int64_t)r * d.w4p);
         const int gx = 4 * g;
-        uint32_t *o = d.dst + ((int64_t)r * 4) * d.w4p + g;
+        uint32_t *o = d.dst ? d.dst + ((int64_t)r * 4) * d.w4p + g : nullptr;  // null: alpha summary only
         if (gx >= d.sw) {  // padding words
-            o[0] = 0u; o[d.w4p] = 0u; o[2 * d.w4p] = 0u; o[3 * d.w4p] = 0u;
+            if (o) { o[0] = 0u; o[d.w4p] = 0u; o[2 * d.w4p] = 0u; o[3 * d.w4p] = 0u; }
             continue;
         }
         const uint8_t *rowp = d.src + (int64_t)r * d.src_pitch + (int64_t)gx * 4;
@@ -129,13 +129,15 @@ __global__ void __launch_bounds__(256) prepare_cutouts_kernel(const PrepDesc *__
         }
         uint32_t R, G, B, A;
         transpose4(p0, p1, p2, p3, R, G, B, A);
-        if (((A ^ (A >> 1)) & 0x7f7f7f7fu) == 0u) {
-            // every alpha is 0 or 255: MULDIV255(c, a) is c or 0 -> mask the colours with the alpha bytes
-            R &= A; G &= A; B &= A;
-        } else {
-            transpose4(premultiply_px(p0), premultiply_px(p1), premultiply_px(p2), premultiply_px(p3), R, G, B, A);
+        if (o) {
+            if (((A ^ (A >> 1)) & 0x7f7f7f7fu) == 0u) {
+                // every alpha is 0 or 255: MULDIV255(c, a) is c or 0 -> mask the colours with the alpha bytes
+                R &= A; G &= A; B &= A;
+            } else {
+                transpose4(premultiply_px(p0), premultiply_px(p1), premultiply_px(p2), premultiply_px(p3), R, G, B, A);
+            }
+            o[0] = R; o[d.w4p] = G; o[2 * d.w4p] = B; o[3 * d.w4p] = A;
         }
-        o[0] = R; o[d.w4p] = G; o[2 * d.w4p] = B; o[3 * d.w4p] = A;
         // alpha summary: lets the tile kernel skip fully transparent patches and the alpha plane of
         // fully opaque ones (pixels past the row end count as neither)
         const int nv = min(4, d.sw - gx);
@@ -484,22 +486,45 @@ bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__
         const DevPlacementT &d = placements[cv.first + min(i, cv.count - 1)];
         const int4 bx = __ldg(boxes + cv.first + min(i, cv.count - 1));  // (x, y, w, h): one 16-byte load per lane
         const bool hit = i < cv.count && max(tx0, bx.x) < min(tx1, bx.x + bx.z) && max(ty0, bx.y) < min(ty1, bx.y + bx.w);
-        Geo g = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        bool fits = false;
         const int mode = hit ? d.mode : 0;
+        // rectangle of the alpha summary (4-row x 16-pixel blocks of the SOURCE) under this tile, and the part of the
+        // tile the placement covers
+        bool scan = false;
+        const uint32_t *s_fl = nullptr;
+        int s_wq = 0, s_c0 = 0, s_nbw = 0, s_r0 = 0, s_r1 = 0, two = 0, tho = 0;
         if (hit && mode != 0) {
-            g = tile_geometry(d, tx0, ty0, tx1, ty1);
-            fits = d.pbw * d.nrbox <= patch_words && 4 * kTileW * (g.NRQ | 1) <= inter_words && 4 * g.NRQ <= d.nrbox &&
-                   g.cw0 < 65536 && g.rw0 < 65536;
+            const Geo g = tile_geometry(d, tx0, ty0, tx1, ty1);
+            const bool fits = d.pbw * d.nrbox <= patch_words && 4 * kTileW * (g.NRQ | 1) <= inter_words &&
+                              4 * g.NRQ <= d.nrbox && g.cw0 < 65536 && g.rw0 < 65536;
             if (!fits) atomicOr(status, kStatusPatchOverflow);  // host sizing bug: flagged, step dropped
+            scan = fits;
+            s_fl = d.flags;
+            s_wq = d.wq;
+            s_c0 = g.bq0;
+            s_nbw = g.bq1 - g.bq0 + 1;
+            s_r0 = g.rw0;
+            s_r1 = min(g.rw0 + g.NRQ, d.sh4);
+            two = g.two;
+            tho = g.tho;
+        } else if (hit) {  // overlay composited as it is: source pixel = canvas pixel - box origin
+            const int ix0 = max(tx0, bx.x), iy0 = max(ty0, bx.y), ix1 = min(tx1, bx.x + bx.z), iy1 = min(ty1, bx.y + bx.w);
+            two = ix1 - ix0;
+            tho = iy1 - iy0;
+            s_fl = d.flags;
+            scan = s_fl != nullptr;
+            s_wq = d.wq;
+            s_c0 = (ix0 - bx.x) >> 4;
+            s_nbw = ((ix1 - 1 - bx.x) >> 4) - s_c0 + 1;
+            s_r0 = (iy0 - bx.y) >> 2;
+            s_r1 = ((iy1 - 1 - bx.y) >> 2) + 1;
         }
         uint32_t my_bits = 0u;
-        for (uint32_t mr = __ballot_sync(0xffffffffu, fits); mr; mr &= mr - 1u) {
+        for (uint32_t mr = __ballot_sync(0xffffffffu, scan); mr; mr &= mr - 1u) {
             const int b = __ffs((int)mr) - 1;
-            const unsigned long long fp = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(d.flags), b);
-            const int wq = __shfl_sync(0xffffffffu, d.wq, b), bq0 = __shfl_sync(0xffffffffu, g.bq0, b);
-            const int nbw = __shfl_sync(0xffffffffu, g.bq1 - g.bq0 + 1, b);
-            const int r0 = __shfl_sync(0xffffffffu, g.rw0, b), r1 = __shfl_sync(0xffffffffu, min(g.rw0 + g.NRQ, d.sh4), b);
+            const unsigned long long fp = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(s_fl), b);
+            const int wq = __shfl_sync(0xffffffffu, s_wq, b), bq0 = __shfl_sync(0xffffffffu, s_c0, b);
+            const int nbw = __shfl_sync(0xffffffffu, s_nbw, b);
+            const int r0 = __shfl_sync(0xffffffffu, s_r0, b), r1 = __shfl_sync(0xffffffffu, s_r1, b);
             const uint32_t *fl = reinterpret_cast<const uint32_t *>((uintptr_t)fp);
             const int nb = nbw * (r1 - r0);
             uint32_t bits = 0u;
@@ -510,15 +535,16 @@ bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__
             bits = __reduce_or_sync(0xffffffffu, bits);
             if (lane == b) my_bits = bits;
         }
-        // keep: identity overlays always; resampled ones unless nothing but alpha 0 lies under the tile
-        const bool keep = hit && (mode == 0 || (fits && (my_bits & 1u)));
+        // keep: unless nothing but alpha 0 lies under the tile (overlays without a summary are always kept;
+        // resampled placements that do not fit the kernel's buffers were flagged above and are dropped)
+        const bool keep = hit && (scan ? (my_bits & 1u) != 0u : mode == 0);
         const uint32_t km = __ballot_sync(0xffffffffu, keep);
-        const bool opaque = keep && mode != 0 && !(my_bits & 2u);  // every alpha 255
+        const bool opaque = keep && scan && !(my_bits & 2u);  // every alpha 255
         const uint32_t om = __ballot_sync(0xffffffffu, opaque);
         // Occlusion: an opaque placement whose box covers the whole tile replaces every pixel of it (the V pass
-        // stores its pixels without reading the canvas), so nothing drawn earlier -- earlier placements and
-        // the background -- can show.  Those steps are dropped; the result is unchanged bit for bit.
-        const uint32_t cm = __ballot_sync(0xffffffffu, cull && opaque && g.two == tx1 - tx0 && g.tho == ty1 - ty0);
+        // stores its pixels without reading the canvas; over_px returns an opaque source pixel as it is), so
+        // nothing drawn earlier -- earlier placements and the background -- can show.  Those steps are dropped; the result is unchanged bit for bit.
+        const uint32_t cm = __ballot_sync(0xffffffffu, cull && opaque && two == tx1 - tx0 && tho == ty1 - ty0);
         if (lane == 0) {
             mk[2 * chunk] = km;
             mk[2 * chunk + 1] = om;
@@ -645,6 +671,7 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
                 const int ix0 = max(tx0, d.x), iy0 = max(ty0, d.y);
                 const int two = min(tx1, d.x + d.w) - ix0, tho = min(ty1, d.y + d.h) - iy0;
                 w[2] = (uint32_t)(ix0 - tx0) | ((uint32_t)(iy0 - ty0) << 8) | ((uint32_t)two << 16) | ((uint32_t)tho << 24);
+                occludes = ((om >> lane) & 1u) && two == tx1 - tx0 && tho == ty1 - ty0;
                 if (d.tmap) {
                     // TMA boxes start on 16-byte boundaries: the box begins up to 3 pixels left of the tile
                     // origin (w5 = that shift) and is kOverlayBoxW = 68 pixels wide
