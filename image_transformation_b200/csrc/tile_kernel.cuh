@@ -764,7 +764,8 @@ __device__ unsigned long long g_prof[16];
 //     tile buffers, up to two tiles ahead; finished tiles leave through TMA stores (bulk groups)
 //   * source patches: one TMA box per step, issued as soon as the previous step's horizontal pass has
 //     released the patch buffer -- also across tile boundaries
-// Thread 0 is the producer (it only issues copies; it never waits for data on behalf of others).
+// Lane 0 of the last warp is the producer (it only issues copies; it never waits for data on behalf of others);
+// the other eleven warps compute.
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict__ stream_off,
                         const DevCanvas *__restrict__ canvases, const uint8_t *__restrict__ maps,
@@ -870,7 +871,7 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
         if (c_flags & kTileOutTma) fence_async_smem();  // generic writes to the tile -> visible to the async proxy
         store_pending = true;
     };
-    // after a barrier: write the finished tile out (TMA store by thread 0, or generic stores by everyone)
+    // after a barrier: write the finished tile out (TMA store by the producer thread, or generic stores by everyone)
     auto flush_tile = [&]() {
         store_pending = false;
         const uint32_t *ct = ctile + (ctseq & (kTileBufs - 1)) * kTileWords;
@@ -982,7 +983,7 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
                 for (int jj = lane; jj < two; jj += 32) prefetch_coeffs(plx, nwx, n_out_x, ox0 + jj);
                 if (lane < tho) prefetch_coeffs(ply, nwy, n_out_y, oy0 + lane);
             }
-            PROF_MARK(2);  // dispatch, decode, producer (thread 0), coefficient prefetch
+            PROF_MARK(2);  // dispatch, decode, producer thread, coefficient prefetch
             mbar_wait(patch_full, pseq & 1u);  // source patch has landed in P
             PROF_MARK(3);  // wait for the patch
             ++pseq;
@@ -1014,7 +1015,7 @@ composite_stream_kernel(const Cmd *__restrict__ streams, const int64_t *__restri
                 else B200_VPASS(5, 3);
             }
 #undef B200_VPASS
-            PROF_MARK(6);  // V pass (+ background wait, producer on thread 0)
+            PROF_MARK(6);  // V pass (+ background wait, producer thread)
         } else if (kind == kCmdIdentTma) {
             // identity-size overlay: P holds the 64x32 source pixels under this tile (zero outside the overlay)
             mbar_wait(patch_full, pseq & 1u);

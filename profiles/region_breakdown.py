@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Instruction / stall-sample share of each phase of composite_tiles_kernel.
+"""Instruction / stall-sample share of each phase of composite_stream_kernel.
 usage: region_breakdown.py <ncu sass source csv> <nvdisasm -g -c dump> <tile_kernel.cuh>"""
 import csv
 import re
