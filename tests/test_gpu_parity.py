@@ -564,6 +564,18 @@ def test_batch_occlusion_culling(B, monkeypatch):
         assert_same(o, oracle.composite(sbg, pool, pl), f"solid {ww}x{hh}")
 
 
+def test_batch_fuzz_vs_oracle():
+    """Randomised batches (tools/fuzz_vs_oracle.py: opaque / soft / binary / transparent cutouts, scales 0.3..3,
+    identity and single-axis cases, off-canvas boxes, solid / opaque / translucent backgrounds), bit-exact."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "fuzz_vs_oracle", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_vs_oracle.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    assert fuzz.run(12, 20261018) == 0
+
+
 def test_batch_c4_aspect_sweep_vs_oracle(B):
     """BASELINE.json configs[3]: one canvas of every aspect ratio of the sweep (4399x1885 has rows TMA cannot
     address: pitch % 16 != 0), 20 objects each, bit-exact vs the oracle."""
