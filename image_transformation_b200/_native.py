@@ -136,3 +136,30 @@ def require_gpu() -> None:
             "no CUDA device visible: the B200 compositor has no CPU fallback "
             "(use the reference's own compositor.py on machines without a GPU)"
         )
+
+
+def rgba_array(img):
+    """(H, W, 4) uint8 array of a PIL RGBA image: the array the image was built on when this package produced it
+    (image_from_rgba) and nobody wrote to it since, else a copy (np.asarray, i.e. Pillow's tobytes()).
+    Pillow >= 11.2 can also export single-block images zero-copy through Arrow; that path was measured (0.2 ms
+    instead of ~1 ms per MB) but is not used: Pillow 12.2's export crashes the process on buffer-backed images.
+    The result is only read during the call that asked for it."""
+    import numpy as np
+
+    w, h = img.size
+    tagged = getattr(img, "_b200_rgba", None)
+    if tagged is not None and getattr(img, "readonly", 0) and tagged.shape == (h, w, 4):
+        return tagged
+    return np.ascontiguousarray(np.asarray(img), dtype=np.uint8)
+
+
+def image_from_rgba(out):
+    """PIL RGBA image over a freshly produced (H, W, 4) uint8 array without a second copy of the pixels
+    (Image.fromarray would copy them again: 33 MB at 4K).  The image is a real mutable PIL image: Pillow marks
+    buffer-backed images read-only and copies on the first write (putpixel, paste, alpha_composite, ImageDraw)."""
+    from PIL import Image
+
+    h, w = out.shape[:2]
+    img = Image.frombuffer("RGBA", (w, h), out, "raw", "RGBA", 0, 1)
+    img._b200_rgba = out  # lets a later composite() / statistics call on this image skip the PIL -> NumPy copy
+    return img

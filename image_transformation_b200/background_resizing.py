@@ -21,13 +21,13 @@ def _load_background_rgba(background_path: str) -> Image.Image:
 
 
 def _as_rgba_array(img: Image.Image) -> np.ndarray:
-    return np.ascontiguousarray(np.asarray(img.convert("RGBA")), dtype=np.uint8)
+    return _native.rgba_array(img if img.mode == "RGBA" else img.convert("RGBA"))
 
 
 def _median_color_nontransparent(img_rgba: Image.Image) -> RGB:
     """Per-channel median over alpha>0 pixels, all pixels if none (background_resizing.py:11-22)."""
     _native.require_gpu()
-    a = np.ascontiguousarray(np.array(img_rgba), dtype=np.uint8)
+    a = _native.rgba_array(img_rgba) if img_rgba.mode == "RGBA" else np.ascontiguousarray(np.array(img_rgba), dtype=np.uint8)
     if a.ndim != 3 or a.shape[2] != 4:
         # the reference indexes arr[:, :, 3]; anything but 4 channels fails there
         raise IndexError("index 3 is out of bounds for axis 2 with size %d" % (a.shape[2] if a.ndim == 3 else 0))
@@ -54,7 +54,7 @@ def fill_solid(background_path: str, canvas_size: Tuple[int, int]) -> Image.Imag
     rc = _native.lib().b200comp_fill_solid_host(a.ctypes.data, a.shape[1], a.shape[0], a.strides[0], out.ctypes.data,
                                                 W, H, out.strides[0], rgb)
     _native.check(rc, "fill_solid")
-    return Image.fromarray(out)
+    return _native.image_from_rgba(out)
 
 
 def _edge_strip_median_colors(img: Image.Image, strip_px: int = 8) -> Tuple[RGB, RGB, RGB, RGB]:
@@ -88,4 +88,4 @@ def fill_gradient(background_path: str, canvas_size: Tuple[int, int]) -> Image.I
                                                    out.ctypes.data, W, H, out.strides[0], 8, edges,
                                                    ctypes.byref(horizontal))
     _native.check(rc, "fill_gradient")
-    return Image.fromarray(out)
+    return _native.image_from_rgba(out)

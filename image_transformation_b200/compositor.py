@@ -42,8 +42,7 @@ def resolve_placements(placements: Sequence[dict], sizes: Dict[int, Tuple[int, i
 
 
 def _rgba_array(img: Image.Image) -> np.ndarray:
-    a = np.asarray(img)
-    return np.ascontiguousarray(a, dtype=np.uint8)
+    return _native.rgba_array(img)
 
 
 def composite(background_img: Image.Image, object_images: Dict[int, Image.Image], placements: List[Dict]) -> Image.Image:
@@ -77,7 +76,7 @@ def composite(background_img: Image.Image, object_images: Dict[int, Image.Image]
     rc = _native.lib().b200comp_composite_host(bg.ctypes.data, W, H, bg.strides[0], out.ctypes.data, out.strides[0],
                                                recs, len(resolved))
     _native.check(rc, "composite")
-    return Image.fromarray(out)
+    return _native.image_from_rgba(out)
 
 
 def load_object_images(results_json_path: str) -> Dict[int, Image.Image]:

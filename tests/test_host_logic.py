@@ -114,3 +114,26 @@ def test_unpremultiply_magic_division_is_exact():
         assert m <= 1 << 24
         for c in range(256):
             assert ((c * 65280) * m) >> 32 == (255 * c) // a, (c, a)
+
+
+def test_rgba_array_paths():
+    """_native.rgba_array: tagged outputs are reused until written to, every other image is copied correctly
+    (owned, buffer-backed / read-only, larger than one Pillow block)."""
+    from PIL import Image
+
+    from image_transformation_b200 import _native
+
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (60, 40, 4), dtype=np.uint8)
+    for img in (Image.fromarray(a, "RGBA"), Image.fromarray(a, "RGBA").copy()):
+        v = _native.rgba_array(img)
+        assert v.shape == (60, 40, 4) and v.dtype == np.uint8 and np.array_equal(v, a)
+    big = Image.new("RGBA", (3000, 1500), (1, 2, 3, 4))  # 18 MB: more than one 16 MB block
+    assert tuple(_native.rgba_array(big)[1499, 2999]) == (1, 2, 3, 4)
+    out = a.copy()
+    tagged = _native.image_from_rgba(out)
+    assert _native.rgba_array(tagged) is out
+    tagged.putpixel((0, 0), (9, 9, 9, 9))  # copy-on-write: the tag no longer applies
+    v = _native.rgba_array(tagged)
+    assert v is not out and tuple(v[0, 0]) == (9, 9, 9, 9) and tuple(out[0, 0]) == tuple(a[0, 0])
+    assert not hasattr(tagged.copy(), "_b200_rgba")
