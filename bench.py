@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--workload", default="c3_4k_20obj")
     ap.add_argument("--batch", type=int, default=0, help="canvases per GPU per step (0: workload default, capped by HBM)")
     ap.add_argument("--e2e-batch", type=int, default=64, help="canvases per end-to-end (host buffer) step")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample", type=int, default=0, help="canvases in the CPU baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -215,7 +215,7 @@ def run_reference(args):
     if rank != 0:
         return  # the CPU arm runs on rank 0 alone
     cores = host_cores()
-    sample = args.cpu_sample or max(8, min(cores, 64))
+    sample = args.cpu_sample or max(8, min(4 * cores, 64))  # about 25 s of CPU work: four canvases per thread
     pool, canvases, placements = build_inputs(args.workload, 0, sample)
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_port_throughput(pool, canvases[: max(1, min(sample, cores))], placements, cores)
@@ -417,7 +417,7 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        sample = args.cpu_sample or max(8, min(cores, 64))
+        sample = args.cpu_sample or max(8, min(4 * cores, 64))  # about 25 s of CPU work: four canvases per thread
         sample = min(sample, batch)
         v, cps, dt = cpu_port_throughput(pool, canvases[:sample], placements[:sample], cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "canvases_per_s": cps,
