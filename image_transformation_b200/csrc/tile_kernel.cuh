@@ -458,8 +458,14 @@ __device__ __forceinline__ void store_cmd(Cmd *dst, const uint32_t (&w)[16]) {
 // must have some non-zero alpha (the whole warp reads the summary rectangle of each candidate).  The keep /
 // opaque masks go to `masks` for the fill kernel; the tile's slot count (1 + steps, or 0 for a tile nothing
 // is drawn on -- such tiles never enter a stream) is stored stream-major for the scan.
-constexpr int kBinWarps = 4;  // tiles per block (16 measured slower: uneven tiles hold block slots)
-__global__ void __launch_bounds__(kBinWarps * 32)
+#ifndef B200COMP_BIN_WARPS
+#define B200COMP_BIN_WARPS 4
+#endif
+constexpr int kBinWarps = B200COMP_BIN_WARPS;  // tiles per block (16 measured slower: uneven tiles hold block slots)
+#ifndef B200COMP_BIN_MINBLOCKS
+#define B200COMP_BIN_MINBLOCKS 10  // resident blocks per SM the binning kernels are compiled for (48 registers: 11 % faster than uncapped)
+#endif
+__global__ void __launch_bounds__(kBinWarps * 32, B200COMP_BIN_MINBLOCKS)
 bin_count_kernel(const DevCanvas *__restrict__ canvases, const DevPlacementT *__restrict__ placements,
                  const int4 *__restrict__ boxes, int64_t run_tile_base, int G, int K, int32_t *__restrict__ cnt, uint32_t *__restrict__ masks,
                  int mask_chunks, int patch_words, int inter_words, unsigned long long *__restrict__ cursor,
@@ -602,7 +608,7 @@ bin_scan_kernel(int32_t *__restrict__ cnt, int G, int K, int64_t n_tiles, int64_
 // fill: warp = tile, lane = placement.  Tiles without steps are finished right here (background or solid
 // colour copied to the output: they never reach the tile kernel); the others get their TILE record and one
 // record per kept placement, in z-order (ballot ranks).
-__global__ void __launch_bounds__(kBinWarps * 32)
+__global__ void __launch_bounds__(kBinWarps * 32, B200COMP_BIN_MINBLOCKS)
 bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPlacementT *__restrict__ placements,
                 int64_t run_tile_base, int G, int K, const int32_t *__restrict__ scan, const uint32_t *__restrict__ masks,
                 int mask_chunks, const int64_t *__restrict__ stream_off, Cmd *__restrict__ streams, int64_t capacity,
