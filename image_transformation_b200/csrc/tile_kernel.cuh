@@ -18,6 +18,10 @@
 #pragma once
 #include "kernels.cuh"
 
+#ifndef B200COMP_UNCHAINED
+#define B200COMP_UNCHAINED 0  // tap_sum: 1 = one accumulator per coefficient plane (more ILP, one more ALU op per sample)
+#endif
+
 namespace b200comp {
 
 __device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
@@ -35,6 +39,18 @@ __device__ __forceinline__ int32_t dp4a_us(uint32_t a, uint32_t b, int32_t c) {
 template <int NW>
 __device__ __forceinline__ int32_t tap_sum(const uint32_t (&wd)[NW], const uint32_t (&k0)[NW], const uint32_t (&k1)[NW],
                                            const uint32_t (&k2)[NW]) {
+#if B200COMP_UNCHAINED
+    // three independent chains (one per plane), recombined with two immediate PRMTs and one three-input add
+    int32_t t2 = 32;
+    uint32_t u1 = 0u, u0 = 0u;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        t2 = dp4a_us(wd[i], k2[i], t2);
+        u1 = dp4a_uu(wd[i], k1[i], u1);
+        u0 = dp4a_uu(wd[i], k0[i], u0);
+    }
+    return (int32_t)(u0 + __byte_perm(u1, 0u, 0x2104) + __byte_perm((uint32_t)t2, 0u, 0x1044));
+#endif
     int32_t t = 32;
 #pragma unroll
     for (int i = 0; i < NW; ++i) t = dp4a_us(wd[i], k2[i], t);
