@@ -403,6 +403,22 @@ def run_b200(args):
                "d2h_bytes_per_step": int(nb * W0 * H0 * 4), "canvases_per_step": nb, "ms_per_step": dt * 1e3,
                "canvases_per_s": world * nb / dt,
                "api": "b200comp_composite_batch_host (pinned host buffers; coefficient tables rebuilt every step)"}
+        # For information: the same call when the caller states the canvases' solid colour (what fill_solid
+        # produces) instead of uploading 33 MB of identical pixels per canvas.  Not the judged e2e.
+        if host_bg is not None and world == 1:
+            cvs_solid = (_native.Canvas * nb)()
+            for i in range(nb):
+                c = cvs[i]
+                cvs_solid[i] = _native.Canvas(c.out, c.out_pitch, None, 0, c.solid_rgba, c.W, c.H, c.first_placement, c.n_placements, 0)
+            rc = L.b200comp_composite_batch_host(cvs_solid, nb, pls, len(recs), n_threads, 4, 3)
+            _native.check(rc, "composite_batch_host")
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                _native.check(L.b200comp_composite_batch_host(cvs_solid, nb, pls, len(recs), n_threads, 4, 3), "composite_batch_host")
+            dts = (time.perf_counter() - t0) / args.e2e_steps
+            e2e["solid_canvas_variant"] = {"value": nb * W0 * H0 / 1e6 / dts, "unit": UNIT, "canvases_per_s": nb / dts,
+                                           "h2d_bytes_per_step": int(sum(pool[k].nbytes for k in used_pool)),
+                                           "note": "same batch with the canvases' colour passed as a value (no background upload); informational"}
         # spot-check one e2e canvas against the device-resident result path's oracle
         if rank == 0:
             import oracle
