@@ -5,9 +5,10 @@ canvases/s at 4K, HBM GB/s vs peak, 1/2/4/8 GPUs).
     python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
     python bench.py --impl reference --gpus N --steps K ...  # CPU port of the reference path
 
-A "step" is one pass of the fused resample + alpha-over kernel over one batch of synthetic
-canvases (workload c3_4k_20obj = BASELINE.json configs[2]: 3840x2160 canvases, 20 RGBA cutouts
-each, scale 0.5..1.0, random flex layouts).  Canvases are independent: every rank owns `--batch`
+A "step" is one b200comp_plan_run -- cutout preparation, the three binning kernels and the persistent
+fused resample + alpha-over kernel: 5 launches -- over one batch of synthetic canvases (workload
+c3_4k_20obj = BASELINE.json configs[2]: 3840x2160 canvases, 20 RGBA cutouts each, scale 0.5..1.0,
+random flex layouts).  Canvases are independent: every rank owns `--batch`
 canvases (weak scaling), there is no collective on the data path.  Rank 0 prints ONE JSON line.
 """
 from __future__ import annotations
