@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=0, help="canvases per GPU per step (0: workload default, capped by HBM)")
     ap.add_argument("--e2e-batch", type=int, default=64, help="canvases per end-to-end (host buffer) step")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="canvases per copy/compute/copy sub-chunk of the host-buffer pipeline (0: library default, about 32 MB of canvas)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="canvases in the CPU baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -383,7 +384,7 @@ def run_b200(args):
 
         def e2e_step():
             t_call = time.perf_counter()
-            rc = L.b200comp_composite_batch_host(cvs, nb, pls, len(recs), n_threads, 4, 3)
+            rc = L.b200comp_composite_batch_host(cvs, nb, pls, len(recs), n_threads, args.e2e_chunk, 3)
             _native.check(rc, "composite_batch_host")
             if os.environ.get("B200COMP_TRACE"):
                 print(f"[bench] composite_batch_host call took {(time.perf_counter() - t_call) * 1e3:.2f} ms", file=sys.stderr)
@@ -411,11 +412,11 @@ def run_b200(args):
             for i in range(nb):
                 c = cvs[i]
                 cvs_solid[i] = _native.Canvas(c.out, c.out_pitch, None, 0, c.solid_rgba, c.W, c.H, c.first_placement, c.n_placements, 0)
-            rc = L.b200comp_composite_batch_host(cvs_solid, nb, pls, len(recs), n_threads, 4, 3)
+            rc = L.b200comp_composite_batch_host(cvs_solid, nb, pls, len(recs), n_threads, args.e2e_chunk, 3)
             _native.check(rc, "composite_batch_host")
             t0 = time.perf_counter()
             for _ in range(args.e2e_steps):
-                _native.check(L.b200comp_composite_batch_host(cvs_solid, nb, pls, len(recs), n_threads, 4, 3), "composite_batch_host")
+                _native.check(L.b200comp_composite_batch_host(cvs_solid, nb, pls, len(recs), n_threads, args.e2e_chunk, 3), "composite_batch_host")
             dts = (time.perf_counter() - t0) / args.e2e_steps
             e2e["solid_canvas_variant"] = {"value": nb * W0 * H0 / 1e6 / dts, "unit": UNIT, "canvases_per_s": nb / dts,
                                            "h2d_bytes_per_step": int(sum(pool[k].nbytes for k in used_pool)),

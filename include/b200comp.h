@@ -170,7 +170,8 @@ int b200comp_composite_batch(const b200comp_canvas *canvases, int n_canvases, co
  * calls): same descriptors, but every pixel pointer is a HOST pointer
  * (pinned memory overlaps copies with compute; pageable works).  Copies
  * cutouts (de-duplicated by pointer) and backgrounds to the device, runs the
- * fused kernel in chunks over `n_streams` streams and copies the canvases back.
+ * fused kernel in chunks of `chunk_canvases` canvases (<= 0: about 32 MB of canvas per chunk) over three
+ * streams (`n_streams` is kept for ABI stability) and copies the canvases back.
  * Synchronous.  b200comp_composite_host is the single-canvas form behind the
  * drop-in composite() (compositor.py:6).
  * ---------------------------------------------------------------------- */
