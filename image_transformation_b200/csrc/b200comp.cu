@@ -1408,6 +1408,14 @@ int b200comp_plan_check(b200comp_plan *plan, void *stream) {
     return 0;
 }
 
+// internal (host_api.cu): copy the status word into pinned host memory in stream order, no synchronisation --
+// the host-buffer pipeline reads it after the event that follows the copy
+int b200comp_plan_status_async_(b200comp_plan *plan, int *pinned_host_dst, void *stream) {
+    if (!plan || !pinned_host_dst) return fail(B200COMP_EINVAL, "plan_status_async: null argument");
+    CUDA_TRY(cudaMemcpyAsync(pinned_host_dst, plan->d_status, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+    return 0;
+}
+
 int b200comp_plan_last_records(b200comp_plan *plan, void *stream, int64_t *records) {
     if (!plan || !records) return fail(B200COMP_EINVAL, "plan_last_records: null argument");
     unsigned long long h = 0;

@@ -54,6 +54,8 @@ int b200comp_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? 0 
 
 // internal: set the message returned by b200comp_last_error() (defined in b200comp.cu)
 int b200comp_set_error_(int code, const char *msg);
+// internal: stream-ordered copy of a plan's status word into pinned host memory (defined in b200comp.cu)
+int b200comp_plan_status_async_(b200comp_plan *plan, int *pinned_host_dst, void *stream);
 
 // Pipelined host-buffer batch.  Canvases are processed in super-chunks (`8 * chunk_canvases`, double
 // buffered on the device); inside a super-chunk three streams form a copy-in / compute / copy-out
@@ -130,16 +132,15 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
             return b200comp_set_error_(B200COMP_ENOMEM, "canvas staging allocation failed");
     cudaStreamSynchronize(nullptr);  // the allocations above are ordered on the default stream
     stamp("staging allocated", 0);
-    cudaStream_t s_in = nullptr, s_exec = nullptr, s_out = nullptr, s_plan = nullptr, s_chk = nullptr;
+    cudaStream_t s_in = nullptr, s_exec = nullptr, s_out = nullptr, s_plan = nullptr;
     struct StreamGuard {
-        cudaStream_t *s[5];
+        cudaStream_t *s[4];
         ~StreamGuard() { for (auto p : s) if (*p) cudaStreamDestroy(*p); }
-    } sguard{{&s_in, &s_exec, &s_out, &s_plan, &s_chk}};
+    } sguard{{&s_in, &s_exec, &s_out, &s_plan}};
     if (cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s_exec, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&s_plan, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&s_chk, cudaStreamNonBlocking) != cudaSuccess)
+        cudaStreamCreateWithFlags(&s_plan, cudaStreamNonBlocking) != cudaSuccess)
         return b200comp_set_error_(B200COMP_ECUDA, "stream creation failed");
     const int max_sub = (super_canvases + chunk_canvases - 1) / chunk_canvases;
     std::vector<cudaEvent_t> ev_in((size_t)max_sub * 3), ev_exec((size_t)max_sub * 3);  // one set per staging buffer
@@ -204,6 +205,10 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
 
     int rc = 0;
     std::string err;
+    // one pinned status word per staging set (allocated once per thread, kept for the thread's lifetime)
+    thread_local int *h_status = nullptr;
+    if (!h_status && cudaHostAlloc((void **)&h_status, kBufs * sizeof(int), cudaHostAllocDefault) != cudaSuccess)
+        return b200comp_set_error_(B200COMP_ENOMEM, "pinned status allocation failed");
     SuperPlan live[kBufs];  // plans of the super-chunks in flight, by staging buffer
     SuperPlan built;    // plan being resolved by the helper thread
     auto retire = [&](int buf) {  // wait for the super-chunk that used `buf`, check it, free its plan
@@ -214,14 +219,12 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
             rc = B200COMP_ECUDA;
             err = cudaGetErrorString(e);
         }
-        if (rc == 0) {
-            // the plan's kernels are complete (ev_done): read its status word on a stream of its own, NOT on
-            // s_exec, whose queue already holds the next super-chunks
-            const int c = b200comp_plan_check(live[buf].plan, s_chk);
-            if (c) {
-                rc = c;
-                err = b200comp_last_error();
-            }
+        if (rc == 0 && h_status[buf] != 0) {
+            // the status word travelled on the copy-out stream right behind this super-chunk's canvases (a copy
+            // of its own on another stream would queue behind the NEXT super-chunks' canvases in the copy engine
+            // and stall the host for their whole transfer)
+            rc = B200COMP_EINTERNAL;
+            err = "binning reported a sizing violation (status " + std::to_string(h_status[buf]) + ")";
         }
         cudaStreamSynchronize(s_plan);
         b200comp_plan_destroy(live[buf].plan);
@@ -277,6 +280,8 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
                                   align_up((size_t)cv.W * 4, 16), (size_t)cv.W * 4, cv.H, cudaMemcpyDeviceToHost, s_out);
             }
         }
+        h_status[buf] = 0;
+        if (rc == 0) rc = b200comp_plan_status_async_(live[buf].plan, &h_status[buf], s_out);
         cudaEventRecord(ev_done[buf], s_out);
         stamp("super-chunk enqueued", si);
         if (rc) {
