@@ -576,7 +576,7 @@ struct b200comp_plan {
     DevPlacementT *d_placements = nullptr;
     DevCanvas *d_canvases = nullptr;
     int *d_status = nullptr;
-    int patch_words = 0, inter_words = 0;
+    int slot_words = 0, iw_words = 0;  // ring slot of the widest patch class / private intermediate of one warp
     size_t smem_bytes = 0;
     int64_t info[B200COMP_INFO_COUNT] = {0};
     // placements resampled by the generic kernels before the tile kernel (extreme scales, vertical-first)
@@ -600,6 +600,8 @@ struct b200comp_plan {
     Cmd *d_streams = nullptr;
     int32_t *d_bin = nullptr;        // [G][K] per-tile slot counts, scanned in place
     int64_t *d_stream_off = nullptr; // [G + 1]
+    int64_t *d_stream_len = nullptr; // [G] records per stream, END included
+    uint32_t *d_dbg = nullptr;       // 16 words written by the tile kernel's watchdog
     uint8_t *d_maps = nullptr;       // every CUtensorMap of the plan (placements, overlays, canvases)
     uint32_t *d_masks = nullptr;     // [tiles][mask_chunks][2] keep / opaque masks from the count kernel
     int4 *d_boxes = nullptr;         // destination boxes (x, y, w, h) of the placements: the binning hit test
@@ -638,12 +640,14 @@ static void keep_pool_memory() {
 
 static const size_t kMaxSmemBytes = 200 * 1024;    // opt-in dynamic shared memory limit we request
 static const size_t kFusedSmemCap = 112 * 1024;    // placements needing more go through the generic kernels
-// dynamic shared memory of the tile kernel: alignment slack + resident tiles + patch + intermediate +
-// command ring + mbarriers
-static size_t tile_smem_bytes(int64_t patch_words, int64_t inter_words) {
-    return 1024 + ((size_t)kTileBufs * kTileWords + (size_t)patch_words + (size_t)inter_words) * 4 + kRing * sizeof(Cmd) +
-           (kTileBufs + 1) * sizeof(uint64_t) + 36 * sizeof(uint32_t);
+// dynamic shared memory of the tile kernel: alignment slack + resident tiles + patch chunk ring + one private
+// intermediate per compute warp + command blocks + TILE records + mbarriers
+static size_t tile_smem_bytes(int64_t slot_words, int64_t iw_words) {
+    return 1024 + ((size_t)kTileBufs * kTileWords + (size_t)kPRing * slot_words + (size_t)kSlabWarps * iw_words) * 4 +
+           (size_t)kCmdRing * kCmdBlk * sizeof(Cmd) + (size_t)kTileBufs * 16 * sizeof(uint32_t) + sizeof(SlabBars) + 16;
 }
+// ring slot of a placement whose patch rows are `pwc` word columns wide: kChunkQuads quads x 4 planes x 4 * pwc words
+static int slot_words_of(int pwc) { return kChunkQuads * 16 * pwc; }
 static_assert(sizeof(b200comp_placement) == 48 && sizeof(b200comp_canvas) == 56, "public struct layout");
 
 #pragma GCC visibility push(default)
@@ -843,7 +847,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     std::vector<DevPlacementT> hp((size_t)std::max(1, n_placements));
     std::vector<std::pair<TableRef, TableRef>> tref((size_t)std::max(1, n_placements));
     std::vector<int> pre_index((size_t)std::max(1, n_placements), -1);
-    int max_patch = kOverlayBoxW * kTileH, max_inter = 16;  // the patch buffer also stages identity overlays
+    int max_slot = kOverlayBoxW * kIdentRows, max_iw = 16;  // the chunk ring also stages identity overlays
     int64_t n_fused = 0, n_ident = 0;
     for (int i = 0; i < n_placements; ++i) {
         const b200comp_placement &p = placements[i];
@@ -851,6 +855,9 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             return fail(B200COMP_EINVAL, "plan_create: placement " + std::to_string(i) + " has a null source or empty size");
         if (!aligned4(p.src, p.src_pitch) || p.src_pitch < (int64_t)p.sw * 4 || p.src_pitch > INT32_MAX)
             return fail(B200COMP_EINVAL, "plan_create: placement " + std::to_string(i) + " source misaligned or bad pitch");
+        // the device hit tests add x + w and y + h in int32
+        if (p.x < -(1 << 30) || p.x > (1 << 30) || p.y < -(1 << 30) || p.y > (1 << 30) || p.w > (1 << 30) || p.h > (1 << 30))
+            return fail(B200COMP_EINVAL, "plan_create: placement " + std::to_string(i) + " box out of range (|x|, |y|, w, h <= 2^30)");
         DevPlacementT &d = hp[i];
         std::memset(&d, 0, sizeof d);
         d.src = p.src;
@@ -867,16 +874,15 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         const int nwy = need_v ? packed_words(lanczos_ksize(p.sh, p.h)) : 3;
         const bool vertical_first = (p.flags & B200COMP_VERTICAL_FIRST) && need_h && need_v;
         bool fused = !vertical_first && nwx > 0 && nwy > 0;
-        int64_t patch = 0, inter = 0;
-        int ncw = 0, nrq = 0;
+        int pwc = 0, slot = 0, iw = 0;
         if (fused) {
-            // TMA: the box must start on a 16-byte boundary of the plane row and span a 16-byte multiple,
-            // so the kernel aligns the first word down to a multiple of 4 (+3 words of slack)
-            ncw = (words_bound(p.sw, p.w, kTileW, nwx) + 3 + 3) & ~3;
-            nrq = words_bound(p.sh, p.h, kTileH, nwy);
-            patch = (int64_t)4 * (4 * nrq) * ncw;          // TMA box: rows x (words x 4 channels)
-            inter = (int64_t)4 * kTileW * (nrq | 1);       // 4 channel planes x columns x row-quads
-            fused = tile_smem_bytes(patch, inter) <= kFusedSmemCap && 4 * ncw <= 256 && 4 * nrq <= 256 &&
+            // patch width class: word columns one tile step can need, rounded up to a multiple of 4 (one tensor map
+            // per cutout and class); row quads one tile step can need -> the warps' private intermediates
+            pwc = (words_bound(p.sw, p.w, kTileW, nwx) + 3) & ~3;
+            const int nrq = words_bound(p.sh, p.h, kTileH, nwy);
+            slot = slot_words_of(pwc);
+            iw = 4 * kSlabW * (nrq | 1);
+            fused = tile_smem_bytes(std::max(slot, kOverlayBoxW * kIdentRows), iw) <= kFusedSmemCap && 4 * pwc <= 256 && nrq <= 255 &&
                     p.sw < 262144 && p.sh < 262144;
         }
         if (fused) {
@@ -885,16 +891,15 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             tref[i].second = ts.want_packed(p.sh, p.h, !need_v);
             d.nwx = tref[i].first.ks;
             d.nwy = tref[i].second.ks;
-            d.pbw = 4 * ncw;
-            d.nrbox = 4 * nrq;
+            d.pwc = pwc;
             // the kernel recomputes each window start from these doubles exactly as the table builder does;
             // a skipped pass is the 1-tap identity: scale 1, support 1 -> first tap = the sample itself
             d.scale_x = need_h ? (double)p.sw / p.w : 1.0;
             d.support_x = need_h ? 3.0 * std::max(d.scale_x, 1.0) : 1.0;
             d.scale_y = need_v ? (double)p.sh / p.h : 1.0;
             d.support_y = need_v ? 3.0 * std::max(d.scale_y, 1.0) : 1.0;
-            max_patch = std::max<int>(max_patch, (int)patch);
-            max_inter = std::max<int>(max_inter, (int)inter);
+            max_slot = std::max(max_slot, slot);
+            max_iw = std::max(max_iw, iw);
             ++n_fused;
         } else {
             // pre-resample with the generic kernels; the tile kernel then sees an identity-size overlay
@@ -1009,13 +1014,14 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
                 pd.src_pitch = p.src_pitch;
                 pd.sw = p.sw;
                 pd.sh = p.sh;
-                pd.w4p = ((p.sw + 3) / 4 + 3) & ~3;
+                pd.w4 = (p.sw + 3) / 4;
+                pd.wq = (pd.w4 + 3) / 4;
                 pd.vec_ok = ((reinterpret_cast<uintptr_t>(p.src) & 15u) == 0 && (p.src_pitch & 15) == 0) ? 1 : 0;
                 prep_off.push_back(prep_bytes);
-                prep_bytes += ((size_t)pd.w4p * 16 * p.sh + 255) & ~(size_t)255;
+                prep_bytes += ((size_t)pd.w4 * 64 * ((p.sh + 3) / 4) + 255) & ~(size_t)255;
                 flag_off.push_back(flag_words);
-                flag_words += (int64_t)((p.sh + 3) / 4) * (pd.w4p / 4);
-                max_words = std::max<int64_t>(max_words, (int64_t)pd.w4p * p.sh);
+                flag_words += (int64_t)((p.sh + 3) / 4) * pd.wq;
+                max_words = std::max<int64_t>(max_words, (int64_t)pd.w4 * ((p.sh + 3) / 4));
                 it = prep_index.emplace(key, (int)hprep.size()).first;
                 hprep.push_back(pd);
             }
@@ -1036,12 +1042,13 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
                 pd.src_pitch = hp[i].src_pitch;
                 pd.sw = hp[i].sw;
                 pd.sh = hp[i].sh;
-                pd.w4p = ((pd.sw + 3) / 4 + 3) & ~3;
+                pd.w4 = (pd.sw + 3) / 4;
+                pd.wq = (pd.w4 + 3) / 4;
                 pd.vec_ok = ((reinterpret_cast<uintptr_t>(pd.src) & 15u) == 0 && (pd.src_pitch & 15) == 0) ? 1 : 0;
                 prep_off.push_back(0);  // no prepared copy: dst stays null
                 flag_off.push_back(flag_words);
-                flag_words += (int64_t)((pd.sh + 3) / 4) * (pd.w4p / 4);
-                max_words = std::max<int64_t>(max_words, (int64_t)pd.w4p * pd.sh);
+                flag_words += (int64_t)((pd.sh + 3) / 4) * pd.wq;
+                max_words = std::max<int64_t>(max_words, (int64_t)pd.w4 * ((pd.sh + 3) / 4));
                 it = flags_only_index.emplace(key, (int)hprep.size()).first;
                 hprep.push_back(pd);
             }
@@ -1056,21 +1063,28 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             CUDA_TRY(dev_alloc((void **)&d_prepared, std::max<size_t>(prep_bytes, 16)));
             for (size_t j = 0; j < n_full_prep; ++j)  // the descriptors after these only produce the alpha summary
                 hprep[j].dst = reinterpret_cast<uint32_t *>(d_prepared + prep_off[j]);
+            // one tensor map per (prepared cutout, patch width class): dims (4 rows x word columns, 4 planes, row quads),
+            // box = (4 * pwc, 4, kChunkQuads) -- every placement of that cutout in that class shares it
+            std::map<std::pair<int, int>, int> class_map;
             for (const PendingMap &pm : pending) {
                 const int i = pm.placement;
                 const PrepDesc &pd = hprep[(size_t)pm.prep];
-                CUtensorMap tm;
-                const cuuint64_t gdim[3] = {(cuuint64_t)pd.w4p, 4, (cuuint64_t)pd.sh};
-                const cuuint64_t gstride[2] = {(cuuint64_t)pd.w4p * 4, (cuuint64_t)pd.w4p * 16};
-                const cuuint32_t box[3] = {(cuuint32_t)hp[i].pbw / 4, 4, (cuuint32_t)hp[i].nrbox};
-                const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, pd.dst, gdim, gstride, box, estride,
-                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (r != CUDA_SUCCESS)
-                    return fail(B200COMP_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for placement " + std::to_string(i));
-                map_of[i] = (int)hmaps.size();
+                auto it = class_map.find(std::make_pair(pm.prep, hp[i].pwc));
+                if (it == class_map.end()) {
+                    CUtensorMap tm;
+                    const cuuint64_t gdim[3] = {(cuuint64_t)pd.w4 * 4, 4, (cuuint64_t)((pd.sh + 3) / 4)};
+                    const cuuint64_t gstride[2] = {(cuuint64_t)pd.w4 * 16, (cuuint64_t)pd.w4 * 64};
+                    const cuuint32_t box[3] = {(cuuint32_t)hp[i].pwc * 4, 4, (cuuint32_t)kChunkQuads};
+                    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, pd.dst, gdim, gstride, box, estride,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    if (r != CUDA_SUCCESS)
+                        return fail(B200COMP_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for placement " + std::to_string(i));
+                    it = class_map.emplace(std::make_pair(pm.prep, hp[i].pwc), (int)hmaps.size()).first;
+                    hmaps.push_back(tm);
+                }
+                map_of[i] = it->second;
                 prep_of[i] = pm.prep;
-                hmaps.push_back(tm);
             }
             CUDA_TRY(dev_alloc((void **)&plan->d_prep, hprep.size() * sizeof(PrepDesc)));
             CUDA_TRY(dev_alloc((void **)&plan->d_flags, (size_t)flag_words * 4));
@@ -1080,8 +1094,8 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             plan->n_prep = (int)hprep.size();
             plan->prep_blocks_x = (int)std::max<int64_t>(1, std::min<int64_t>((max_words + 255) / 256, 64));
         }
-        // 2-D maps: u32 pixels x rows.  Overlays composited as they are: one 68x32-pixel box per tile step.
-        // Canvases: 32x32-pixel boxes with the 128-byte swizzle (tile_kernel.cuh ct_off).  Buffers TMA cannot
+        // 2-D maps: u32 pixels x rows.  Overlays composited as they are: 68 x 16-pixel boxes (one chunk each).
+        // Canvases: 32-pixel x kTileH-row boxes with the 128-byte swizzle (tile_kernel.cuh ct_off).  Buffers TMA cannot
         // address (base not 16-byte aligned, pitch not a multiple of 16) keep a null map: generic loads/stores.
         auto encode_2d = [&](const void *base, int64_t pitch, int w, int h, int bw, int bh, bool swizzle, CUtensorMap *tm) -> bool {
             if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (pitch & 15) != 0 || pitch <= 0) return false;
@@ -1101,7 +1115,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
                 if (it == overlay_map.end()) {
                     CUtensorMap tm;
                     int idx = -1;
-                    if (encode_2d(hp[i].src, hp[i].src_pitch, hp[i].sw, hp[i].sh, kOverlayBoxW, kTileH, false, &tm)) {
+                    if (encode_2d(hp[i].src, hp[i].src_pitch, hp[i].sw, hp[i].sh, kOverlayBoxW, kIdentRows, false, &tm)) {
                         idx = (int)hmaps.size();
                         hmaps.push_back(tm);
                     }
@@ -1132,7 +1146,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             if (pi >= 0) {
                 const PrepDesc &pd = hprep[(size_t)pi];
                 hp[i].flags = pd.flags;
-                hp[i].wq = pd.w4p / 4;
+                hp[i].wq = pd.wq;
                 hp[i].sh4 = (pd.sh + 3) / 4;
             }
         }
@@ -1144,9 +1158,12 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     // command streams: records + ring read-ahead slack; per-tile counts; stream offsets
     {
         const int64_t K = (tiles + plan->G - 1) / plan->G;
-        CUDA_TRY(dev_alloc((void **)&plan->d_streams, (size_t)(plan->stream_capacity + kRing) * sizeof(Cmd)));
+        CUDA_TRY(dev_alloc((void **)&plan->d_streams, (size_t)(plan->stream_capacity + kCmdBlk) * sizeof(Cmd)));
         CUDA_TRY(dev_alloc((void **)&plan->d_bin, (size_t)plan->G * (size_t)std::max<int64_t>(1, K) * sizeof(int32_t)));
         CUDA_TRY(dev_alloc((void **)&plan->d_stream_off, (size_t)(plan->G + 1) * sizeof(int64_t)));
+        CUDA_TRY(dev_alloc((void **)&plan->d_stream_len, (size_t)plan->G * sizeof(int64_t)));
+        CUDA_TRY(dev_alloc((void **)&plan->d_dbg, 16 * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemsetAsync(plan->d_dbg, 0, 16 * sizeof(uint32_t), st));
         int max_count = 1;
         for (int c = 0; c < n_canvases; ++c) max_count = std::max(max_count, canvases[c].n_placements);
         plan->mask_chunks = (max_count + 31) / 32;
@@ -1177,10 +1194,11 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     CUDA_TRY(cudaMemsetAsync(plan->d_status, 0, sizeof(int), st));
     CUDA_TRY(cudaStreamSynchronize(st));  // host staging vectors die with this scope
 
-    plan->patch_words = max_patch;
-    plan->inter_words = max_inter;
-    plan->smem_bytes = tile_smem_bytes(max_patch, max_inter);
-    CUDA_TRY(cudaFuncSetAttribute(composite_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemBytes));
+    plan->slot_words = (max_slot + 31) & ~31;  // slots stay 128-byte aligned
+    plan->iw_words = max_iw;
+    plan->smem_bytes = tile_smem_bytes(plan->slot_words, plan->iw_words);
+    if (plan->smem_bytes > kMaxSmemBytes) return fail(B200COMP_EINTERNAL, "plan_create: tile kernel shared memory over the limit");
+    CUDA_TRY(cudaFuncSetAttribute(composite_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemBytes));
 
     plan->info[B200COMP_INFO_ALGORITHMIC_BYTES] = algo;
     plan->info[B200COMP_INFO_LAUNCHES_PER_RUN] = 4 + (plan->n_prep > 0 ? 1 : 0);  // 3 binning kernels + tile kernel
@@ -1269,10 +1287,10 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
         const int nc = std::min(65535, first + count - c0);
         bin_count_kernel<<<dim3(gx, (unsigned)nc), kBinWarps * 32, 0, st>>>(
             plan->d_canvases + c0, plan->d_placements, plan->d_boxes, tile0, G, K, plan->d_bin, plan->d_masks,
-            plan->mask_chunks, plan->patch_words, plan->inter_words, c0 == first ? cursor : nullptr, plan->d_status, cull);
+            plan->mask_chunks, plan->iw_words, c0 == first ? cursor : nullptr, plan->d_status, cull);
     }
     if (int rc = checkpoint("bin_count_kernel")) return rc;
-    bin_scan_kernel<<<(unsigned)((G + 7) / 8), 256, 0, st>>>(plan->d_bin, G, K, n_tiles, plan->d_stream_off, cursor,
+    bin_scan_kernel<<<(unsigned)((G + 7) / 8), 256, 0, st>>>(plan->d_bin, G, K, n_tiles, plan->d_stream_off, plan->d_stream_len, cursor,
                                                              plan->d_streams, plan->stream_capacity, plan->d_status);
     if (int rc = checkpoint("bin_scan_kernel")) return rc;
     for (int c0 = first; c0 < first + count; c0 += 65535) {
@@ -1284,15 +1302,15 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
     }
     if (int rc = checkpoint("bin_fill_kernel")) return rc;
     if (pe[1]) CUDA_TRY(cudaEventRecord(pe[1], st));
-    composite_stream_kernel<<<(unsigned)G, kThreads, plan->smem_bytes, st>>>(
-        plan->d_streams, plan->d_stream_off, plan->d_canvases, plan->d_maps,
-        reinterpret_cast<const uint32_t *>(plan->d_tables), plan->patch_words, plan->inter_words);
+    composite_slab_kernel<<<(unsigned)G, kThreads, plan->smem_bytes, st>>>(
+        plan->d_streams, plan->d_stream_off, plan->d_stream_len, plan->d_canvases, plan->d_maps,
+        reinterpret_cast<const uint32_t *>(plan->d_tables), plan->slot_words, plan->iw_words, plan->d_status, plan->d_dbg);
     CUDA_TRY(cudaGetLastError());
     if (pe[2]) {
         CUDA_TRY(cudaEventRecord(pe[2], st));
         ++plan->prof_runs;
     }
-    if (int rc = checkpoint("composite_stream_kernel")) return rc;
+    if (int rc = checkpoint("composite_slab_kernel")) return rc;
     return 0;
 }
 
@@ -1349,7 +1367,7 @@ int64_t b200comp_debug_compare_tables_(const int *in_sizes, const int *out_sizes
 
 // internal (tools/): phase cycle counters of a -DB200COMP_PROFILE=1 build; reset after reading
 int b200comp_debug_profile_(unsigned long long *out16) {
-#if B200COMP_PROFILE
+#if defined(B200COMP_PROFILE) && B200COMP_PROFILE
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out16, g_prof, sizeof(unsigned long long) * 16);
     unsigned long long z[16] = {0};
@@ -1404,6 +1422,14 @@ int b200comp_plan_check(b200comp_plan *plan, void *stream) {
     int h = 0;
     CUDA_TRY(cudaMemcpyAsync(&h, plan->d_status, sizeof h, cudaMemcpyDeviceToHost, S(stream)));
     CUDA_TRY(cudaStreamSynchronize(S(stream)));
+    if (h & kStatusWatchdog) {
+        uint32_t d[16] = {0};
+        cudaMemcpy(d, plan->d_dbg, sizeof d, cudaMemcpyDeviceToHost);
+        char msg[200];
+        std::snprintf(msg, sizeof msg, "tile kernel watchdog: wait tag 0x%x parity %u aux %u in CTA %u thread %u never came true",
+                      d[0], d[3], d[4], d[1], d[2]);
+        return fail(B200COMP_EINTERNAL, msg);
+    }
     if (h != 0) return fail(B200COMP_EINTERNAL, "binning reported a sizing violation (status " + std::to_string(h) + ")");
     return 0;
 }

@@ -25,42 +25,58 @@ struct DevCanvas {
 static_assert(sizeof(DevCanvas) == 88, "DevCanvas layout");
 
 constexpr int kTileW = 64;
-constexpr int kTileH = 32;
-#ifndef B200COMP_THREADS
-#define B200COMP_THREADS 384
+#ifndef B200COMP_TILE_H
+#define B200COMP_TILE_H 32
 #endif
+constexpr int kTileH = B200COMP_TILE_H;  // 32 or 64 (the vertical pass walks row groups of 32)
+static_assert(kTileH == 32 || kTileH == 64, "tile height");
 #ifndef B200COMP_CTAS_PER_SM
 #define B200COMP_CTAS_PER_SM 2
 #endif
-constexpr int kThreads = B200COMP_THREADS;  // warps per CTA x 32
 constexpr int kCtasPerSm = B200COMP_CTAS_PER_SM;  // persistent CTAs resident per SM (registers and shared memory permitting)
-constexpr int kWarps = kThreads / 32;
-// The last warp is the producer: its lane 0 issues every asynchronous copy (command ring, TMA loads and stores)
-// and does no pass work, so that bookkeeping never delays the compute warps at a barrier.
-constexpr int kComputeWarps = kWarps - 1;
-constexpr int kComputeThreads = kComputeWarps * 32;
-constexpr int kProducerTid = kComputeThreads;
-constexpr int kRowSweep = kComputeThreads / kTileW;  // tile rows covered per sweep of the element-wise loops
-constexpr int kElemThreads = kRowSweep * kTileW;     // threads taking part in them (whole rows only)
+// The tile kernel gives every compute warp a SLAB of the resident tile: kSlabW columns, all rows.  A warp runs the
+// horizontal pass, the vertical pass and the over of its slab on its own -- its intermediate is private -- so
+// the passes need no CTA-wide barrier.  Two more warps only move data: lane 0 of the producer warp issues every
+// asynchronous load (command blocks, background tiles, source patch chunks), lane 0 of the store warp writes
+// finished tiles back.
+constexpr int kSlabW = 8;
+constexpr int kSlabWarps = kTileW / kSlabW;
+constexpr int kProducerWarp = kSlabWarps;
+constexpr int kStoreWarp = kSlabWarps + 1;
+constexpr int kThreads = (kSlabWarps + 2) * 32;
 constexpr int kPrecisionBits = 22;
-constexpr int kTileWords = kTileW * kTileH;  // one resident canvas tile: two 32x32-pixel halves, 128-byte swizzled
-constexpr int kOverlayBoxW = kTileW + 4;       // identity overlays: box widened so its start can be 16-byte aligned
-constexpr int kTileBufs = 4;                 // canvas tiles in flight per CTA (background prefetch / compute / store)
+constexpr int kTileWords = kTileW * kTileH;  // one resident canvas tile: two halves of 32 pixels x kTileH rows, 128-byte swizzled
+constexpr int kOverlayBoxW = kTileW + 4;     // identity overlays: box widened so its start can be 16-byte aligned
+constexpr int kIdentRows = 16;               // overlay rows per chunk (one ring slot)
+#ifndef B200COMP_TILE_BUFS
+#define B200COMP_TILE_BUFS 4
+#endif
+constexpr int kTileBufs = B200COMP_TILE_BUFS;  // canvas tiles in flight per CTA (background prefetch / compute / store)
+// Source patches stream through a ring of chunks: kChunkQuads row quads (4 rows each) x 4 channel planes x the
+// placement's patch width.  A chunk is one TMA box; every compute warp consumes every chunk.
+constexpr int kChunkQuads = 4;
+#ifndef B200COMP_PRING
+#define B200COMP_PRING 4
+#endif
+constexpr int kPRing = B200COMP_PRING;
+constexpr int kCmdBlk = 8;   // command records per block (one bulk copy)
+constexpr int kCmdRing = 4;  // command blocks in shared memory
 
-enum : int { kStatusPatchOverflow = 1, kStatusInterOverflow = 2, kStatusStreamOverflow = 4 };
+enum : int { kStatusPatchOverflow = 1, kStatusInterOverflow = 2, kStatusStreamOverflow = 4, kStatusWatchdog = 8 };
 
 // ------------------------------------------------------------------ command streams
 // The tile kernel is persistent: CTA c of G walks the canvas tiles t = c, c + G, c + 2G, ... of a run.
 // A binning pass turns (canvases, placements) into one command stream per CTA, so the tile kernel never
-// chases pointers: it prefetches fixed-size records from a linear array.  A record is 16 words:
+// chases pointers: it streams fixed-size records from a linear array.  A record is 16 words:
 //   TILE      w0 kind, w1 n_steps, w2 tx0, w3 ty0, w4 tw | th << 16, w5 solid, w6 flags, w7 canvas index,
 //             w8-9 bg tensor map, w10-11 out tensor map
 //   RESAMPLE  w0 kind, w1 nwx | nwy << 8 | nch << 16 | NRQ << 24, w2 dx | dy << 8 | two << 16 | tho << 24,
-//             w3 ox0, w4 oy0, w5 cw0 | rw0 << 16, w6 w (coefficient plane stride x), w7 h,
-//             w8 tensor map index, w9 plx word offset, w10 ply word offset, w11 pbw | nrbox << 16,
+//             w3 ox0, w4 oy0, w5 cw0 | rw0 << 16 (first patch word column / first source row quad),
+//             w6 w (coefficient plane stride x), w7 h, w8 tensor map index, w9 plx word offset,
+//             w10 ply word offset, w11 pwc (patch width class: word columns per chunk row),
 //             w12-13 scale_x, w14-15 scale_y
-//   IDENT_TMA w0 kind, w2 as above, w3 / w4 source coordinates of the box (w3 a multiple of 4: TMA boxes
-//             start on 16-byte boundaries), w5 pixels from the box start to the tile origin, w8 map index
+//   IDENT_TMA w0 kind, w2 as above, w3 / w4 source coordinates of the tile origin's box (w3 a multiple of 4: TMA
+//             boxes start on 16-byte boundaries), w5 pixels from the box start to the tile origin, w8 map index
 //   IDENT_LDG w0 kind, w2 as above, w3 / w4 source coordinates of the intersection, w6 pitch, w12-13 src
 struct __align__(16) Cmd {
     uint32_t w[16];
@@ -68,9 +84,6 @@ struct __align__(16) Cmd {
 static_assert(sizeof(Cmd) == 64, "Cmd layout");
 enum : uint32_t { kCmdTile = 0, kCmdResample = 1, kCmdIdentTma = 2, kCmdIdentLdg = 3, kCmdNop = 4, kCmdEnd = 5 };
 enum : uint32_t { kTileBgTma = 1, kTileOutTma = 2, kTileHasBg = 4, kTileNoBg = 8 };
-constexpr int kRing = 8;       // command ring slots in shared memory
-constexpr int kRingAhead = 6;  // records fetched ahead of the consumer
-constexpr int kLook = 3;       // records the producer may run ahead of the consumer
 
 // ------------------------------------------------------------------ pixel arithmetic
 // ImagingUtils.h MULDIV255
