@@ -338,7 +338,7 @@ static int resample_two_pass(const uint8_t *src, int sw, int sh, int64_t sp, uin
 // ---- coefficient tables of one plan / call ------------------------------------------------
 // Two device formats share one int32 buffer:
 //   legacy : k[out][ks] int32 + bounds[out][2]              (generic one-axis kernels)
-//   packed : planes[3*nw][out] (byte planes, SoA)            (fused tile kernel, dp4a)
+//   packed : rows[out][coef_row_words(nw)] (byte planes)      (fused tile kernel, dp4a; see kernels.cuh)
 struct TableRef {
     int64_t k_off = 0;  // legacy: k      | packed: w0
     int64_t b_off = 0;  // legacy: bounds | packed: planes
@@ -381,7 +381,7 @@ struct TableSet {
             r.ks = key.kind == 2 ? 3 : packed_words(lanczos_ksize(key.in_size, key.out_size));
             r.k_off = total;
             r.b_off = total;
-            total += (int64_t)3 * r.ks * n;
+            total += (int64_t)coef_row_words(r.ks) * n;
         }
         total = (total + 3) & ~(int64_t)3;  // keep every table 16-byte aligned
         order.push_back(key);
@@ -400,9 +400,10 @@ struct TableSet {
             for (int t = 0; t < n; ++t) {
                 const int pos = (lo & 3) + t, word = pos >> 2, sh = 8 * (pos & 3);
                 const int32_t kv = k[(size_t)j * ks + t];
-                pl[(size_t)(0 * nw + word) * n_out + j] |= (uint32_t)(kv & 0xff) << sh;
-                pl[(size_t)(1 * nw + word) * n_out + j] |= (uint32_t)((kv >> 8) & 0xff) << sh;
-                pl[(size_t)(2 * nw + word) * n_out + j] |= (uint32_t)((kv >> 16) & 0xff) << sh;  // signed top byte
+                uint32_t *row = pl + (size_t)j * coef_row_words(nw);
+                row[0 * nw + word] |= (uint32_t)(kv & 0xff) << sh;
+                row[1 * nw + word] |= (uint32_t)((kv >> 8) & 0xff) << sh;
+                row[2 * nw + word] |= (uint32_t)((kv >> 16) & 0xff) << sh;  // signed top byte
             }
         }
     }
@@ -528,7 +529,7 @@ static int build_packed_on_device(const TableSet &ts, int32_t *d_tables, cudaStr
             for (int p = 0; p < 3; ++p)
                 for (int i = 0; i < job.nw; ++i) {
                     WordPatch wp;
-                    wp.off = job.planes_off + (int64_t)(p * job.nw + i) * job.out_size + f.j;
+                    wp.off = job.planes_off + (int64_t)f.j * coef_row_words(job.nw) + p * job.nw + i;
                     wp.value = pl[p][i];
                     wp.pad_ = 0;
                     patches.push_back(wp);
@@ -1359,15 +1360,17 @@ int64_t b200comp_debug_compare_tables_(const int *in_sizes, const int *out_sizes
     int64_t bad = 0;
     for (const TableSet::Key &key : ts.order) {
         const TableRef &ref = ts.refs.at(key);
-        const int64_t words = (int64_t)3 * ref.ks * key.out_size;
-        for (int64_t w = 0; w < words; ++w) bad += got[(size_t)(ref.b_off + w)] != ts.host[(size_t)(ref.b_off + w)];
+        const int rw = coef_row_words(ref.ks);
+        for (int64_t j = 0; j < key.out_size; ++j)
+            for (int w = 0; w < 3 * ref.ks; ++w)  // the padding words of a row are never used
+                bad += got[(size_t)(ref.b_off + j * rw + w)] != ts.host[(size_t)(ref.b_off + j * rw + w)];
     }
     return bad;
 }
 
 // internal (tools/): phase cycle counters of a -DB200COMP_PROFILE=1 build; reset after reading
 int b200comp_debug_profile_(unsigned long long *out16) {
-#if defined(B200COMP_PROFILE) && B200COMP_PROFILE
+#if B200COMP_PROFILE
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out16, g_prof, sizeof(unsigned long long) * 16);
     unsigned long long z[16] = {0};

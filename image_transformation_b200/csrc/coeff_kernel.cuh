@@ -17,7 +17,7 @@
 namespace b200comp {
 
 struct CoefJob {
-    int64_t planes_off;  // word offset of planes[3*nw][out] in the table buffer
+    int64_t planes_off;  // word offset of rows[out][coef_row_words(nw)] in the table buffer
     int32_t in_size, out_size;
     int32_t nw;          // words per output sample
     int32_t identity;    // skipped pass: one tap of 1.0 at the sample itself
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(128) build_packed_tables_kernel(const CoefJob 
         for (int p = 0; p < 3; ++p)
 #pragma unroll
             for (int i = 0; i < 5; ++i)
-                if (i < nw) planes[(int64_t)(p * nw + i) * n_out + j] = pl[p][i];
+                if (i < nw) planes[(int64_t)j * coef_row_words(nw) + p * nw + i] = pl[p][i];
         if (uncertain) {
             const int idx = atomicAdd(fix_count, 1);
             if (idx < fix_cap) {

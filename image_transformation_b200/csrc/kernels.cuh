@@ -62,6 +62,11 @@ constexpr int kPRing = B200COMP_PRING;
 constexpr int kCmdBlk = 8;   // command records per block (one bulk copy)
 constexpr int kCmdRing = 4;  // command blocks in shared memory
 
+// Packed coefficient tables (fused tile kernel): one row per output sample, holding its 3 * nw byte-plane words
+// [plane 0 (low byte) words 0..nw-1 | plane 1 | plane 2 (signed top byte)] padded to a multiple of four words, so a
+// lane fetches its whole row with three or four 128-bit loads.
+__host__ __device__ constexpr int coef_row_words(int nw) { return nw == 5 ? 16 : 12; }
+
 enum : int { kStatusPatchOverflow = 1, kStatusInterOverflow = 2, kStatusStreamOverflow = 4, kStatusWatchdog = 8 };
 
 // ------------------------------------------------------------------ command streams
@@ -148,6 +153,18 @@ __device__ __forceinline__ uint32_t over_px(uint32_t d, uint32_t s) {
     const uint32_t b = shiftfordiv255(((s >> 16) & 0xffu) * coef1 + ((d >> 16) & 0xffu) * coef2 + (0x80u << 7)) >> 7;
     return r | (g << 8) | (b << 16) | (outa << 24);
 }
+
+// partially transparent resampled pixel onto the canvas pixel: un-premultiply, then over.  Out of line: it is the
+// rare path of the vertical pass (soft cutout edges) and long (divisions for a non-opaque destination).
+#ifndef B200COMP_OVER_INLINE
+#define B200COMP_OVER_INLINE 1  // out of line measured 20 % slower (the call makes the compiler spill live state around it)
+#endif
+#if B200COMP_OVER_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+uint32_t over_unpremul_px(uint32_t d, uint32_t s) { return over_px(d, unpremultiply_px(s)); }
 
 // Resample.c clip8: arithmetic shift then clamp
 __device__ __forceinline__ uint32_t clip8(int32_t v) { return (uint32_t)min(255, max(0, v >> kPrecisionBits)); }

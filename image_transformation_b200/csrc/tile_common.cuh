@@ -85,6 +85,39 @@ __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
     return ok != 0u;
 }
 
+// try_wait with a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the time is up,
+// instead of burning issue slots in a polling loop
+__device__ __forceinline__ bool mbar_try_sleep(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0u;
+}
+
+// One output sample's coefficient row (kernels.cuh coef_row_words): three or four 128-bit loads.
+template <int NW>
+__device__ __forceinline__ void load_coef_row(const uint32_t *__restrict__ table, int j, uint32_t (&k0)[NW], uint32_t (&k1)[NW],
+                                              uint32_t (&k2)[NW]) {
+    constexpr int S = coef_row_words(NW);
+    const uint4 *row = reinterpret_cast<const uint4 *>(table + (int64_t)j * S);
+    uint32_t w[S];
+#pragma unroll
+    for (int v = 0; v < S / 4; ++v) {
+        const uint4 t = __ldg(row + v);
+        w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        k0[i] = w[i];
+        k1[i] = w[NW + i];
+        k2[i] = w[2 * NW + i];
+    }
+}
+
 // (4*words x 4 channel planes x row quads) box of the prepared cutout -> shared memory; completion on `bar`
 __device__ __forceinline__ void tma_load_3d(void *smem_dst, const void *tmap, int c0, int c1, int c2, uint64_t *bar) {
     asm volatile(
@@ -110,6 +143,28 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Hardware named barriers (ids 1..15; 0 is __syncthreads): arrive does not block, sync parks the warp in the barrier
+// unit -- no polling, no issue slots -- until `threads` threads (whole warps) have arrived or synced.
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// shared-memory accesses by 32-bit shared-space byte address (no generic-address arithmetic in the hot loops)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 __device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }

@@ -18,8 +18,8 @@ out = (ctypes.c_ulonglong * 16)()
 lib.b200comp_debug_profile_(out)
 b.run(); b.check()
 assert lib.b200comp_debug_profile_(out) == 0, "not a profiling build"
-names = ["step tail + loop top", "barrier A", "dispatch+decode+producer", "patch wait", "H pass", "barrier B", "V pass", "tile begin", "empty tile", "NOP record"]
+names = ["command block wait", "tile wait (background)", "tile fill (solid / plain loads)", "step decode + coefficient rows", "patch chunk wait", "H pass", "V pass + over", "identity / chunks passed on", "tile end", "loop overhead"]
 tot = sum(out[i] for i in range(10))
 for i in range(10):
-    print(f"{names[i]:28s} {out[i] / tot * 100:6.2f} %   {out[i] / 296 / 1e3:9.1f} kcycles per CTA")
-print("total kcycles per CTA", tot / 296 / 1e3)
+    print(f"{names[i]:28s} {out[i] / tot * 100:6.2f} %   {out[i] / 296 / 8 / 1e3:9.1f} kcycles per warp")
+print("total kcycles per compute warp", tot / 296 / 8 / 1e3)
