@@ -338,7 +338,7 @@ static int resample_two_pass(const uint8_t *src, int sw, int sh, int64_t sp, uin
 // ---- coefficient tables of one plan / call ------------------------------------------------
 // Two device formats share one int32 buffer:
 //   legacy : k[out][ks] int32 + bounds[out][2]              (generic one-axis kernels)
-//   packed : rows[out][coef_row_words(nw)] (byte planes)      (fused tile kernel, dp4a; see kernels.cuh)
+//   packed : planes[3*nw][out] (byte planes, SoA)            (fused tile kernel, dp4a)
 struct TableRef {
     int64_t k_off = 0;  // legacy: k      | packed: w0
     int64_t b_off = 0;  // legacy: bounds | packed: planes
@@ -1362,7 +1362,7 @@ int64_t b200comp_debug_compare_tables_(const int *in_sizes, const int *out_sizes
         const TableRef &ref = ts.refs.at(key);
         const int rw = coef_row_words(ref.ks);
         for (int64_t j = 0; j < key.out_size; ++j)
-            for (int w = 0; w < 3 * ref.ks; ++w)  // the padding words of a row are never used
+            for (int w = 0; w < 3 * ref.ks; ++w)
                 bad += got[(size_t)(ref.b_off + j * rw + w)] != ts.host[(size_t)(ref.b_off + j * rw + w)];
     }
     return bad;
@@ -1370,7 +1370,7 @@ int64_t b200comp_debug_compare_tables_(const int *in_sizes, const int *out_sizes
 
 // internal (tools/): phase cycle counters of a -DB200COMP_PROFILE=1 build; reset after reading
 int b200comp_debug_profile_(unsigned long long *out16) {
-#if B200COMP_PROFILE
+#if defined(B200COMP_PROFILE) && B200COMP_PROFILE
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out16, g_prof, sizeof(unsigned long long) * 16);
     unsigned long long z[16] = {0};

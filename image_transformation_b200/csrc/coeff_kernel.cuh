@@ -17,7 +17,7 @@
 namespace b200comp {
 
 struct CoefJob {
-    int64_t planes_off;  // word offset of rows[out][coef_row_words(nw)] in the table buffer
+    int64_t planes_off;  // word offset of planes[3*nw][out] in the table buffer
     int32_t in_size, out_size;
     int32_t nw;          // words per output sample
     int32_t identity;    // skipped pass: one tap of 1.0 at the sample itself

@@ -26,9 +26,11 @@ static_assert(sizeof(DevCanvas) == 88, "DevCanvas layout");
 
 constexpr int kTileW = 64;
 #ifndef B200COMP_TILE_H
-#define B200COMP_TILE_H 32
+#define B200COMP_TILE_H 64
 #endif
-constexpr int kTileH = B200COMP_TILE_H;  // 32 or 64 (the vertical pass walks row groups of 32)
+constexpr int kTileH = B200COMP_TILE_H;  // 32 or 64 (the vertical pass walks row groups of 32).  64: half as many tile steps, so the
+                                         // per-step work of a warp (decode, coefficient rows, waits) is amortised over twice the pixels,
+                                         // and 9 % fewer H-pass rows (window halo); measured 4.6 % faster than 32 (profiles/r2_tile_kernel_ab.txt)
 static_assert(kTileH == 32 || kTileH == 64, "tile height");
 #ifndef B200COMP_CTAS_PER_SM
 #define B200COMP_CTAS_PER_SM 2
@@ -49,22 +51,19 @@ constexpr int kTileWords = kTileW * kTileH;  // one resident canvas tile: two ha
 constexpr int kOverlayBoxW = kTileW + 4;     // identity overlays: box widened so its start can be 16-byte aligned
 constexpr int kIdentRows = 16;               // overlay rows per chunk (one ring slot)
 #ifndef B200COMP_TILE_BUFS
-#define B200COMP_TILE_BUFS 4
+#define B200COMP_TILE_BUFS 2
 #endif
-constexpr int kTileBufs = B200COMP_TILE_BUFS;  // canvas tiles in flight per CTA (background prefetch / compute / store)
+constexpr int kTileBufs = B200COMP_TILE_BUFS;  // resident canvas tiles per CTA: one being composited, one being stored and then pre-loaded
 // Source patches stream through a ring of chunks: kChunkQuads row quads (4 rows each) x 4 channel planes x the
 // placement's patch width.  A chunk is one TMA box; every compute warp consumes every chunk.
 constexpr int kChunkQuads = 4;
 #ifndef B200COMP_PRING
-#define B200COMP_PRING 4
+#define B200COMP_PRING 3
 #endif
 constexpr int kPRing = B200COMP_PRING;
 constexpr int kCmdBlk = 8;   // command records per block (one bulk copy)
 constexpr int kCmdRing = 4;  // command blocks in shared memory
 
-// Packed coefficient tables (fused tile kernel): one row per output sample, holding its 3 * nw byte-plane words
-// [plane 0 (low byte) words 0..nw-1 | plane 1 | plane 2 (signed top byte)] padded to a multiple of four words, so a
-// lane fetches its whole row with three or four 128-bit loads.
 __host__ __device__ constexpr int coef_row_words(int nw) { return nw == 5 ? 16 : 12; }
 
 enum : int { kStatusPatchOverflow = 1, kStatusInterOverflow = 2, kStatusStreamOverflow = 4, kStatusWatchdog = 8 };
@@ -154,17 +153,7 @@ __device__ __forceinline__ uint32_t over_px(uint32_t d, uint32_t s) {
     return r | (g << 8) | (b << 16) | (outa << 24);
 }
 
-// partially transparent resampled pixel onto the canvas pixel: un-premultiply, then over.  Out of line: it is the
-// rare path of the vertical pass (soft cutout edges) and long (divisions for a non-opaque destination).
-#ifndef B200COMP_OVER_INLINE
-#define B200COMP_OVER_INLINE 1  // out of line measured 20 % slower (the call makes the compiler spill live state around it)
-#endif
-#if B200COMP_OVER_INLINE
-__device__ __forceinline__
-#else
-__device__ __noinline__
-#endif
-uint32_t over_unpremul_px(uint32_t d, uint32_t s) { return over_px(d, unpremultiply_px(s)); }
+__device__ __forceinline__ uint32_t over_unpremul_px(uint32_t d, uint32_t s) { return over_px(d, unpremultiply_px(s)); }
 
 // Resample.c clip8: arithmetic shift then clamp
 __device__ __forceinline__ uint32_t clip8(int32_t v) { return (uint32_t)min(255, max(0, v >> kPrecisionBits)); }

@@ -85,20 +85,6 @@ __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
     return ok != 0u;
 }
 
-// try_wait with a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the time is up,
-// instead of burning issue slots in a polling loop
-__device__ __forceinline__ bool mbar_try_sleep(uint64_t *bar, uint32_t parity, uint32_t ns) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
-    return ok != 0u;
-}
-
-// One output sample's coefficient row (kernels.cuh coef_row_words): three or four 128-bit loads.
 template <int NW>
 __device__ __forceinline__ void load_coef_row(const uint32_t *__restrict__ table, int j, uint32_t (&k0)[NW], uint32_t (&k1)[NW],
                                               uint32_t (&k2)[NW]) {
@@ -144,16 +130,12 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Hardware named barriers (ids 1..15; 0 is __syncthreads): arrive does not block, sync parks the warp in the barrier
-// unit -- no polling, no issue slots -- until `threads` threads (whole warps) have arrived or synced.
 __device__ __forceinline__ void named_bar_arrive(int id, int threads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
-
-// shared-memory accesses by 32-bit shared-space byte address (no generic-address arithmetic in the hot loops)
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));

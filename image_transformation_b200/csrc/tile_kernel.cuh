@@ -440,53 +440,20 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
     store_cmd(streams + base, w);
 }
 
-// Optional phase timing (-DB200COMP_PROFILE=1): cycles lane 0 of every compute warp spends in each phase, summed
-// over warps and CTAs into g_prof (read with b200comp_debug_profile_; tools/phase_profile.py).
-#ifndef B200COMP_PROFILE
-#define B200COMP_PROFILE 0
-#endif
-#ifndef B200COMP_HSKIP
-#define B200COMP_HSKIP 1  // H pass: skip the arithmetic of items whose source words are all zero (whole-warp vote)
-#endif
-#if B200COMP_PROFILE
-__device__ unsigned long long g_prof[16];
-#define PROF_DECL unsigned long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t = clock64()
-#define PROF_MARK(slot)                                             \
-    do {                                                            \
-        const long long now__ = clock64();                          \
-        prof_acc[slot] += (unsigned long long)(now__ - prof_t);     \
-        prof_t = now__;                                             \
-    } while (0)
-#define PROF_PARAMS , unsigned long long (&prof_acc)[12], long long &prof_t
-#define PROF_ARGS , prof_acc, prof_t
-#define PROF_FLUSH()                                                                        \
-    do {                                                                                    \
-        if ((threadIdx.x & 31) == 0)                                                        \
-            for (int i__ = 0; i__ < 12; ++i__) atomicAdd(&g_prof[i__], prof_acc[i__]);      \
-    } while (0)
-#else
-#define PROF_DECL do { } while (0)
-#define PROF_PARAMS
-#define PROF_ARGS
-#define PROF_MARK(slot) do { } while (0)
-#define PROF_FLUSH() do { } while (0)
-#endif
-enum { kProfCmd = 0, kProfTileWait, kProfFill, kProfDecode, kProfPatchWait, kProfH, kProfV, kProfIdent, kProfTileEnd, kProfPass };
-
 // ---- the persistent tile kernel ------------------------------------------------------------------
 // Shared-memory rendezvous points of one CTA.  Every ring uses the n-th use of a slot <-> phase parity
 // (n / ring size) & 1 convention; a producer re-fills a slot only after the matching `empty` / `free` phase.
 struct SlabBars {
-    uint64_t p_full[kPRing];                                             // patch chunks (release: named barriers 1..kPRing)
+    uint64_t p_full[kPRing], p_empty[kPRing];                            // patch chunks
     uint64_t t_ready[kTileBufs], t_done[kTileBufs], t_free[kTileBufs];  // resident tiles
     uint64_t c_full[kCmdRing], c_empty[kCmdRing];                        // command blocks
 };
 
-// A wait that does not come true within seconds is a protocol bug: record who waited for what in the plan's debug
+// A wait that does not come true within ~1.5 s is a protocol bug: record who waited for what in the plan's debug
 // words, raise kStatusWatchdog (every other wait then gives up as well) and leave the kernel, so a test run
 // reports the fault instead of hanging the GPU.
-constexpr int kProducerSleepNs = 100;  // producer thread back-off between polls
-constexpr int kStoreSleepNs = 2000;    // store thread: nobody waits for it at this granularity
+constexpr int kProducerSleepNs = 100;
+constexpr int kStoreSleepNs = 2000;
 struct Watch {
     int *status;
     uint32_t *dbg;
@@ -501,9 +468,6 @@ __device__ __noinline__ void watchdog_fire(const Watch &w, uint32_t tag, uint32_
         __threadfence();
     }
 }
-// SLEEP_NS == 0: compute warps -- they have nothing else to do, poll back to back (try_wait suspends for a short
-// hardware-defined time).  SLEEP_NS > 0: the producer and store threads wait almost all the time; they back off with
-// nanosleep so that their polling does not take issue slots from the compute warps of their SM sub-partition.
 template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, const Watch &w, uint32_t tag, uint32_t aux) {
     if (mbar_try(bar, parity)) return;
@@ -511,7 +475,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, const 
     for (;;) {
         if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
         if (mbar_try(bar, parity)) return;
-        if (++spins < (SLEEP_NS > 0 ? (1u << 22) : (1u << 26))) continue;  // seconds: a protocol bug, not a slow tile
+        if (++spins < (SLEEP_NS > 0 ? (1u << 22) : (1u << 26))) continue;
         if ((*reinterpret_cast<volatile int *>(w.status) & kStatusWatchdog) == 0) watchdog_fire(w, tag, parity, aux);
         asm volatile("exit;");
     }
@@ -521,129 +485,163 @@ enum : uint32_t {
     kTagRoleConsumer = 0x100, kTagRoleProducer = 0x200, kTagRoleStore = 0x300
 };
 
-// ---- the tap engine: both passes of one warp's slab ------------------------------------------------
-// Horizontal pass.  Lane = (column jl = lane & 7 of the slab, item lane q = lane >> 3).  The work items of a patch
-// chunk are its (row quad, channel) pairs, nch per quad; the four lanes of a column take items q, q + 4, ... --
-// with four channels a lane keeps one channel, with three (opaque patch: the alpha plane is 255 after both passes,
-// because |sum(k) - 2^22| <= taps, and is not computed) the twelve items of a full chunk still split evenly.  One
-// item = four source rows of one channel: NW LDS.128, four tap sums, one word of four clipped bytes stored to
-// Iw[jl][rq][c].  The alpha lanes (q == 3 with four channels) also accumulate OR / AND of the alpha words they
-// produce: the vertical pass classifies whole columns from them (nothing to draw / opaque).
-// Vertical pass.  Lane <-> output row (row groups of 32); per slab column NW LDS.128 bring the lane's window of all
-// four channels, four tap sums give the pixel, which is un-premultiplied and composited onto the resident tile.
-// Both passes are "NW 128-bit loads, four independent tap sums" and run through ONE loop: the dp4a block, which is
-// most of the kernel's hot code, exists once per NW, so the warps of a scheduler -- some in their horizontal, some
-// in their vertical pass -- share it in the 6 KB L0 instruction cache (with separate, twice-unrolled loops the
-// kernel was instruction-fetch bound: profiles/r2_icache_notes.txt).  The price: opaque columns compute an alpha sum
-// they do not need.
-struct TapUnit {
-    int mode;                  // 0: the H items of one chunk, 1: the V columns of one row group
-    int n_iter;
-    const uint8_t *src;        // H: the lane's next item; V: the lane's window in the next column
-    const uint8_t *safe;       // H: readable memory for lanes without an item
-    uint32_t sstep, sstep_wrap;  // bytes from one item / column to the next (H with three channels: see advance)
-    uint8_t *dst;              // H: the lane's next word of the intermediate
-    uint32_t dstep;
-    int it, n_items, ch;       // H: item index (q, q + 4, ...), items in the chunk, channel
-    bool four, active;         // H: four channels; the lane's column is on the step
-    uint32_t a_any, a_all;     // H: OR / AND of the words produced so far (alpha lanes)
-    uint32_t *p_lo, *p_hi;     // V: canvas pixel of slab column 0 / 4 in this lane's row (ct_off: two 16-byte chunks)
-    int xx;                    // V: slab column
-    uint32_t m_any, m_all;     // V: bit xx = column xx has something to draw / is opaque
-};
-
-// Alpha tests use the raw accumulator (clip8(acc) == 0 / == 255).  Do NOT test the clamped value: CUDA 12.9 ptxas
-// folds `clamp(x) == 255` into VIMNMX.RELU's predicate output with the wrong sense on sm_100a (partially
-// transparent pixels took the opaque branch).
-template <int NW>
-__device__ __forceinline__ void tap_engine(TapUnit &u, const uint32_t (&kk0)[5], const uint32_t (&kk1)[5],
-                                           const uint32_t (&kk2)[5]) {
+// ---- H pass of one warp's slab --------------------------------------------------------------------
+// Lane = (column jl = lane & 7 of the slab, item lane q = lane >> 3).  The work items of a chunk are its
+// (row quad, channel) pairs, nch per quad; the four lanes of a column take items q, q + 4, ... -- with four
+// channels a lane keeps one channel, with three (opaque patch: the alpha plane is 255 after both passes, because
+// |sum(k) - 2^22| <= taps, and is not computed) the twelve items of a full chunk still split evenly.  One item =
+// four source rows of one channel: NW LDS.128, 12 * NW dp4a, one word of four clipped bytes stored to
+// Iw[jl][rq][c].  An item whose source words are all zero -- transparent pixels: premultiplied colours are zero
+// as well -- stores zero without computing (whole-warp vote, so the pipes see no divergence).
+template <int NW, int NCH>
+__device__ __forceinline__ void slab_hpass(const uint32_t *__restrict__ P, int slot_words, SlabBars *bars, uint32_t &cseq,
+                                           const Watch &watch, uint32_t *__restrict__ Iw, int CS, int NRQ, int pwc,
+                                           int cw0, int j, bool active, double scale, double support,
+                                           const uint32_t *__restrict__ plx, int n_out) {
+    const int lane = threadIdx.x & 31, jl = lane & 7, q = lane >> 3;
+    const int wb4 = ((first_tap(j, scale, support) >> 2) - cw0) * 4;
     uint32_t k0[NW], k1[NW], k2[NW];
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-        k0[i] = kk0[i];
-        k1[i] = kk1[i];
-        k2[i] = kk2[i];
-    }
+    load_coef_row<NW>(plx, j, k0, k1, k2);
+    (void)n_out;
+    uint32_t QSb = 64u * (uint32_t)pwc, PSb = 16u * (uint32_t)pwc;
+    asm volatile("" : "+r"(QSb), "+r"(PSb));
+    const int ch0 = (NCH == 4 || q < 3) ? q : 0, rq0 = (NCH == 4 || q < 3) ? 0 : 1;
+    const uint32_t lane_src = smem_u32(P) + 4u * (uint32_t)wb4;
+    const uint32_t lane_dst = smem_u32(Iw) + 4u * (uint32_t)(jl * CS + ch0);
+    const uint32_t soff0 = active ? (uint32_t)rq0 * QSb + (uint32_t)ch0 * PSb : 0u;
 #pragma unroll 1
-    for (int t = 0; t < u.n_iter; ++t) {
-        bool valid;
-        const uint4 *p;
-        if (u.mode == 0) {
-            valid = u.active && u.it < u.n_items;
-            p = reinterpret_cast<const uint4 *>(valid ? u.src : u.safe);
-        } else {
-            valid = ((u.m_any >> u.xx) & 1u) != 0u;  // warp-uniform
-            p = reinterpret_cast<const uint4 *>(u.src);
-            if (!valid) {  // every source alpha under this column is 0
-                u.src += u.sstep;
-                ++u.xx;
-                continue;
+    for (int q0 = 0; q0 < NRQ; q0 += kChunkQuads, ++cseq) {
+        const int s = (int)(cseq % kPRing);
+        mbar_wait(&bars->p_full[s], (cseq / kPRing) & 1u, watch, kTagRoleConsumer | kTagPatchFull, cseq);
+        const uint32_t slot = lane_src + (uint32_t)(s * slot_words) * 4u;
+        const int n_items = NCH * min(kChunkQuads, NRQ - q0);
+        const int n_iter = (n_items + 3) >> 2;
+        int it = q, ch = ch0;
+        uint32_t src = slot + soff0;
+        uint32_t dst = lane_dst + 16u * (uint32_t)(q0 + rq0);
+#pragma unroll 1
+        for (int t = 0; t < n_iter; ++t) {
+            const bool valid = active && it < n_items;
+            uint4 v[NW];
+#pragma unroll
+            for (int i = 0; i < NW; ++i) v[i] = lds128((valid ? src : slot) + 16u * i);
+            uint32_t o = 0u;
+            {
+                uint32_t wd[NW];
+                int32_t sv[4];
+#pragma unroll
+                for (int i = 0; i < NW; ++i) wd[i] = v[i].x;
+                sv[0] = tap_sum<NW>(wd, k0, k1, k2);
+#pragma unroll
+                for (int i = 0; i < NW; ++i) wd[i] = v[i].y;
+                sv[1] = tap_sum<NW>(wd, k0, k1, k2);
+#pragma unroll
+                for (int i = 0; i < NW; ++i) wd[i] = v[i].z;
+                sv[2] = tap_sum<NW>(wd, k0, k1, k2);
+#pragma unroll
+                for (int i = 0; i < NW; ++i) wd[i] = v[i].w;
+                sv[3] = tap_sum<NW>(wd, k0, k1, k2);
+                o = pack2_clip(sv[0], sv[1], pack2_clip(sv[2], sv[3], 0u));
+            }
+            if (valid) sts32(dst, o);
+            it += 4;
+            if (NCH == 4) {
+                src += QSb;
+                dst += 16u;
+            } else {
+                ch += 1;
+                src += QSb + PSb;
+                dst += 20u;
+                if (ch >= 3) {
+                    ch -= 3;
+                    src += QSb - 3u * PSb;
+                    dst += 4u;
+                }
             }
         }
-        uint4 v[NW];
-#pragma unroll
-        for (int i = 0; i < NW; ++i) v[i] = p[i];
-        uint32_t wd[NW];
-        int32_t sv[4];
-#pragma unroll
-        for (int i = 0; i < NW; ++i) wd[i] = v[i].x;
-        sv[0] = tap_sum<NW>(wd, k0, k1, k2);
-#pragma unroll
-        for (int i = 0; i < NW; ++i) wd[i] = v[i].y;
-        sv[1] = tap_sum<NW>(wd, k0, k1, k2);
-#pragma unroll
-        for (int i = 0; i < NW; ++i) wd[i] = v[i].z;
-        sv[2] = tap_sum<NW>(wd, k0, k1, k2);
-#pragma unroll
-        for (int i = 0; i < NW; ++i) wd[i] = v[i].w;
-        sv[3] = tap_sum<NW>(wd, k0, k1, k2);
-        if (u.mode == 0) {
-            const uint32_t o = pack2_clip(sv[0], sv[1], pack2_clip(sv[2], sv[3], 0u));
-            if (valid) *reinterpret_cast<uint32_t *>(u.dst) = o;
-            u.a_any |= valid ? o : 0u;
-            u.a_all &= valid ? o : 0xffffffffu;
-            // item i -> i + 4.  Four channels: same channel, next quad.  Three: channel + 1, quad + 1, and on a
-            // channel wrap channel - 2, quad + 2 (adds only: IMAD would take dp4a's pipe)
-            u.it += 4;
-            u.ch += 1;
-            const bool wrap = !u.four && u.ch >= 3;
-            u.src += wrap ? u.sstep_wrap : u.sstep;
-            u.dst += wrap ? 24u : u.dstep;
-            if (wrap) u.ch -= 3;
-        } else {
-            uint32_t *cpx = ((u.xx & 4) ? u.p_hi : u.p_lo) + (u.xx & 3);
-            if ((u.m_all >> u.xx) & 1u) {  // opaque column: the pixel replaces the canvas pixel
-                *cpx = pack2_clip(sv[0], sv[1], pack2_clip(sv[2], 255 << kPrecisionBits, 0u));
-            } else if (sv[3] >= (1 << kPrecisionBits)) {  // else transparent: canvas pixel unchanged
-                uint32_t s = pack2_clip(sv[0], sv[1], pack2_clip(sv[2], sv[3], 0u));
-                if (sv[3] < (255 << kPrecisionBits)) s = over_px(*cpx, unpremultiply_px(s));
-                *cpx = s;
-            }
-            u.src += u.sstep;
-            ++u.xx;
-        }
+        named_bar_arrive(1 + s, (kSlabWarps + 1) * 32);
     }
 }
 
-// the lane's coefficient row -> k0..k2[0..nw)
-__device__ __forceinline__ void load_coefs(int nw, const uint32_t *__restrict__ table, int idx, uint32_t (&k0)[5],
-                                           uint32_t (&k1)[5], uint32_t (&k2)[5]) {
-    const uint4 *row = reinterpret_cast<const uint4 *>(table + (int64_t)idx * coef_row_words(nw));
-    const uint4 t0 = __ldg(row), t1 = __ldg(row + 1), t2 = __ldg(row + 2);
-    if (nw == 3) {
-        k0[0] = t0.x; k0[1] = t0.y; k0[2] = t0.z;
-        k1[0] = t0.w; k1[1] = t1.x; k1[2] = t1.y;
-        k2[0] = t1.z; k2[1] = t1.w; k2[2] = t2.x;
-    } else if (nw == 4) {
-        k0[0] = t0.x; k0[1] = t0.y; k0[2] = t0.z; k0[3] = t0.w;
-        k1[0] = t1.x; k1[1] = t1.y; k1[2] = t1.z; k1[3] = t1.w;
-        k2[0] = t2.x; k2[1] = t2.y; k2[2] = t2.z; k2[3] = t2.w;
-    } else {
-        const uint4 t3 = __ldg(row + 3);
-        k0[0] = t0.x; k0[1] = t0.y; k0[2] = t0.z; k0[3] = t0.w; k0[4] = t1.x;
-        k1[0] = t1.y; k1[1] = t1.z; k1[2] = t1.w; k1[3] = t2.x; k1[4] = t2.y;
-        k2[0] = t2.z; k2[1] = t2.w; k2[2] = t3.x; k2[3] = t3.y; k2[4] = t3.z;
+template <int NW>
+__device__ __forceinline__ void vcol3(const uint4 (&v)[NW], uint32_t cpx, const uint32_t (&k0)[NW],
+                                      const uint32_t (&k1)[NW], const uint32_t (&k2)[NW]) {
+    uint32_t wd[NW];
+    int32_t acc[3];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) wd[i] = v[i].x;
+    acc[0] = tap_sum<NW>(wd, k0, k1, k2);
+#pragma unroll
+    for (int i = 0; i < NW; ++i) wd[i] = v[i].y;
+    acc[1] = tap_sum<NW>(wd, k0, k1, k2);
+#pragma unroll
+    for (int i = 0; i < NW; ++i) wd[i] = v[i].z;
+    acc[2] = tap_sum<NW>(wd, k0, k1, k2);
+    sts32(cpx, pack2_clip(acc[0], acc[1], pack2_clip(acc[2], 255 << kPrecisionBits, 0u)));
+}
+template <int NW>
+__device__ __forceinline__ void vcol4(const uint4 (&v)[NW], uint32_t cpx, const uint32_t (&k0)[NW],
+                                      const uint32_t (&k1)[NW], const uint32_t (&k2)[NW]) {
+    uint32_t wd[NW];
+    int32_t acc[4];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) wd[i] = v[i].w;
+    acc[3] = tap_sum<NW>(wd, k0, k1, k2);
+    if (acc[3] < (1 << kPrecisionBits)) return;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) wd[i] = v[i].x;
+    acc[0] = tap_sum<NW>(wd, k0, k1, k2);
+#pragma unroll
+    for (int i = 0; i < NW; ++i) wd[i] = v[i].y;
+    acc[1] = tap_sum<NW>(wd, k0, k1, k2);
+#pragma unroll
+    for (int i = 0; i < NW; ++i) wd[i] = v[i].z;
+    acc[2] = tap_sum<NW>(wd, k0, k1, k2);
+    uint32_t s = pack2_clip(acc[0], acc[1], pack2_clip(acc[2], acc[3], 0u));
+    if (acc[3] < (255 << kPrecisionBits)) s = over_unpremul_px(lds32(cpx), s);
+    sts32(cpx, s);
+}
+
+template <int NW, int NCH>
+__device__ __forceinline__ void slab_vpass(const uint32_t *__restrict__ Iw, int CS, uint32_t *__restrict__ ct, int xa, int xb,
+                                           int col0, int rw0, int oy0, int tho, int dy, double scale, double support,
+                                           const uint32_t *__restrict__ ply, int n_out) {
+    const int lane = threadIdx.x & 31;
+    (void)n_out;
+    uint32_t CSb = 4u * (uint32_t)CS;
+    asm volatile("" : "+r"(CSb));
+#pragma unroll 1
+    for (int r0 = 0; r0 < tho; r0 += 32) {
+        const int lrow = min(r0 + lane, tho - 1);
+        const int y = oy0 + lrow;
+        const int wb4 = ((first_tap(y, scale, support) >> 2) - rw0) * 4;
+        uint32_t k0[NW], k1[NW], k2[NW];
+        load_coef_row<NW>(ply, y, k0, k1, k2);
+        const int r = dy + lrow;
+        const uint32_t crow = smem_u32(ct) + 4u * (uint32_t)((r << 5) + ((col0 & 32) ? kTileH * 32 : 0));
+        const uint32_t p_lo = crow + 4u * (uint32_t)((((col0 >> 2) ^ r) & 7) << 2);
+        const uint32_t p_hi = crow + 4u * (uint32_t)(((((col0 >> 2) | 1) ^ r) & 7) << 2);
+        uint32_t col = smem_u32(Iw) + 4u * (uint32_t)((xa - col0) * CS + wb4);
+#pragma unroll 1
+        for (int xx = xa - col0; xx < xb - col0; ++xx, col += CSb) {
+            uint4 v[NW];
+#pragma unroll
+            for (int i = 0; i < NW; ++i) v[i] = lds128(col + 16u * i);
+            const uint32_t cpx = ((xx & 4) ? p_hi : p_lo) + 4u * (uint32_t)(xx & 3);
+            if (NCH == 3) {
+                vcol3<NW>(v, cpx, k0, k1, k2);
+            } else {
+                uint32_t any = 0u, all = 0xffffffffu;
+#pragma unroll
+                for (int i = 0; i < NW; ++i) {
+                    any |= v[i].w;
+                    all &= v[i].w;
+                }
+                if (!__any_sync(0xffffffffu, any != 0u)) continue;
+                if (__all_sync(0xffffffffu, all == 0xffffffffu)) vcol3<NW>(v, cpx, k0, k1, k2);
+                else vcol4<NW>(v, cpx, k0, k1, k2);
+            }
+        }
     }
 }
 
@@ -668,6 +666,7 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
     if (tid == 0) {
         for (int i = 0; i < kPRing; ++i) {
             mbar_init(&bars->p_full[i], 1);
+            mbar_init(&bars->p_empty[i], kSlabWarps);
         }
         for (int i = 0; i < kTileBufs; ++i) {
             mbar_init(&bars->t_ready[i], 1);
@@ -685,8 +684,6 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
     const Cmd *stream = streams + stream_off[blockIdx.x];
 
     if (warp == kProducerWarp) {
-        // ---------------- producer: walks the stream in order and issues every asynchronous load ----------------
-        // The whole warp runs the loop (the hardware barrier below is a warp-level rendezvous); lane 0 issues.
         const int64_t len = stream_len[blockIdx.x];  // records, END included
         const int nblk = (int)((len + kCmdBlk - 1) / kCmdBlk);
         auto load_block = [&](int b) {
@@ -728,7 +725,7 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                         tma_load_2d(dst, map, (int)c.w[2], (int)c.w[3], &bars->t_ready[buf]);
                         if (tw > 32) tma_load_2d(dst + kTileH * 32, map, (int)c.w[2] + 32, (int)c.w[3], &bars->t_ready[buf]);
                     } else {
-                        mbar_arrive(&bars->t_ready[buf]);  // solid colour / plain loads / fully occluded: the warps fill their slabs
+                        mbar_arrive(&bars->t_ready[buf]);
                     }
                 }
                 ++tseq;
@@ -736,16 +733,13 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                 const bool resample = kind == kCmdResample;
                 const uint32_t w1 = uni(c.w[1]), w2 = uni(c.w[2]), w5 = uni(c.w[5]);
                 const int dy = (int)((w2 >> 8) & 0xffu), tho = (int)(w2 >> 24);
-                // chunk index range and the chunk's TMA arguments
                 const int c_lo = resample ? 0 : dy / kIdentRows;
                 const int c_hi = resample ? ((int)(w1 >> 24) + kChunkQuads - 1) / kChunkQuads : (dy + tho - 1) / kIdentRows + 1;
                 const void *map = maps + ((uint64_t)uni(c.w[8]) << 7);
-                const uint32_t bytes = resample ? uni(c.w[11]) * (uint32_t)(kChunkQuads * 64)  // 4 * pwc words x 4 planes x quads
+                const uint32_t bytes = resample ? uni(c.w[11]) * (uint32_t)(kChunkQuads * 64)
                                                 : (uint32_t)(kOverlayBoxW * kIdentRows * 4);
                 for (int ci = c_lo; ci < c_hi; ++ci, ++cseq) {
                     const int ps = (int)(cseq % kPRing);
-                    // every compute warp has released the slot's previous chunk: hardware barrier, the warp sleeps
-                    // in it without taking issue slots (consumers bar.arrive, see release_chunk)
                     if (cseq >= kPRing) named_bar_sync(1 + ps, (kSlabWarps + 1) * 32);
                     if (lane == 0) {
                         fence_async_smem();
@@ -777,7 +771,7 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                 __nanosleep(kStoreSleepNs);
                 if (mbar_try(&bars->t_done[buf], par)) { have = true; break; }
                 const int total = *n_tiles_total;
-                if (total >= 0 && tseq >= total) break;  // the stream has ended and every tile is out
+                if (total >= 0 && tseq >= total) break;
                 if (spins < (1u << 22)) continue;
                 if ((*reinterpret_cast<volatile int *>(status) & kStatusWatchdog) == 0)
                     watchdog_fire(watch, kTagRoleStore | kTagTileDone, par, (uint32_t)tseq);
@@ -792,11 +786,9 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                 tma_store_2d(map, (int)tr[2], (int)tr[3], src);
                 if ((int)(tr[4] & 0xffffu) > 32) tma_store_2d(map, (int)tr[2] + 32, (int)tr[3], src + kTileH * 32);
             }
-            bulk_commit();  // tiles the warps stored themselves are an empty group: the counting stays uniform
-            if (tseq >= 1) {
-                bulk_wait_read<1>();  // the previous tile's store has read its buffer
-                mbar_arrive(&bars->t_free[(tseq - 1) % kTileBufs]);
-            }
+            bulk_commit();  // tiles the warps stored themselves are an empty group
+            bulk_wait_read<0>();  // the store has read the buffer (this thread has nothing else to do meanwhile)
+            mbar_arrive(&bars->t_free[buf]);
         }
         bulk_wait_all();
         return;
@@ -812,18 +804,13 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
     bool ready_pending = false;  // the wait for the resident tile is deferred to the first access (the H pass does not need it)
     uint32_t *ct = ctile;
     const uint32_t *tr = trec;
-    PROF_DECL;
     auto tile_wait = [&]() {
-        PROF_MARK(kProfPass);
         mbar_wait(&bars->t_ready[tseq % kTileBufs], (uint32_t)(tseq / kTileBufs) & 1u, watch, kTagRoleConsumer | kTagTileReady, (uint32_t)tseq);
         ready_pending = false;
-        PROF_MARK(kProfTileWait);
     };
     for (int pos = 0;; ++pos) {
         const int b = pos / kCmdBlk, s = b % kCmdRing, e = pos % kCmdBlk;
-        PROF_MARK(kProfPass);
         if (e == 0) mbar_wait(&bars->c_full[s], (b / kCmdRing) & 1, watch, kTagRoleConsumer | kTagCmdFull, (uint32_t)pos);
-        PROF_MARK(kProfCmd);
         const Cmd &cmd = ring[s * kCmdBlk + e];
         // Record fields are the same for every lane, but the compiler cannot know that of a shared-memory load:
         // broadcasting them from lane 0 marks them warp-uniform (offsets then live on the uniform datapath).
@@ -875,6 +862,7 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                     const uint32_t w5 = uni(cmd.w[5]);
                     const int ox0 = (int)uni(cmd.w[3]), oy0 = (int)uni(cmd.w[4]);
                     const int cw0 = (int)(w5 & 0xffffu), rw0 = (int)(w5 >> 16);
+                    const int n_out_x = (int)uni(cmd.w[6]), n_out_y = (int)uni(cmd.w[7]);
                     const uint32_t *plx = tables + uni(cmd.w[9]), *ply = tables + uni(cmd.w[10]);
                     const int pwc = (int)uni(cmd.w[11]);
                     const double scale_x = __longlong_as_double((long long)((uint64_t)cmd.w[12] | ((uint64_t)cmd.w[13] << 32)));
@@ -891,93 +879,33 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                     }
                     const bool active = X >= xa && X < xb;
                     const int j = ox0 + (active ? X : xa) - dx;  // lanes off the step read a valid column's table
-                    uint32_t k0[5], k1[5], k2[5];
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) k0[i] = k1[i] = k2[i] = 0u;
-                    load_coefs(nwx, plx, j, k0, k1, k2);
-                    // horizontal pass constants of this lane (shared-memory byte offsets)
-                    const int wbx4 = ((first_tap(j, scale_x, support_x) >> 2) - cw0) * 4;
-                    uint32_t QSb = 64u * (uint32_t)pwc, PSb = 16u * (uint32_t)pwc;  // bytes per row quad / channel plane of a chunk
-                    uint32_t CSb = 4u * (uint32_t)CS;
-                    asm volatile("" : "+r"(QSb), "+r"(PSb), "+r"(CSb));  // stay in registers: re-deriving them costs IMADs on dp4a's pipe
-                    const bool four = nch == 4;
-                    // first item of the lane in a chunk: (channel, quad) = four ? (q, 0) : (q % 3, q / 3)
-                    const int ch0 = (four || q < 3) ? q : 0, rq0 = (four || q < 3) ? 0 : 1;
-                    const uint8_t *lane_src = reinterpret_cast<const uint8_t *>(P + wbx4);
-                    uint8_t *lane_dst = reinterpret_cast<uint8_t *>(Iw + jl * CS + ch0);
-                    const uint32_t soff0 = active ? (uint32_t)rq0 * QSb + (uint32_t)ch0 * PSb : 0u;
-                    TapUnit u;
-                    u.four = four;
-                    u.active = active;
-                    u.a_any = 0u;
-                    u.a_all = 0xffffffffu;
-                    u.m_any = u.m_all = 0xffu;
-                    u.p_lo = u.p_hi = ct;
-                    u.xx = 0;
-                    const int n_chunks = (NRQ + kChunkQuads - 1) / kChunkQuads, n_groups = (tho + 31) >> 5;
-                    PROF_MARK(kProfDecode);
-#pragma unroll 1
-                    for (int un = 0; un < n_chunks + n_groups; ++un) {
-                        int nw, ps = 0;
-                        if (un < n_chunks) {
-                            // ---- H items of patch chunk `un`
-                            const int q0 = un * kChunkQuads;
-                            ps = (int)(cseq % kPRing);
-                            PROF_MARK(kProfH);
-                            mbar_wait(&bars->p_full[ps], (cseq / kPRing) & 1u, watch, kTagRoleConsumer | kTagPatchFull, cseq);
-                            PROF_MARK(kProfPatchWait);
-                            const uint8_t *slot = lane_src + (size_t)(ps * slot_words) * 4u;
-                            u.mode = 0;
-                            u.n_items = nch * min(kChunkQuads, NRQ - q0);
-                            u.n_iter = (u.n_items + 3) >> 2;
-                            u.it = q;
-                            u.ch = ch0;
-                            u.src = slot + soff0;
-                            u.safe = slot;
-                            u.dst = lane_dst + 16u * (uint32_t)(q0 + rq0);
-                            u.sstep = four ? QSb : QSb + PSb;
-                            u.sstep_wrap = 2u * QSb - 2u * PSb;
-                            u.dstep = four ? 16u : 20u;
-                            nw = nwx;
-                        } else {
-                            // ---- V columns of row group un - n_chunks
-                            if (un == n_chunks) {
-                                __syncwarp();  // the slab's intermediate is complete
-                                // column classes: bit xx = slab column xx (the alpha lanes are lanes 24..31); an opaque
-                                // patch has no alpha plane: every column draws, every column is opaque
-                                if (four) {
-                                    u.m_any = __ballot_sync(0xffffffffu, u.a_any != 0u) >> 24;
-                                    u.m_all = __ballot_sync(0xffffffffu, u.a_all == 0xffffffffu) >> 24;
-                                }
-                                PROF_MARK(kProfH);
-                                if (ready_pending) tile_wait();
-                            }
-                            // Lanes past the last row redo the last row (same loads, same value stored to the same address).
-                            const int lrow = min((un - n_chunks) * 32 + lane, tho - 1);
-                            const int y = oy0 + lrow;
-                            load_coefs(nwy, ply, y, k0, k1, k2);
-                            const int wby4 = ((first_tap(y, scale_y, support_y) >> 2) - rw0) * 4;
-                            const int r = dy + lrow;
-                            uint32_t *crow = ct + (r << 5) + ((col0 & 32) ? kTileH * 32 : 0);
-                            u.p_lo = crow + ((((col0 >> 2) ^ r) & 7) << 2);
-                            u.p_hi = crow + (((((col0 >> 2) | 1) ^ r) & 7) << 2);
-                            u.mode = 1;
-                            u.src = reinterpret_cast<const uint8_t *>(Iw + (xa - col0) * CS + wby4);
-                            u.sstep = CSb;
-                            u.xx = xa - col0;
-                            u.n_iter = xb - xa;
-                            nw = nwy;
-                        }
-                        if (nw == 3) tap_engine<3>(u, k0, k1, k2);
-                        else if (nw == 4) tap_engine<4>(u, k0, k1, k2);
-                        else tap_engine<5>(u, k0, k1, k2);
-                        if (un < n_chunks) {
-                            named_bar_arrive(1 + ps, (kSlabWarps + 1) * 32);  // chunk released (warp-level arrive: all lanes' reads are done)
-                            ++cseq;
-                        }
+#define B200_HPASS(NWX, NCH_) \
+    slab_hpass<NWX, NCH_>(P, slot_words, bars, cseq, watch, Iw, CS, NRQ, pwc, cw0, j, active, scale_x, support_x, plx, n_out_x)
+                    if (nch == 4) {
+                        if (nwx == 3) B200_HPASS(3, 4);
+                        else if (nwx == 4) B200_HPASS(4, 4);
+                        else B200_HPASS(5, 4);
+                    } else {
+                        if (nwx == 3) B200_HPASS(3, 3);
+                        else if (nwx == 4) B200_HPASS(4, 3);
+                        else B200_HPASS(5, 3);
                     }
+#undef B200_HPASS
+                    __syncwarp();  // the slab's intermediate is complete
+                    if (ready_pending) tile_wait();
+#define B200_VPASS(NWY, NCH_) \
+    slab_vpass<NWY, NCH_>(Iw, CS, ct, xa, xb, col0, rw0, oy0, tho, dy, scale_y, support_y, ply, n_out_y)
+                    if (nch == 4) {
+                        if (nwy == 3) B200_VPASS(3, 4);
+                        else if (nwy == 4) B200_VPASS(4, 4);
+                        else B200_VPASS(5, 4);
+                    } else {
+                        if (nwy == 3) B200_VPASS(3, 3);
+                        else if (nwy == 4) B200_VPASS(4, 3);
+                        else B200_VPASS(5, 3);
+                    }
+#undef B200_VPASS
                     __syncwarp();  // the next step's H pass overwrites the intermediate
-                    PROF_MARK(kProfV);
                 }
             } else if (kind == kCmdIdentTma) {
                 // identity-size overlay: chunks of kIdentRows tile rows of the raw overlay (zero outside it)
@@ -1012,7 +940,6 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                     }
                 __syncwarp();
             }
-            PROF_MARK(kProfIdent);  // identity overlays, chunks passed on by warps off the step
             if (--steps_left == 0) {
                 // the slab's pixels are final
                 if (ready_pending) tile_wait();
@@ -1030,7 +957,6 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->t_done[tseq % kTileBufs]);
-                PROF_MARK(kProfTileEnd);
             }
         }
         if (e == kCmdBlk - 1) {
@@ -1038,7 +964,6 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
             if (lane == 0) mbar_arrive(&bars->c_empty[s]);
         }
     }
-    PROF_FLUSH();
 }
 
 }  // namespace b200comp
