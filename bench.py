@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="canvases in the CPU baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fresh-plan", action="store_true", help="skip the new-plan-every-step measurement")
     ap.add_argument("--solid-bg", action="store_true", help="synthesise the solid background in-kernel (no bg read)")
     return ap.parse_args()
 
@@ -336,6 +337,57 @@ def run_b200(args):
         "how": "cudaEvent pairs around each phase of b200comp_plan_run on the launching stream",
     }
 
+    # ---- fresh layouts: a NEW plan (coefficient tables, tensor maps, descriptor uploads) for every step ----
+    # Two plans alternate; while one runs on the launching stream, a host thread resolves the other on a side stream
+    # (b200comp_plan_create is a host call plus a few small kernels).  Same canvases, same bytes per step as above.
+    fresh = None
+    if not args.no_fresh_plan:
+        import concurrent.futures
+
+        plan_c_s = cb.plan_create_s
+        cb2 = B.CompositeBatch(dpool, canvases, placements, backgrounds=bgs, solid=solids, out=cb.out_buffer,
+                               host_threads=host_cores())
+        side = torch.cuda.Stream(device=dev)
+        plans = [cb, cb2]
+        done_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        create_s = []
+
+        def make(i):
+            side.wait_event(done_ev[i])  # the plan's last run has finished before its buffers are freed
+            t0 = time.perf_counter()
+            plans[i].recreate(side)
+            create_s.append(time.perf_counter() - t0)
+
+        main = torch.cuda.current_stream()
+        for i in range(2):
+            done_ev[i].record(main)
+        with concurrent.futures.ThreadPoolExecutor(1) as ex:
+            fut = ex.submit(make, 0)
+            n_fresh = args.steps + 2
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for k in range(n_fresh):
+                if k == 2:
+                    barrier()
+                    f0.record()
+                i = k & 1
+                fut.result()
+                plans[i].run()
+                done_ev[i].record(main)
+                fut = ex.submit(make, i ^ 1)
+            f1.record()
+            fut.result()
+            torch.cuda.synchronize()
+        for pl_ in plans:
+            pl_.check()
+        tf = torch.tensor([f0.elapsed_time(f1) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        fresh = {"fresh_plan_ms_per_step": float(tf.item()), "plan_create_ms": plan_c_s * 1e3,
+                 "plan_create_ms_pipelined": 1e3 * sorted(create_s)[len(create_s) // 2],
+                 "how": "a new plan per step (b200comp_plan_create on a host thread + side stream under the previous "
+                        "step's run, two plans alternating); plan_create_ms = the C call alone, nothing else running"}
+        cb2.close()
+
     # ---- end to end: host buffers through the C ABI (H2D cutouts + backgrounds, D2H canvases) ----
     e2e = None
     if not args.no_e2e:
@@ -457,12 +509,12 @@ def run_b200(args):
                        "parallelism": f"canvas-sharded x{world}, no collective",
                        "fused_placements": info["fused_placements"], "identity_placements": info["identity_placements"],
                        "preresampled_placements": info["preresampled_placements"], "smem_bytes_per_cta": info["smem_bytes"],
-                       "coeff_table_bytes": info["coeff_bytes"], "plan_create_s": plan_s, "setup_s": setup_s,
+                       "coeff_table_bytes": info["coeff_bytes"], "plan_create_s": plan_s, "setup_s": setup_s, "fresh_plan": fresh,
                        "host_cores": host_cores()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (ratio * algo if ratio else None), "peak_source": peak_src,
                          "traffic_source": ratio_src, "algorithmic_bytes_per_launch": algo,
-                         "kernel": "b200comp_plan_run = prepare_cutouts + 3 binning kernels + composite_stream_kernel "
+                         "kernel": "b200comp_plan_run = prepare_cutouts + 3 binning kernels + composite_slab_kernel "
                                    "(persistent tile kernel, the dominant launch); achieved = algorithmic bytes of the "
                                    "step / whole step time, so every kernel that moves those bytes is inside",
                          "kernel_split": kernel_split},

@@ -49,12 +49,14 @@ def fill_solid(background_path: str, canvas_size: Tuple[int, int]) -> Image.Imag
         return Image.new("RGBA", (W, H), color + (255,))
     _native.require_gpu()
     a = _as_rgba_array(bg)
-    out = np.empty((H, W, 4), np.uint8)
+    result, out = _native.new_rgba_image(W, H)  # the library writes into an image Pillow owns (fully mutable)
+    if result is None:
+        out = np.empty((H, W, 4), np.uint8)
     rgb = (ctypes.c_int32 * 3)()
     rc = _native.lib().b200comp_fill_solid_host(a.ctypes.data, a.shape[1], a.shape[0], a.strides[0], out.ctypes.data,
                                                 W, H, out.strides[0], rgb)
     _native.check(rc, "fill_solid")
-    return _native.image_from_rgba(out)
+    return result if result is not None else _native.image_from_rgba(out)
 
 
 def _edge_strip_median_colors(img: Image.Image, strip_px: int = 8) -> Tuple[RGB, RGB, RGB, RGB]:
@@ -81,11 +83,13 @@ def fill_gradient(background_path: str, canvas_size: Tuple[int, int]) -> Image.I
     W, H = (int(canvas_size[0]), int(canvas_size[1]))
     _native.require_gpu()
     a = _as_rgba_array(bg)
-    out = np.empty((H, W, 4), np.uint8)
+    result, out = _native.new_rgba_image(W, H)
+    if result is None:
+        out = np.empty((H, W, 4), np.uint8)
     edges = (ctypes.c_int32 * 12)()
     horizontal = ctypes.c_int(0)
     rc = _native.lib().b200comp_fill_gradient_host(a.ctypes.data, a.shape[1], a.shape[0], a.strides[0],
                                                    out.ctypes.data, W, H, out.strides[0], 8, edges,
                                                    ctypes.byref(horizontal))
     _native.check(rc, "fill_gradient")
-    return _native.image_from_rgba(out)
+    return result if result is not None else _native.image_from_rgba(out)

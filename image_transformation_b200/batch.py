@@ -12,6 +12,7 @@ PyTorch is used for device memory and streams only.
 from __future__ import annotations
 
 import ctypes
+import time
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -152,13 +153,29 @@ class CompositeBatch:
             pl[j] = _native.Placement(pool.ptr(oid), pool.pitch(oid), sw, sh, x, y, w, h, flags, 0)
             self.src_bytes += sw * sh * 4
         self.n_placements = len(recs)
-        with torch.cuda.device(pool.device):
-            rc = _native.lib().b200comp_plan_create(cv, n, pl, len(recs), int(host_threads), _stream_handle(stream),
-                                                    ctypes.byref(self._plan))
+        self._cv, self._pl, self._host_threads = cv, pl, int(host_threads)  # kept for recreate()
+        self.plan_create_s = 0.0
+        self._create(stream)
+
+    def _create(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+        t0 = time.perf_counter()
+        with torch.cuda.device(self.pool.device):
+            rc = _native.lib().b200comp_plan_create(self._cv, self.n, self._pl, self.n_placements, self._host_threads,
+                                                    _stream_handle(stream), ctypes.byref(self._plan))
         _native.check(rc, "CompositeBatch")
+        self.plan_create_s = time.perf_counter() - t0  # the C call alone: tables, tensor maps, uploads
         info = (ctypes.c_int64 * len(_native.INFO_KEYS))()
         _native.check(_native.lib().b200comp_plan_info(self._plan, info), "plan_info")
         self.info = dict(zip(_native.INFO_KEYS, (int(v) for v in info)))
+
+    def recreate(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Throw the plan away and resolve the same descriptors again (what a fresh layout costs: coefficient
+        tables, tensor maps, uploads) -- bench.py's fresh-plan figure."""
+        if self._plan:
+            with torch.cuda.device(self.pool.device):
+                _native.lib().b200comp_plan_destroy(self._plan)
+            self._plan = ctypes.c_void_p()
+        self._create(stream)
 
     # ------------------------------------------------------------------ execution
     def run(self, stream: Optional[torch.cuda.Stream] = None) -> None:

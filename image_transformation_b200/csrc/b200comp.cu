@@ -1,6 +1,7 @@
 // libb200comp.so -- kernels and C ABI of the B200 compositor hot path (include/b200comp.h).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo (see build.py).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -843,6 +844,14 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     plan->create_stream = st;
     plan->n_canvases = n_canvases;
 
+    // B200COMP_TRACE_PLAN=1: host-side timeline of plan creation on stderr
+    static const bool trace_plan = std::getenv("B200COMP_TRACE_PLAN") != nullptr;
+    const auto t_trace0 = std::chrono::steady_clock::now();
+    auto stamp = [&](const char *what) {
+        if (!trace_plan) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_trace0).count();
+        std::fprintf(stderr, "[b200comp plan] %8.3f ms  %s\n", ms, what);
+    };
     // ---- validate, classify placements, collect tables ----
     TableSet ts;
     std::vector<DevPlacementT> hp((size_t)std::max(1, n_placements));
@@ -918,6 +927,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         }
     }
 
+    stamp("placements classified");
     // ---- canvases / tiles ----
     std::vector<DevCanvas> hc((size_t)n_canvases);
     int64_t tiles = 0, algo = 0, step_records = 0;
@@ -960,6 +970,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         plan->stream_capacity = tiles + step_records + plan->G;
     }
 
+    stamp("canvases / tiles");
     // ---- build tables on the host threads, upload everything ----
     // B200COMP_HOST_TABLES=1 builds the packed tables with libm on the host threads instead (validation)
     static const bool host_tables = std::getenv("B200COMP_HOST_TABLES") != nullptr;
@@ -988,6 +999,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             d.src = plan->pre[(size_t)pre_index[i]].dst;
         }
     }
+    stamp("allocations");
     // ---- prepared cutouts (premultiplied, planar) + one TMA descriptor per resampled placement ----
     {
         typedef std::tuple<const uint8_t *, int, int, int64_t> SrcKey;
@@ -1140,7 +1152,9 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         CUDA_TRY(dev_alloc((void **)&plan->d_maps, std::max<size_t>(1, hmaps.size()) * sizeof(CUtensorMap)));
         if (!hmaps.empty())
             CUDA_TRY(cudaMemcpyAsync(plan->d_maps, hmaps.data(), hmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+        stamp("tensor maps encoded");
         CUDA_TRY(cudaStreamSynchronize(st));  // hmaps / hprep are locals
+        stamp("maps uploaded (sync)");
         for (int i = 0; i < n_placements; ++i) {
             if (map_of[i] >= 0) hp[i].tmap = plan->d_maps + (size_t)map_of[i] * sizeof(CUtensorMap);
             const int pi = prep_of[i] >= 0 ? prep_of[i] : flags_only_of[i];
@@ -1170,6 +1184,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         plan->mask_chunks = (max_count + 31) / 32;
         CUDA_TRY(dev_alloc((void **)&plan->d_masks, (size_t)std::max<int64_t>(1, tiles) * plan->mask_chunks * 2 * sizeof(uint32_t)));
     }
+    stamp("stream buffers allocated");
     int64_t n_fixed = 0;
     if (tables_on_device) {
         if (ts.has_legacy()) {  // legacy tables of the generic kernels: host-built, uploaded with the (still empty) packed regions
@@ -1193,7 +1208,9 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     CUDA_TRY(cudaMemcpyAsync(plan->d_boxes, hboxes.data(), hboxes.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(plan->d_canvases, hc.data(), hc.size() * sizeof(DevCanvas), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(plan->d_status, 0, sizeof(int), st));
+    stamp("tables built");
     CUDA_TRY(cudaStreamSynchronize(st));  // host staging vectors die with this scope
+    stamp("descriptors uploaded (sync)");
 
     plan->slot_words = (max_slot + 31) & ~31;  // slots stay 128-byte aligned
     plan->iw_words = max_iw;

@@ -312,20 +312,232 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
     return 0;
 }
 
-int b200comp_composite_host(const uint8_t *bg, int W, int H, size_t bg_pitch, uint8_t *out, size_t out_pitch,
-                            const b200comp_placement *placements, int n_placements) {
-    if (!bg || !out) return b200comp_set_error_(B200COMP_EINVAL, "composite_host: null canvas");
+// ---- single canvas, host buffers: the call behind the drop-in composite() (compositor.py:6-22) ----
+// Everything a call needs besides the plan is cached per thread and only ever grows: one stream, one event, pinned
+// bounce buffers (pageable caller memory is copied through them in chunks, so the copy engine overlaps the host
+// memcpy), device staging for background, canvas and cutouts.  No helper thread, no device-wide synchronisation:
+// concurrent callers (one Streamlit session thread each) do not serialise on anything but the GPU itself.
+namespace {
+
+struct LeanCtx {
+    int device = -1;
+    cudaStream_t st = nullptr;
+    uint8_t *pin_in = nullptr, *pin_out = nullptr;
+    size_t pin_in_cap = 0, pin_out_cap = 0;
+    uint8_t *d_bg = nullptr, *d_out = nullptr, *d_pool = nullptr;
+    size_t d_bg_cap = 0, d_out_cap = 0, d_pool_cap = 0;
+    int *h_status = nullptr;
+
+    void release() {
+        if (device >= 0) {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            if (cur != device) cudaSetDevice(device);
+            if (st) cudaStreamSynchronize(st);
+            if (pin_in) cudaFreeHost(pin_in);
+            if (pin_out) cudaFreeHost(pin_out);
+            if (d_bg) cudaFree(d_bg);
+            if (d_out) cudaFree(d_out);
+            if (d_pool) cudaFree(d_pool);
+            if (h_status) cudaFreeHost(h_status);
+            if (st) cudaStreamDestroy(st);
+            if (cur != device) cudaSetDevice(cur);
+        }
+        *this = LeanCtx();
+    }
+    ~LeanCtx() {
+        // thread exit: the CUDA context may already be gone at process exit; errors are ignored
+        if (device >= 0 && cudaSetDevice(device) == cudaSuccess) release();
+    }
+    static bool grow_pinned(uint8_t **p, size_t *cap, size_t need) {
+        if (need <= *cap) return true;
+        if (*p) cudaFreeHost(*p);
+        *p = nullptr;
+        *cap = 0;
+        const size_t want = align_up(need + need / 4, 1 << 20);
+        if (cudaHostAlloc((void **)p, want, cudaHostAllocDefault) != cudaSuccess) return false;
+        *cap = want;
+        return true;
+    }
+    static bool grow_device(uint8_t **p, size_t *cap, size_t need, cudaStream_t st) {
+        if (need <= *cap) return true;
+        if (*p) {
+            cudaStreamSynchronize(st);
+            cudaFree(*p);
+        }
+        *p = nullptr;
+        *cap = 0;
+        const size_t want = align_up(need + need / 4, 1 << 20);
+        if (cudaMalloc((void **)p, want) != cudaSuccess) return false;
+        *cap = want;
+        return true;
+    }
+};
+thread_local LeanCtx g_lean;
+
+// rows of a pageable (or pinned) host image -> device, through the pinned bounce buffer in ~4 MB chunks
+void upload_rows(uint8_t *dev, size_t dev_pitch, const uint8_t *host, size_t host_pitch, size_t row_bytes, int rows,
+                 uint8_t *pin, cudaStream_t st) {
+    const int chunk_rows = (int)std::max<size_t>(1, ((size_t)4 << 20) / std::max<size_t>(1, dev_pitch));
+    for (int r0 = 0; r0 < rows; r0 += chunk_rows) {
+        const int n = std::min(chunk_rows, rows - r0);
+        uint8_t *p = pin + (size_t)r0 * dev_pitch;
+        if (host_pitch == dev_pitch) {
+            std::memcpy(p, host + (size_t)r0 * host_pitch, (size_t)n * dev_pitch);
+        } else {
+            for (int r = 0; r < n; ++r) std::memcpy(p + (size_t)r * dev_pitch, host + (size_t)(r0 + r) * host_pitch, row_bytes);
+        }
+        cudaMemcpyAsync(dev + (size_t)r0 * dev_pitch, p, (size_t)n * dev_pitch, cudaMemcpyHostToDevice, st);
+    }
+}
+
+}  // namespace
+
+int b200comp_composite_host_ex(const uint8_t *bg, uint32_t solid_rgba, int W, int H, size_t bg_pitch, uint8_t *out,
+                               size_t out_pitch, const b200comp_placement *placements, int n_placements) {
+    if (!out || W < 1 || H < 1 || out_pitch < (size_t)W * 4 || (bg && bg_pitch < (size_t)W * 4) || n_placements < 0 ||
+        (n_placements > 0 && !placements))
+        return b200comp_set_error_(B200COMP_EINVAL, "composite_host: bad canvas or placement argument");
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, "no CUDA device");
+    LeanCtx &cx = g_lean;
+    if (cx.device != device) {
+        cx.release();
+        cx.device = device;
+        if (cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaHostAlloc((void **)&cx.h_status, sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+            cx.release();
+            return b200comp_set_error_(B200COMP_ECUDA, "composite_host: stream / pinned status allocation failed");
+        }
+    }
+    cudaStream_t st = cx.st;
+    const size_t dp = align_up((size_t)W * 4, 16), canvas_bytes = dp * H;
+
+    // distinct host cutouts of the call -> one staging pool (16-byte aligned pitches); device cutouts are used in place
+    struct Src { const uint8_t *p; int sw, sh; int64_t pitch; size_t off; };
+    std::vector<Src> srcs;
+    std::vector<b200comp_placement> pp((size_t)n_placements);
+    size_t pool_bytes = 0;
+    for (int i = 0; i < n_placements; ++i) {
+        b200comp_placement p = placements[i];
+        if (!p.src || p.sw < 1 || p.sh < 1 || p.w < 1 || p.h < 1 || p.src_pitch < (int64_t)p.sw * 4)
+            return b200comp_set_error_(B200COMP_EINVAL, "composite_host: bad placement");
+        if (!(p.flags & B200COMP_SRC_DEVICE)) {
+            size_t k = 0;
+            for (; k < srcs.size(); ++k)
+                if (srcs[k].p == p.src && srcs[k].sw == p.sw && srcs[k].sh == p.sh && srcs[k].pitch == p.src_pitch) break;
+            if (k == srcs.size()) {
+                srcs.push_back(Src{p.src, p.sw, p.sh, p.src_pitch, pool_bytes});
+                pool_bytes = align_up(pool_bytes + align_up((size_t)p.sw * 4, 16) * p.sh, 256);
+            }
+            p.src = reinterpret_cast<const uint8_t *>(srcs[k].off);  // offset for now; the pool may still move
+            p.src_pitch = (int64_t)align_up((size_t)p.sw * 4, 16);
+        }
+        p.flags &= ~B200COMP_SRC_DEVICE;
+        pp[(size_t)i] = p;
+    }
+    const size_t in_bytes = pool_bytes + (bg ? canvas_bytes : 0);
+    if (!LeanCtx::grow_pinned(&cx.pin_in, &cx.pin_in_cap, in_bytes) || !LeanCtx::grow_pinned(&cx.pin_out, &cx.pin_out_cap, canvas_bytes) ||
+        !LeanCtx::grow_device(&cx.d_out, &cx.d_out_cap, canvas_bytes, st) ||
+        (bg && !LeanCtx::grow_device(&cx.d_bg, &cx.d_bg_cap, canvas_bytes, st)) ||
+        (pool_bytes && !LeanCtx::grow_device(&cx.d_pool, &cx.d_pool_cap, pool_bytes, st)))
+        return b200comp_set_error_(B200COMP_ENOMEM, "composite_host: staging allocation failed");
+    for (int i = 0; i < n_placements; ++i)
+        if (!(placements[i].flags & B200COMP_SRC_DEVICE)) pp[(size_t)i].src = cx.d_pool + reinterpret_cast<size_t>(pp[(size_t)i].src);
+
+    // copy-in: cutouts first (the plan's prepare kernel reads them), then the background
+    for (const Src &s : srcs) {
+        const size_t pitch = align_up((size_t)s.sw * 4, 16);
+        upload_rows(cx.d_pool + s.off, pitch, s.p, (size_t)s.pitch, (size_t)s.sw * 4, s.sh, cx.pin_in + s.off, st);
+    }
+    if (bg) upload_rows(cx.d_bg, dp, bg, bg_pitch, (size_t)W * 4, H, cx.pin_in + pool_bytes, st);
+
     b200comp_canvas cv;
     std::memset(&cv, 0, sizeof cv);
-    cv.out = out;
-    cv.out_pitch = (int64_t)out_pitch;
-    cv.bg = bg;
-    cv.bg_pitch = (int64_t)bg_pitch;
+    cv.out = cx.d_out;
+    cv.out_pitch = (int64_t)dp;
+    cv.bg = bg ? cx.d_bg : nullptr;
+    cv.bg_pitch = bg ? (int64_t)dp : 0;
+    cv.solid_rgba = solid_rgba;
     cv.W = W;
     cv.H = H;
     cv.first_placement = 0;
     cv.n_placements = n_placements;
-    return b200comp_composite_batch_host(&cv, 1, placements, n_placements, 8, 1, 1);
+    b200comp_plan *plan = nullptr;
+    int rc = b200comp_plan_create(&cv, 1, pp.data(), n_placements, 1, st, &plan);
+    if (rc) return rc;
+    rc = b200comp_plan_run(plan, st);
+    *cx.h_status = 0;
+    if (!rc) rc = b200comp_plan_status_async_(plan, cx.h_status, st);
+    if (rc) {
+        cudaStreamSynchronize(st);
+        b200comp_plan_destroy(plan);
+        return rc;
+    }
+    // copy-out in chunks: while the copy engine fills the next chunk of the pinned buffer, the host copies the
+    // previous one into the caller's (pageable) canvas
+    const int chunk_rows = (int)std::max<size_t>(1, ((size_t)4 << 20) / dp);
+    const int n_chunks = (H + chunk_rows - 1) / chunk_rows;
+    std::vector<cudaEvent_t> evs((size_t)n_chunks, nullptr);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int r0 = c * chunk_rows, n = std::min(chunk_rows, H - r0);
+        cudaMemcpyAsync(cx.pin_out + (size_t)r0 * dp, cx.d_out + (size_t)r0 * dp, (size_t)n * dp, cudaMemcpyDeviceToHost, st);
+        cudaEventCreateWithFlags(&evs[(size_t)c], cudaEventDisableTiming);
+        cudaEventRecord(evs[(size_t)c], st);
+    }
+    cudaError_t e = cudaSuccess;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int r0 = c * chunk_rows, n = std::min(chunk_rows, H - r0);
+        const cudaError_t ec = cudaEventSynchronize(evs[(size_t)c]);
+        if (ec != cudaSuccess) e = ec;
+        if (e == cudaSuccess) {
+            if (out_pitch == dp) {
+                std::memcpy(out + (size_t)r0 * out_pitch, cx.pin_out + (size_t)r0 * dp, (size_t)n * dp);
+            } else {
+                for (int r = 0; r < n; ++r)
+                    std::memcpy(out + (size_t)(r0 + r) * out_pitch, cx.pin_out + (size_t)(r0 + r) * dp, (size_t)W * 4);
+            }
+        }
+        cudaEventDestroy(evs[(size_t)c]);
+    }
+    const int status = *cx.h_status;  // travelled on the stream ahead of the canvas
+    b200comp_plan_destroy(plan);      // (its stream is idle: every chunk event has fired)
+    if (e != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, cudaGetErrorString(e));
+    if (status != 0)
+        return b200comp_set_error_(B200COMP_EINTERNAL, ("tile kernel / binning status " + std::to_string(status)).c_str());
+    return 0;
+}
+
+int b200comp_composite_host(const uint8_t *bg, int W, int H, size_t bg_pitch, uint8_t *out, size_t out_pitch,
+                            const b200comp_placement *placements, int n_placements) {
+    if (!bg) return b200comp_set_error_(B200COMP_EINVAL, "composite_host: null canvas");
+    return b200comp_composite_host_ex(bg, 0u, W, H, bg_pitch, out, out_pitch, placements, n_placements);
+}
+
+int b200comp_device_upload(const uint8_t *img, int w, int h, size_t pitch, uint8_t **dev, size_t *dev_pitch) {
+    if (!img || !dev || !dev_pitch || w < 1 || h < 1 || pitch < (size_t)w * 4)
+        return b200comp_set_error_(B200COMP_EINVAL, "device_upload: bad argument");
+    const size_t dp = align_up((size_t)w * 4, 16);
+    uint8_t *d = nullptr;
+    if (cudaMalloc((void **)&d, dp * h) != cudaSuccess) return b200comp_set_error_(B200COMP_ENOMEM, "device_upload: allocation failed");
+    const cudaError_t e = cudaMemcpy2D(d, dp, img, pitch, (size_t)w * 4, h, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return b200comp_set_error_(B200COMP_ECUDA, cudaGetErrorString(e));
+    }
+    *dev = d;
+    *dev_pitch = dp;
+    return 0;
+}
+
+int b200comp_device_free(uint8_t *dev) { return cudaFree(dev) == cudaSuccess ? 0 : b200comp_set_error_(B200COMP_ECUDA, "device_free failed"); }
+
+int b200comp_trim(void) {
+    g_lean.release();
+    int device = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&device) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    return 0;
 }
 
 // decoded image (HOST) -> tightly packed device copy

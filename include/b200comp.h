@@ -39,6 +39,10 @@ enum b200comp_status {
  * mirror sets it when Pillow >= 12 would (src_h > 100*src_w and h < src_h,
  * PIL Image.py:2431-2435, reached from compositor.py:20). */
 #define B200COMP_VERTICAL_FIRST 1
+/* Placement flag for the host-buffer entry points: `src` is DEVICE memory (a cutout uploaded once with
+ * b200comp_device_upload and reused over many calls -- the refine loop of macro_placement_test.py:1493-1513,
+ * 1679-1699 re-composites the same bundle every iteration). */
+#define B200COMP_SRC_DEVICE 2
 
 int b200comp_abi_version(void);
 const char *b200comp_last_error(void);
@@ -180,6 +184,19 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
                                   int chunk_canvases, int n_streams);
 int b200comp_composite_host(const uint8_t *bg, int W, int H, size_t bg_pitch, uint8_t *out, size_t out_pitch,
                             const b200comp_placement *placements, int n_placements);
+/* Same call with two short cuts for the callers around composite() (macro_placement_test.py:1427 -> :1510-1511):
+ * bg == NULL composites onto a canvas of the solid colour `solid_rgba` (what fill_solid returned: no W*H*4 upload),
+ * and placements flagged B200COMP_SRC_DEVICE read cutouts that already live on the device.  Both forms run on a
+ * per-thread cached context (one stream, pinned bounce buffers, device staging): no helper thread, no device-wide
+ * synchronisation, safe to call from several threads at once. */
+int b200comp_composite_host_ex(const uint8_t *bg, uint32_t solid_rgba, int W, int H, size_t bg_pitch, uint8_t *out,
+                               size_t out_pitch, const b200comp_placement *placements, int n_placements);
+/* Device-resident copy of a decoded RGBA image (16-byte aligned pitch); free with b200comp_device_free. */
+int b200comp_device_upload(const uint8_t *img, int w, int h, size_t pitch, uint8_t **dev, size_t *dev_pitch);
+int b200comp_device_free(uint8_t *dev);
+/* Give cached memory back to the driver: the stream-ordered pool the library allocates from and the calling
+ * thread's cached host-call context (pinned bounce buffers, device staging). */
+int b200comp_trim(void);
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
 int b200comp_host_alloc(void **ptr, size_t bytes);
 int b200comp_host_free(void *ptr);

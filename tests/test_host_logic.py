@@ -117,8 +117,8 @@ def test_unpremultiply_magic_division_is_exact():
 
 
 def test_rgba_array_paths():
-    """_native.rgba_array: tagged outputs are reused until written to, every other image is copied correctly
-    (owned, buffer-backed / read-only, larger than one Pillow block)."""
+    """_native.rgba_array / new_rgba_image / image_from_rgba: zero-copy views of single-block images stay coherent
+    with the image, bigger and buffer-backed images are copied correctly, results are fully mutable PIL images."""
     from PIL import Image
 
     from image_transformation_b200 import _native
@@ -128,12 +128,26 @@ def test_rgba_array_paths():
     for img in (Image.fromarray(a, "RGBA"), Image.fromarray(a, "RGBA").copy()):
         v = _native.rgba_array(img)
         assert v.shape == (60, 40, 4) and v.dtype == np.uint8 and np.array_equal(v, a)
+    owned = Image.fromarray(a, "RGBA").copy()
+    owned.putpixel((3, 5), (9, 8, 7, 6))  # a view (or a copy taken now) shows the pixels as they are at call time
+    assert tuple(_native.rgba_array(owned)[5, 3]) == (9, 8, 7, 6)
     big = Image.new("RGBA", (3000, 1500), (1, 2, 3, 4))  # 18 MB: more than one 16 MB block
-    assert tuple(_native.rgba_array(big)[1499, 2999]) == (1, 2, 3, 4)
-    out = a.copy()
-    tagged = _native.image_from_rgba(out)
-    assert _native.rgba_array(tagged) is out
-    tagged.putpixel((0, 0), (9, 9, 9, 9))  # copy-on-write: the tag no longer applies
-    v = _native.rgba_array(tagged)
-    assert v is not out and tuple(v[0, 0]) == (9, 9, 9, 9) and tuple(out[0, 0]) == tuple(a[0, 0])
-    assert not hasattr(tagged.copy(), "_b200_rgba")
+    big.putpixel((2999, 1499), (5, 6, 7, 8))
+    v = _native.rgba_array(big)
+    assert v.shape == (1500, 3000, 4) and tuple(v[1499, 2999]) == (5, 6, 7, 8) and tuple(v[0, 0]) == (1, 2, 3, 4)
+    img = _native.image_from_rgba(a.copy())
+    assert img.mode == "RGBA" and img.size == (40, 60) and np.array_equal(np.asarray(img), a)
+    # a real mutable image: pixel-access writes, putpixel and paste all work in place (the reference's result is
+    # `background_img.copy()`, compositor.py:11)
+    assert not getattr(img, "readonly", 0)
+    px = img.load()
+    px[0, 0] = (1, 1, 1, 1)
+    img.putpixel((1, 0), (2, 2, 2, 2))
+    img.paste((3, 3, 3, 3), (2, 0, 3, 1))
+    assert img.getpixel((0, 0)) == (1, 1, 1, 1) and img.getpixel((1, 0)) == (2, 2, 2, 2) and img.getpixel((2, 0)) == (3, 3, 3, 3)
+    fresh, view = _native.new_rgba_image(7, 5)
+    if fresh is not None:
+        view[...] = 11
+        assert fresh.getpixel((6, 4)) == (11, 11, 11, 11)
+        fresh.putpixel((0, 0), (1, 2, 3, 4))
+        assert tuple(view[0, 0]) == (1, 2, 3, 4)  # the view IS the image's memory
