@@ -327,6 +327,7 @@ struct LeanCtx {
     uint8_t *d_bg = nullptr, *d_out = nullptr, *d_pool = nullptr;
     size_t d_bg_cap = 0, d_out_cap = 0, d_pool_cap = 0;
     int *h_status = nullptr;
+    std::vector<cudaEvent_t> events;  // one per copy-out chunk, created once
 
     void release() {
         if (device >= 0) {
@@ -340,6 +341,7 @@ struct LeanCtx {
             if (d_out) cudaFree(d_out);
             if (d_pool) cudaFree(d_pool);
             if (h_status) cudaFreeHost(h_status);
+            for (cudaEvent_t e : events) cudaEventDestroy(e);
             if (st) cudaStreamDestroy(st);
             if (cur != device) cudaSetDevice(cur);
         }
@@ -375,18 +377,36 @@ struct LeanCtx {
 };
 thread_local LeanCtx g_lean;
 
+// host memcpy of `rows` rows; large copies (a 4K canvas is 33 MB) are split over a few threads -- one core moves
+// about 10 GB/s, which would make the host copy, not PCIe, the slowest stage of a single-canvas call
+void copy_rows(uint8_t *dst, size_t dst_pitch, const uint8_t *src, size_t src_pitch, size_t row_bytes, int rows) {
+    auto part = [=](int r0, int r1) {
+        if (dst_pitch == src_pitch && row_bytes + 16 > dst_pitch) {
+            std::memcpy(dst + (size_t)r0 * dst_pitch, src + (size_t)r0 * src_pitch, (size_t)(r1 - r0) * dst_pitch - (dst_pitch - row_bytes));
+        } else {
+            for (int r = r0; r < r1; ++r) std::memcpy(dst + (size_t)r * dst_pitch, src + (size_t)r * src_pitch, row_bytes);
+        }
+    };
+    const size_t bytes = row_bytes * (size_t)rows;
+    const int n_thr = bytes >= ((size_t)8 << 20) ? (int)std::min<size_t>(4, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (n_thr <= 1 || rows < n_thr) {
+        part(0, rows);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_thr; ++t) th.emplace_back(part, (int)((int64_t)rows * t / n_thr), (int)((int64_t)rows * (t + 1) / n_thr));
+    part(0, (int)((int64_t)rows / n_thr));
+    for (auto &t : th) t.join();
+}
+
 // rows of a pageable (or pinned) host image -> device, through the pinned bounce buffer in ~4 MB chunks
 void upload_rows(uint8_t *dev, size_t dev_pitch, const uint8_t *host, size_t host_pitch, size_t row_bytes, int rows,
                  uint8_t *pin, cudaStream_t st) {
-    const int chunk_rows = (int)std::max<size_t>(1, ((size_t)4 << 20) / std::max<size_t>(1, dev_pitch));
+    const int chunk_rows = (int)std::max<size_t>(1, ((size_t)8 << 20) / std::max<size_t>(1, dev_pitch));
     for (int r0 = 0; r0 < rows; r0 += chunk_rows) {
         const int n = std::min(chunk_rows, rows - r0);
         uint8_t *p = pin + (size_t)r0 * dev_pitch;
-        if (host_pitch == dev_pitch) {
-            std::memcpy(p, host + (size_t)r0 * host_pitch, (size_t)n * dev_pitch);
-        } else {
-            for (int r = 0; r < n; ++r) std::memcpy(p + (size_t)r * dev_pitch, host + (size_t)(r0 + r) * host_pitch, row_bytes);
-        }
+        copy_rows(p, dev_pitch, host + (size_t)r0 * host_pitch, host_pitch, row_bytes, n);
         cudaMemcpyAsync(dev + (size_t)r0 * dev_pitch, p, (size_t)n * dev_pitch, cudaMemcpyHostToDevice, st);
     }
 }
@@ -476,13 +496,21 @@ int b200comp_composite_host_ex(const uint8_t *bg, uint32_t solid_rgba, int W, in
     }
     // copy-out in chunks: while the copy engine fills the next chunk of the pinned buffer, the host copies the
     // previous one into the caller's (pageable) canvas
-    const int chunk_rows = (int)std::max<size_t>(1, ((size_t)4 << 20) / dp);
+    const int chunk_rows = (int)std::max<size_t>(1, ((size_t)8 << 20) / dp);
     const int n_chunks = (H + chunk_rows - 1) / chunk_rows;
-    std::vector<cudaEvent_t> evs((size_t)n_chunks, nullptr);
+    while ((int)cx.events.size() < n_chunks) {
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            cudaStreamSynchronize(st);
+            b200comp_plan_destroy(plan);
+            return b200comp_set_error_(B200COMP_ECUDA, "composite_host: event creation failed");
+        }
+        cx.events.push_back(ev);
+    }
+    std::vector<cudaEvent_t> &evs = cx.events;
     for (int c = 0; c < n_chunks; ++c) {
         const int r0 = c * chunk_rows, n = std::min(chunk_rows, H - r0);
         cudaMemcpyAsync(cx.pin_out + (size_t)r0 * dp, cx.d_out + (size_t)r0 * dp, (size_t)n * dp, cudaMemcpyDeviceToHost, st);
-        cudaEventCreateWithFlags(&evs[(size_t)c], cudaEventDisableTiming);
         cudaEventRecord(evs[(size_t)c], st);
     }
     cudaError_t e = cudaSuccess;
@@ -490,15 +518,8 @@ int b200comp_composite_host_ex(const uint8_t *bg, uint32_t solid_rgba, int W, in
         const int r0 = c * chunk_rows, n = std::min(chunk_rows, H - r0);
         const cudaError_t ec = cudaEventSynchronize(evs[(size_t)c]);
         if (ec != cudaSuccess) e = ec;
-        if (e == cudaSuccess) {
-            if (out_pitch == dp) {
-                std::memcpy(out + (size_t)r0 * out_pitch, cx.pin_out + (size_t)r0 * dp, (size_t)n * dp);
-            } else {
-                for (int r = 0; r < n; ++r)
-                    std::memcpy(out + (size_t)(r0 + r) * out_pitch, cx.pin_out + (size_t)(r0 + r) * dp, (size_t)W * 4);
-            }
-        }
-        cudaEventDestroy(evs[(size_t)c]);
+        if (e == cudaSuccess)
+            copy_rows(out + (size_t)r0 * out_pitch, out_pitch, cx.pin_out + (size_t)r0 * dp, dp, (size_t)W * 4, n);
     }
     const int status = *cx.h_status;  // travelled on the stream ahead of the canvas
     b200comp_plan_destroy(plan);      // (its stream is idle: every chunk event has fired)

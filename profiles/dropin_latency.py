@@ -50,8 +50,8 @@ def main():
         if "bundle" not in c:
             continue
         bg, objs, pls, exp = G.case(name)
-        bg_i = Image.fromarray(bg, "RGBA")
-        objs_i = {k: Image.fromarray(v, "RGBA") for k, v in objs.items()}
+        bg_i = Image.fromarray(bg, "RGBA").copy()  # images Pillow owns, as Image.open(...).convert("RGBA") returns
+        objs_i = {k: Image.fromarray(v, "RGBA").copy() for k, v in objs.items()}
         out = compositor.composite(bg_i, objs_i, pls)
         assert np.array_equal(np.asarray(out), exp), name
         rows.append({"case": name, "canvas": list(bg_i.size), "placements": len(pls),
@@ -62,14 +62,35 @@ def main():
     sizes = {k: (v.shape[1], v.shape[0]) for k, v in pool.items()}
     pls = synth.workload_placements("c3_4k_20obj", sizes, 0)
     bg_i = Image.new("RGBA", (3840, 2160), (38, 73, 115, 255))
-    objs_i = {k: Image.fromarray(v, "RGBA") for k, v in pool.items()}
+    objs_i = {k: Image.fromarray(v, "RGBA").copy() for k, v in pool.items()}
     a = np.asarray(compositor.composite(bg_i, objs_i, pls))
     b = np.asarray(pil_composite(bg_i, objs_i, pls))
     assert np.array_equal(a, b)
     rows.append({"case": "c3_4k_20obj canvas 0", "canvas": [3840, 2160], "placements": len(pls),
                  "b200_ms": med(lambda: compositor.composite(bg_i, objs_i, pls), 10),
                  "pillow_ms": med(lambda: pil_composite(bg_i, objs_i, pls), 3)})
-    print(json.dumps({"rows": rows}, indent=1))
+    # the refine loop of macro_placement_test.py:1679-1699 on the squarespace bundle: reload the bundle, composite
+    ref = os.path.join(ROOT, "baseline", "_ref", "output", "squarespace")
+    loop = None
+    if os.path.isdir(ref):
+        bg_i = Image.new("RGBA", (492, 492), (220, 238, 245, 255))
+        probe = compositor.load_object_images(os.path.join(ref, "results.json"))
+        pls = [{"object_id": k, "box": [20 + 30 * i, 15 + 90 * i, 20 + 30 * i + im.size[0], 15 + 90 * i + im.size[1]]}
+               for i, (k, im) in enumerate(sorted(probe.items()))]
+
+        def b200_iter():
+            return compositor.composite(bg_i, compositor.load_object_images(os.path.join(ref, "results.json")), pls)
+
+        def pillow_iter():
+            with open(os.path.join(ref, "results.json")) as f:
+                items = json.load(f)
+            objs = {int(it["object_id"]): Image.open(os.path.join(ref, it["filename"])).convert("RGBA") for it in items}
+            return pil_composite(bg_i, objs, pls)
+
+        assert np.array_equal(np.asarray(b200_iter()), np.asarray(pillow_iter()))
+        loop = {"case": "refine-loop iteration: load_object_images + composite (squarespace, 492x492, identity sizes)",
+                "b200_ms": med(b200_iter, 30), "pillow_ms": med(pillow_iter, 30)}
+    print(json.dumps({"rows": rows, "refine_loop": loop}, indent=1))
 
 
 if __name__ == "__main__":
