@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fresh-plan", action="store_true", help="skip the new-plan-every-step measurement")
+    ap.add_argument("--stats-in-step", action="store_true",
+                    help="every step also computes the fill_solid statistics (masked median) of a background of the canvas "
+                         "size and synthesises the canvases from that colour in-kernel (default for c5_8k_64obj)")
     ap.add_argument("--solid-bg", action="store_true", help="synthesise the solid background in-kernel (no bg read)")
     return ap.parse_args()
 
@@ -163,9 +166,10 @@ def bg_colour(i: int):
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_port_throughput(pool, canvases, placements, n_threads: int, repeats: int = 1):
+def cpu_port_throughput(pool, canvases, placements, n_threads: int, repeats: int = 1, keep=None):
     """Oracle port (oracle/compositor_oracle.c) of the reference composite(), one canvas per
-    task on `n_threads` host threads (ctypes releases the GIL)."""
+    task on `n_threads` host threads (ctypes releases the GIL).  `keep`: a list that receives the composited
+    canvases (the parity check of the end-to-end leg compares every one of them with the GPU's)."""
     import oracle
 
     oracle.lib()
@@ -174,9 +178,13 @@ def cpu_port_throughput(pool, canvases, placements, n_threads: int, repeats: int
         b = np.empty((H, W, 4), np.uint8)
         b[...] = bg_colour(i)
         bgs.append(b)
+    if keep is not None:
+        keep[:] = [None] * len(canvases)
 
     def one(i):
-        oracle.composite(bgs[i], pool, placements[i])
+        out = oracle.composite(bgs[i], pool, placements[i])
+        if keep is not None:
+            keep[i] = out
         return canvases[i][0] * canvases[i][1]
 
     best = None
@@ -189,17 +197,37 @@ def cpu_port_throughput(pool, canvases, placements, n_threads: int, repeats: int
     return px / 1e6 / best, len(canvases) / best, best
 
 
+def reference_composite():
+    """The UNMODIFIED composite() of the reference (compositor.py:6-22) from baseline/_ref (a copy of /root/reference
+    made by baseline/install_ref.sh; git-ignored, shipped to the GPU box), or None where that copy is missing."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "_ref", "compositor.py")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_reference_compositor", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.composite
+
+
 def pillow_throughput(pool, canvases, placements, n_threads: int):
-    """Same sample through Pillow itself (the library the reference calls), for information."""
+    """Same sample through the reference's own composite() (Python over Pillow; Pillow releases the GIL, so one canvas
+    per task on the host threads is what multiprocessing would give).  Falls back to the same loop written out with
+    PIL calls where baseline/_ref is missing."""
     try:
         from PIL import Image
     except Exception:
         return None
-    ims = {k: Image.fromarray(v) for k, v in pool.items()}
+    ims = {k: Image.fromarray(v).copy() for k, v in pool.items()}
+    ref = reference_composite()
 
     def one(i):
         W, H = canvases[i]
         c = Image.new("RGBA", (W, H), bg_colour(i))
+        if ref is not None:
+            ref(c, ims, placements[i])
+            return W * H
         for p in placements[i]:
             x1, y1, x2, y2 = (int(v) for v in p["box"])
             r = ims[p["object_id"]].resize((max(1, x2 - x1), max(1, y2 - y1)), Image.LANCZOS)
@@ -232,6 +260,13 @@ def run_reference(args):
     dt = float(np.mean(times))
     value = px / 1e6 / dt
     W, H = canvases[0]
+    # the reference itself (unmodified compositor.py over Pillow, baseline/_ref) on the same sample: slower than the
+    # port, so the port stays the line's value (the conservative denominator of the speed-up)
+    ref_line = None
+    if reference_composite() is not None:
+        pv = pillow_throughput(pool, canvases, placements, cores)
+        ref_line = {"value": pv, "unit": UNIT, "cores": cores,
+                    "what": "compositor.composite from baseline/_ref (copy of /root/reference), one canvas per task"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
         "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -240,7 +275,8 @@ def run_reference(args):
                    "canvases_per_step": sample, "canvases_per_s": sample / dt},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} canvases of {args.workload} per step, one canvas per task on {cores} threads "
-                                   "(oracle/compositor_oracle.c; the reference path is Python over Pillow, not compilable)"},
+                                   "(oracle/compositor_oracle.c; the reference path is Python over Pillow, not compilable)",
+                         "unmodified_reference": ref_line},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -267,6 +303,10 @@ def run_b200(args):
     dev = torch.device("cuda", local)
 
     wl = synth.WORKLOADS[args.workload]
+    if args.workload == "c5_8k_64obj":  # BASELINE.json configs[4]: "+ background colour synthesis"
+        args.stats_in_step = True
+    if args.stats_in_step:
+        args.solid_bg = True
     batch = args.batch or wl["batch"]
     W0, H0 = synth.workload_canvas_size(args.workload, 0)
     free_b, _ = torch.cuda.mem_get_info()
@@ -293,6 +333,17 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    stats_bg = None
+    if args.stats_in_step:
+        # one decoded background.png of the canvas size per step (binary alpha, ~30 % transparent, smooth RGB + noise)
+        stats_bg = torch.from_numpy(synth.synthetic_background(W0, H0)).to(dev)
+        run_plan = cb.run
+
+        def run_step():
+            B.masked_median_rgb(stats_bg)  # background_resizing.py:11-22; the colour goes back to the host, as fill_solid needs it
+            run_plan()
+
+        cb.run = run_step
     for _ in range(max(3, args.warmup)):
         cb.run()
     cb.check()
@@ -316,8 +367,10 @@ def run_b200(args):
     ms_step = ms_total / args.steps
     px_step_rank = sum(w * h for w, h in canvases)
     value = world * px_step_rank / 1e6 / (ms_step / 1e3)
-    algo = cb.algorithmic_bytes
+    algo = cb.algorithmic_bytes + (W0 * H0 * 4 if args.stats_in_step else 0)
     info = dict(cb.info)
+    if args.stats_in_step:
+        cb.run = run_plan  # (the phase split and the fresh-plan leg below time the compositor alone)
     achieved = algo / 1e9 / (ms_step / 1e3)
     peak, peak_src = measured_peak()
     ratio, ratio_src = traffic_ratio()
@@ -390,6 +443,7 @@ def run_b200(args):
 
     # ---- end to end: host buffers through the C ABI (H2D cutouts + backgrounds, D2H canvases) ----
     e2e = None
+    e2e_out = None
     if not args.no_e2e:
         cb.close()
         del cb, bgs
@@ -398,11 +452,11 @@ def run_b200(args):
         L = _native.lib()
         import ctypes
 
-        host_bg = None if args.solid_bg else torch.empty((nb, H0 * W0 * 4), dtype=torch.uint8, pin_memory=True)
-        host_out = torch.empty((nb, H0 * W0 * 4), dtype=torch.uint8, pin_memory=True)
-        uniform = all(c == (W0, H0) for c in canvases[:nb])
-        if not uniform:
-            raise SystemExit("e2e leg expects uniform canvases; use --no-e2e for mixed-size workloads")
+        maxb = max(w * h * 4 for (w, h) in canvases[:nb])  # (C4 mixes aspect ratios of one pixel budget)
+        e2e_px = sum(w * h for (w, h) in canvases[:nb])
+        host_bg = None if args.solid_bg else torch.empty((nb, maxb), dtype=torch.uint8, pin_memory=True)
+        host_out = torch.empty((nb, maxb), dtype=torch.uint8, pin_memory=True)
+        e2e_out = host_out
         host_pool = {}
         pool_bytes = 0
         for k, v in pool.items():
@@ -412,7 +466,8 @@ def run_b200(args):
             pool_bytes += v.nbytes
         if host_bg is not None:
             for i in range(nb):
-                host_bg[i].view(H0, W0, 4).numpy()[...] = solids[i]
+                wi, hi = canvases[i]
+                host_bg[i][: wi * hi * 4].view(hi, wi, 4).numpy()[...] = solids[i]
         sizes = {k: (v.shape[1], v.shape[0]) for k, v in pool.items()}
         from image_transformation_b200.compositor import resolve_placements
 
@@ -421,9 +476,10 @@ def run_b200(args):
         for i in range(nb):
             res = resolve_placements(placements[i], sizes)
             r, g, b_, a = solids[i]
-            cvs[i] = _native.Canvas(host_out[i].data_ptr(), W0 * 4, host_bg[i].data_ptr() if host_bg is not None else None,
-                                    W0 * 4 if host_bg is not None else 0, r | (g << 8) | (b_ << 16) | (a << 24),
-                                    W0, H0, len(recs), len(res), 0)
+            wi, hi = canvases[i]
+            cvs[i] = _native.Canvas(host_out[i].data_ptr(), wi * 4, host_bg[i].data_ptr() if host_bg is not None else None,
+                                    wi * 4 if host_bg is not None else 0, r | (g << 8) | (b_ << 16) | (a << 24),
+                                    wi, hi, len(recs), len(res), 0)
             recs.extend(res)
         pls = (_native.Placement * len(recs))()
         used_pool = set()
@@ -452,9 +508,9 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        h2d = sum(pool[k].nbytes for k in used_pool) + (nb * W0 * H0 * 4 if host_bg is not None else 0)
-        e2e = {"value": world * nb * W0 * H0 / 1e6 / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(nb * W0 * H0 * 4), "canvases_per_step": nb, "ms_per_step": dt * 1e3,
+        h2d = sum(pool[k].nbytes for k in used_pool) + (e2e_px * 4 if host_bg is not None else 0)
+        e2e = {"value": world * e2e_px / 1e6 / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(e2e_px * 4), "canvases_per_step": nb, "ms_per_step": dt * 1e3,
                "canvases_per_s": world * nb / dt,
                "api": "b200comp_composite_batch_host (pinned host buffers; coefficient tables rebuilt every step)"}
         # For information: the same call when the caller states the canvases' solid colour (what fill_solid
@@ -470,7 +526,7 @@ def run_b200(args):
             for _ in range(args.e2e_steps):
                 _native.check(L.b200comp_composite_batch_host(cvs_solid, nb, pls, len(recs), n_threads, args.e2e_chunk, 3), "composite_batch_host")
             dts = (time.perf_counter() - t0) / args.e2e_steps
-            e2e["solid_canvas_variant"] = {"value": nb * W0 * H0 / 1e6 / dts, "unit": UNIT, "canvases_per_s": nb / dts,
+            e2e["solid_canvas_variant"] = {"value": e2e_px / 1e6 / dts, "unit": UNIT, "canvases_per_s": nb / dts,
                                            "h2d_bytes_per_step": int(sum(pool[k].nbytes for k in used_pool)),
                                            "note": "same batch with the canvases' colour passed as a value (no background upload); informational"}
         # spot-check one e2e canvas against the device-resident result path's oracle
@@ -480,7 +536,7 @@ def run_b200(args):
             bg0 = np.empty((H0, W0, 4), np.uint8)
             bg0[...] = solids[0]
             exp = oracle.composite(bg0, pool, placements[0])
-            if not np.array_equal(host_out[0].view(H0, W0, 4).numpy(), exp):
+            if not np.array_equal(host_out[0][: W0 * H0 * 4].view(H0, W0, 4).numpy(), exp):
                 raise SystemExit("bench.py: e2e canvas 0 differs from the oracle -- refusing to report a number")
 
     # ---- CPU baseline (rank 0, N=1 only) ----
@@ -489,13 +545,26 @@ def run_b200(args):
         cores = host_cores()
         sample = args.cpu_sample or max(8, min(4 * cores, 64))  # about 25 s of CPU work: four canvases per thread
         sample = min(sample, batch)
-        v, cps, dt = cpu_port_throughput(pool, canvases[:sample], placements[:sample], cores)
+        kept = []
+        v, cps, dt = cpu_port_throughput(pool, canvases[:sample], placements[:sample], cores, keep=kept)
+        # every canvas the CPU arm composited against the GPU's end-to-end result of the same canvas (bit for bit)
+        if e2e is not None:
+            checked = 0
+            for i in range(min(sample, e2e["canvases_per_step"])):
+                wi, hi = canvases[i]
+                if not np.array_equal(e2e_out[i][: wi * hi * 4].view(hi, wi, 4).numpy(), kept[i]):
+                    raise SystemExit(f"bench.py: e2e canvas {i} differs from the oracle -- refusing to report a number")
+                checked += 1
+            e2e["parity_checked_canvases"] = checked
+        del kept
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "canvases_per_s": cps,
                "sample": f"{sample} canvases of {args.workload} (same placements/pool), one canvas per task on {cores} "
                          f"threads, {dt:.1f} s of wall time; oracle/compositor_oracle.c"}
         pv = pillow_throughput(pool, canvases[:sample], placements[:sample], cores)
         if pv is not None:
             cpu["pillow_same_sample"] = pv
+            cpu["pillow_same_sample_is"] = ("unmodified reference composite() from baseline/_ref" if reference_composite()
+                                            else "the reference's loop written out with PIL calls (baseline/_ref missing)")
 
     if rank == 0:
         line = {
@@ -504,7 +573,9 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload, "canvas": [W0, H0], "objects_per_canvas": wl["n_objects"],
                        "canvases_per_gpu_per_step": batch, "canvases_per_s": world * batch / (ms_step / 1e3),
-                       "background": "solid colour synthesised in-kernel" if args.solid_bg else "per-canvas RGBA buffer read from HBM",
+                       "background": ("masked-median statistics of a canvas-sized background every step, canvases synthesised "
+                                      "in-kernel from the colour" if args.stats_in_step else
+                                      "solid colour synthesised in-kernel" if args.solid_bg else "per-canvas RGBA buffer read from HBM"),
                        "l2": f"inputs+outputs {algo / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
                        "parallelism": f"canvas-sharded x{world}, no collective",
                        "fused_placements": info["fused_placements"], "identity_placements": info["identity_placements"],

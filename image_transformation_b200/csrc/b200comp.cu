@@ -704,6 +704,37 @@ int b200comp_resize_rgba_lanczos(const uint8_t *src, int sw, int sh, size_t src_
         return resample_two_pass(src, sw, sh, (int64_t)src_pitch, dst, w, h, (int64_t)dst_pitch, nullptr, nullptr, 0,
                                  nullptr, nullptr, 0, nullptr, flags, st);
     keep_pool_memory();
+    // The fused tile kernel in "replace" mode onto a canvas that is the destination: prepared planar source, TMA patch
+    // chunks, dp4a passes, device-built coefficient tables (scales down to 2.66x; buffers of any 4-byte alignment).
+    // Only what it cannot take -- more taps, Pillow 12's vertical-first order -- goes through the generic kernels below.
+    {
+        const bool need_h = w != sw, need_v = h != sh;
+        const bool vertical_first = (flags & B200COMP_VERTICAL_FIRST) && need_h && need_v;
+        const int nwx = need_h ? packed_words(lanczos_ksize(sw, w)) : 3, nwy = need_v ? packed_words(lanczos_ksize(sh, h)) : 3;
+        if (!vertical_first && nwx > 0 && nwy > 0 && src_pitch <= (size_t)INT32_MAX && sw < 262144 && sh < 262144) {
+            b200comp_canvas cv;
+            std::memset(&cv, 0, sizeof cv);
+            cv.out = dst;
+            cv.out_pitch = (int64_t)dst_pitch;
+            cv.W = w;
+            cv.H = h;
+            cv.n_placements = 1;
+            b200comp_placement pl;
+            std::memset(&pl, 0, sizeof pl);
+            pl.src = src;
+            pl.src_pitch = (int64_t)src_pitch;
+            pl.sw = sw; pl.sh = sh; pl.w = w; pl.h = h;
+            pl.flags = B200COMP_REPLACE;
+            b200comp_plan *plan = nullptr;
+            const int rc = b200comp_plan_create(&cv, 1, &pl, 1, 1, stream, &plan);
+            if (rc == 0) {
+                const int rr = b200comp_plan_run(plan, stream);
+                b200comp_plan_destroy(plan);  // frees are ordered on `stream`, behind the run
+                return rr;
+            }
+            if (rc != B200COMP_EINVAL) return rc;  // EINVAL: the placement needs more shared memory than the fused kernel has
+        }
+    }
     TableSet ts;
     TableRef tx, ty;
     if (w != sw) tx = ts.want_legacy(sw, w);
@@ -875,6 +906,8 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         d.sw = p.sw; d.sh = p.sh;
         d.x = p.x; d.y = p.y; d.w = p.w; d.h = p.h;
         if (p.w == p.sw && p.h == p.sh) {
+            if (p.flags & B200COMP_REPLACE)
+                return fail(B200COMP_EINVAL, "plan_create: B200COMP_REPLACE needs a placement the fused kernel resamples");
             d.mode = 0;
             ++n_ident;
             continue;
@@ -902,6 +935,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             d.nwx = tref[i].first.ks;
             d.nwy = tref[i].second.ks;
             d.pwc = pwc;
+            d.replace = (p.flags & B200COMP_REPLACE) ? 1 : 0;
             // the kernel recomputes each window start from these doubles exactly as the table builder does;
             // a skipped pass is the 1-tap identity: scale 1, support 1 -> first tap = the sample itself
             d.scale_x = need_h ? (double)p.sw / p.w : 1.0;
@@ -912,6 +946,8 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             max_iw = std::max(max_iw, iw);
             ++n_fused;
         } else {
+            if (p.flags & B200COMP_REPLACE)
+                return fail(B200COMP_EINVAL, "plan_create: B200COMP_REPLACE needs a placement the fused kernel resamples");
             // pre-resample with the generic kernels; the tile kernel then sees an identity-size overlay
             b200comp_plan::Pre pr;
             pr.src = p.src; pr.sp = p.src_pitch; pr.sw = p.sw; pr.sh = p.sh; pr.w = p.w; pr.h = p.h;
@@ -1105,7 +1141,10 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
             for (size_t j = 0; j < hprep.size(); ++j) hprep[j].flags = plan->d_flags + flag_off[j];
             CUDA_TRY(cudaMemcpyAsync(plan->d_prep, hprep.data(), hprep.size() * sizeof(PrepDesc), cudaMemcpyHostToDevice, st));
             plan->n_prep = (int)hprep.size();
-            plan->prep_blocks_x = (int)std::max<int64_t>(1, std::min<int64_t>((max_words + 255) / 256, 64));
+            // grid.y = cutouts; grid.x = enough blocks that a plan with one large cutout (the stand-alone resize) still
+            // fills the GPU, and not more than one block per 256 items of the largest cutout
+            plan->prep_blocks_x = (int)std::max<int64_t>(1, std::min<int64_t>((max_words + 255) / 256,
+                                                                              std::max<int64_t>(64, 148 * 16 / (int64_t)hprep.size())));
         }
         // 2-D maps: u32 pixels x rows.  Overlays composited as they are: 68 x 16-pixel boxes (one chunk each).
         // Canvases: 32-pixel x kTileH-row boxes with the 128-byte swizzle (tile_kernel.cuh ct_off).  Buffers TMA cannot

@@ -111,7 +111,7 @@ struct DevPlacementT {
     int32_t nwx, nwy;      // words per output sample (3, 4 or 5)
     int32_t mode;          // 0 = plain over, 1 = resample in the tile kernel
     int32_t pwc;           // patch width class: word columns (4 pixels of one channel) per chunk row
-    int32_t pad_;
+    int32_t replace;       // mode 1: store the resampled pixel instead of compositing it (stand-alone resize)
     int32_t wq, sh4;       // alpha summary extent: blocks per row, block rows
 };
 static_assert(sizeof(DevPlacementT) == 128, "DevPlacementT layout");
@@ -399,7 +399,8 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
                 const Geo g = tile_geometry(d, tx0, ty0, tx1, ty1);
                 occludes = ((om >> lane) & 1u) && g.two == tx1 - tx0 && g.tho == ty1 - ty0;
                 w[0] = kCmdResample;
-                w[1] = (uint32_t)d.nwx | ((uint32_t)d.nwy << 8) | (((om >> lane) & 1u) ? (3u << 16) : (4u << 16)) | ((uint32_t)g.NRQ << 24);
+                w[1] = (uint32_t)d.nwx | ((uint32_t)d.nwy << 8) | (((om >> lane) & 1u) ? (3u << 16) : (4u << 16)) |
+                       (d.replace ? (0x80u << 16) : 0u) | ((uint32_t)g.NRQ << 24);
                 w[2] = (uint32_t)(g.ix0 - tx0) | ((uint32_t)(g.iy0 - ty0) << 8) | ((uint32_t)g.two << 16) | ((uint32_t)g.tho << 24);
                 w[3] = (uint32_t)g.ox0;
                 w[4] = (uint32_t)g.oy0;
@@ -579,15 +580,17 @@ __device__ __forceinline__ void vcol3(const uint4 (&v)[NW], uint32_t cpx, const 
     acc[2] = tap_sum<NW>(wd, k0, k1, k2);
     sts32(cpx, pack2_clip(acc[0], acc[1], pack2_clip(acc[2], 255 << kPrecisionBits, 0u)));
 }
+// `replace`: the stand-alone resampler (Image.resize, no over): the un-premultiplied pixel is stored whatever its
+// alpha -- Convert.c rgba2rgbA keeps the colours of a pixel whose alpha resampled to 0.
 template <int NW>
 __device__ __forceinline__ void vcol4(const uint4 (&v)[NW], uint32_t cpx, const uint32_t (&k0)[NW],
-                                      const uint32_t (&k1)[NW], const uint32_t (&k2)[NW]) {
+                                      const uint32_t (&k1)[NW], const uint32_t (&k2)[NW], bool replace) {
     uint32_t wd[NW];
     int32_t acc[4];
 #pragma unroll
     for (int i = 0; i < NW; ++i) wd[i] = v[i].w;
     acc[3] = tap_sum<NW>(wd, k0, k1, k2);
-    if (acc[3] < (1 << kPrecisionBits)) return;
+    if (acc[3] < (1 << kPrecisionBits) && !replace) return;
 #pragma unroll
     for (int i = 0; i < NW; ++i) wd[i] = v[i].x;
     acc[0] = tap_sum<NW>(wd, k0, k1, k2);
@@ -598,16 +601,16 @@ __device__ __forceinline__ void vcol4(const uint4 (&v)[NW], uint32_t cpx, const 
     for (int i = 0; i < NW; ++i) wd[i] = v[i].z;
     acc[2] = tap_sum<NW>(wd, k0, k1, k2);
     uint32_t s = pack2_clip(acc[0], acc[1], pack2_clip(acc[2], acc[3], 0u));
-    if (acc[3] < (255 << kPrecisionBits)) s = over_unpremul_px(lds32(cpx), s);
+    if (replace) s = unpremultiply_px(s);
+    else if (acc[3] < (255 << kPrecisionBits)) s = over_unpremul_px(lds32(cpx), s);
     sts32(cpx, s);
 }
 
 template <int NW, int NCH>
 __device__ __forceinline__ void slab_vpass(const uint32_t *__restrict__ Iw, int CS, uint32_t *__restrict__ ct, int xa, int xb,
                                            int col0, int rw0, int oy0, int tho, int dy, double scale, double support,
-                                           const uint32_t *__restrict__ ply, int n_out) {
+                                           const uint32_t *__restrict__ ply, bool replace) {
     const int lane = threadIdx.x & 31;
-    (void)n_out;
     uint32_t CSb = 4u * (uint32_t)CS;
     asm volatile("" : "+r"(CSb));
 #pragma unroll 1
@@ -639,7 +642,7 @@ __device__ __forceinline__ void slab_vpass(const uint32_t *__restrict__ Iw, int 
                 }
                 if (!__any_sync(0xffffffffu, any != 0u)) continue;
                 if (__all_sync(0xffffffffu, all == 0xffffffffu)) vcol3<NW>(v, cpx, k0, k1, k2);
-                else vcol4<NW>(v, cpx, k0, k1, k2);
+                else vcol4<NW>(v, cpx, k0, k1, k2, replace);
             }
         }
     }
@@ -850,7 +853,8 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
             if (kind == kCmdResample) {
                 const uint32_t w1 = uni(cmd.w[1]);
                 const int nwx = (int)(w1 & 0xffu), nwy = (int)((w1 >> 8) & 0xffu);
-                const int nch = (int)((w1 >> 16) & 0xffu), NRQ = (int)(w1 >> 24);
+                const int nch = (int)((w1 >> 16) & 0x7u), NRQ = (int)(w1 >> 24);
+                const bool replace = ((w1 >> 23) & 1u) != 0u;  // stand-alone resize: store, do not composite
                 if (xa >= xb) {
                     // not on this warp's slab: pass the chunks on
                     for (int q0 = 0; q0 < NRQ; q0 += kChunkQuads, ++cseq) {
@@ -894,7 +898,7 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                     __syncwarp();  // the slab's intermediate is complete
                     if (ready_pending) tile_wait();
 #define B200_VPASS(NWY, NCH_) \
-    slab_vpass<NWY, NCH_>(Iw, CS, ct, xa, xb, col0, rw0, oy0, tho, dy, scale_y, support_y, ply, n_out_y)
+    slab_vpass<NWY, NCH_>(Iw, CS, ct, xa, xb, col0, rw0, oy0, tho, dy, scale_y, support_y, ply, replace)
                     if (nch == 4) {
                         if (nwy == 3) B200_VPASS(3, 4);
                         else if (nwy == 4) B200_VPASS(4, 4);

@@ -43,6 +43,11 @@ enum b200comp_status {
  * b200comp_device_upload and reused over many calls -- the refine loop of macro_placement_test.py:1493-1513,
  * 1679-1699 re-composites the same bundle every iteration). */
 #define B200COMP_SRC_DEVICE 2
+/* Placement flag: the resampled cutout REPLACES the canvas pixels of its box instead of being composited onto them
+ * (`obj.resize((w, h), LANCZOS)` without the alpha_composite that follows it in compositor.py:20-21; Convert.c
+ * rgba2rgbA keeps the colours of pixels whose alpha resampled to 0).  Only for placements the fused kernel
+ * resamples (size != cutout size, scale down to 2.66x, no vertical-first order); b200comp_plan_create rejects others. */
+#define B200COMP_REPLACE 4
 
 int b200comp_abi_version(void);
 const char *b200comp_last_error(void);
