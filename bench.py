@@ -83,9 +83,13 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def traffic_ratio():
-    """dram bytes / algorithmic bytes of the fused kernel from the committed ncu capture."""
-    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+def traffic_ratio(workload="c3_4k_20obj"):
+    """dram bytes / algorithmic bytes of one plan run from the committed ncu launch list of that workload
+    (profiles/ncu_traffic.json for the headline workload, profiles/ncu_traffic_<tag>.json for the others)."""
+    tag = {"c3_4k_20obj": "", "c5_8k_64obj": "_c5", "c4_aspect_sweep": "_c4"}.get(workload)
+    if tag is None:
+        return None, None
+    path = os.path.join(ROOT, "profiles", f"ncu_traffic{tag}.json")
     try:
         with open(path) as f:
             d = json.load(f)
@@ -373,7 +377,7 @@ def run_b200(args):
         cb.run = run_plan  # (the phase split and the fresh-plan leg below time the compositor alone)
     achieved = algo / 1e9 / (ms_step / 1e3)
     peak, peak_src = measured_peak()
-    ratio, ratio_src = traffic_ratio()
+    ratio, ratio_src = traffic_ratio(args.workload)
     # per-kernel split of the step, measured live with CUDA events on the launching stream (a separate
     # pass of the same length, so the event records do not sit inside the timed region above)
     cb.profile(True)
@@ -397,6 +401,8 @@ def run_b200(args):
     if not args.no_fresh_plan:
         import concurrent.futures
 
+        cb.recreate()  # the C call alone, warm, nothing else running on the GPU
+        torch.cuda.synchronize()
         plan_c_s = cb.plan_create_s
         cb2 = B.CompositeBatch(dpool, canvases, placements, backgrounds=bgs, solid=solids, out=cb.out_buffer,
                                host_threads=host_cores())

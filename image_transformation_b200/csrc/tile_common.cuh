@@ -119,6 +119,13 @@ __device__ __forceinline__ void tma_store_2d(const void *tmap, int x, int y, con
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                  ::"l"(tmap), "r"(x), "r"(y), "r"(smem_u32(smem_src)) : "memory");
 }
+// TMA prefetch of a box into L2 (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_3d(const void *tmap, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const void *tmap, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tmap), "r"(x), "r"(y) : "memory");
+}
 // plain 1-D bulk copy global -> shared (command blocks); bytes a multiple of 16, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

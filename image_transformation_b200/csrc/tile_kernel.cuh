@@ -441,6 +441,9 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
     store_cmd(streams + base, w);
 }
 
+#ifndef B200COMP_L2_PREFETCH
+#define B200COMP_L2_PREFETCH 0  // measured +-0 (profiles/r2_tile_kernel_ab.txt): the patch loads are not what the warps wait for
+#endif
 // ---- the persistent tile kernel ------------------------------------------------------------------
 // Shared-memory rendezvous points of one CTA.  Every ring uses the n-th use of a slot <-> phase parity
 // (n / ring size) & 1 convention; a producer re-fills a slot only after the matching `empty` / `free` phase.
@@ -712,6 +715,26 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
             const Cmd &c = ring[s * kCmdBlk + e];
             const uint32_t kind = uni(c.w[0]);
             if (kind == kCmdEnd) break;
+#if B200COMP_L2_PREFETCH
+            // The record after this one, if its block is already here: start moving what it will load towards L2.  The
+            // ring holds about a third of a step's patch, so the real loads are issued well under a DRAM round trip
+            // before they are needed; from L2 they arrive in time.
+            if (lane == 0) {
+                const int pn = pos + 1, bn = pn / kCmdBlk, sn = bn % kCmdRing;
+                if (bn == b || (bn < nblk && mbar_try(&bars->c_full[sn], (bn / kCmdRing) & 1))) {
+                    const Cmd &n = ring[sn * kCmdBlk + pn % kCmdBlk];
+                    if (n.w[0] == kCmdResample) {
+                        const void *map = maps + ((uint64_t)n.w[8] << 7);
+                        const int nrq = (int)(n.w[1] >> 24), cw = 4 * (int)(n.w[5] & 0xffffu), rw = (int)(n.w[5] >> 16);
+                        for (int q0 = 0; q0 < nrq; q0 += kChunkQuads) tma_prefetch_3d(map, cw, 0, rw + q0);
+                    } else if (n.w[0] == kCmdTile && (n.w[6] & kTileBgTma)) {
+                        const void *map = reinterpret_cast<const void *>((uint64_t)n.w[8] | ((uint64_t)n.w[9] << 32));
+                        tma_prefetch_2d(map, (int)n.w[2], (int)n.w[3]);
+                        if ((int)(n.w[4] & 0xffffu) > 32) tma_prefetch_2d(map, (int)n.w[2] + 32, (int)n.w[3]);
+                    }
+                }
+            }
+#endif
             if (kind == kCmdTile) {
                 const int buf = tseq % kTileBufs;
                 if (tseq >= kTileBufs)

@@ -5,7 +5,7 @@
 usage: make_traffic.py <launches.csv> <bench json of the same command> <out json>
 
 The LAST step of the run is used: the launches from the last prepare_cutouts_kernel to the last
-composite_stream_kernel (prepare + 3 binning kernels + tile kernel = one b200comp_plan_run)."""
+composite_slab_kernel (prepare + 3 binning kernels + tile kernel = one b200comp_plan_run)."""
 import csv
 import json
 import sys
@@ -19,7 +19,7 @@ def main():
         d = launches.setdefault(int(r[0]), {"name": r[4].split("(")[0]})
         d[r[12]] = float(r[14].replace(",", ""))
     ids = sorted(launches)
-    last_tile = max(i for i in ids if launches[i]["name"].startswith("composite_stream_kernel"))
+    last_tile = max(i for i in ids if launches[i]["name"].startswith("composite_slab_kernel"))
     first = max(i for i in ids if i < last_tile and launches[i]["name"].startswith("prepare_cutouts_kernel"))
     step = [launches[i] for i in ids if first <= i <= last_tile]
     dram = sum(l["dram__bytes_read.sum"] + l["dram__bytes_write.sum"] for l in step)
