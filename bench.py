@@ -391,7 +391,8 @@ def run_b200(args):
         "binning_ms_per_step": prof["binning_ms"] / max(1, prof["runs"]),
         "prepare_ms_per_step": prof["prepare_ms"] / max(1, prof["runs"]),
         "tile_kernel_share_of_step": prof["tile_kernel_ms"] / split_total if split_total > 0 else None,
-        "how": "cudaEvent pairs around each phase of b200comp_plan_run on the launching stream",
+        "how": "cudaEvent pairs around each phase of b200comp_plan_run on the launching stream, in a separate pass with "
+               "the phases one after another (the timed steps overlap binning with the tile kernel, wave by wave)",
     }
 
     # ---- fresh layouts: a NEW plan (coefficient tables, tensor maps, descriptor uploads) for every step ----

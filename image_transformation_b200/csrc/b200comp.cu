@@ -568,6 +568,8 @@ using namespace b200comp;
 // =====================================================================================
 // Plan
 // =====================================================================================
+static constexpr int kMaxWaves = 16;  // sub-ranges of canvases a run is cut into (see b200comp_plan_run_canvases)
+
 struct b200comp_plan {
     int device = 0;
     cudaStream_t create_stream = nullptr;
@@ -600,15 +602,21 @@ struct b200comp_plan {
     int G = 1;                       // persistent CTAs = streams
     int64_t stream_capacity = 0;     // records (exact upper bound from the host-side box/tile count)
     Cmd *d_streams = nullptr;
-    int32_t *d_bin = nullptr;        // [G][K] per-tile slot counts, scanned in place
-    int64_t *d_stream_off = nullptr; // [G + 1]
-    int64_t *d_stream_len = nullptr; // [G] records per stream, END included
+    int32_t *d_bin = nullptr;        // per wave [G][K_wave] per-tile slot counts, scanned in place
+    int64_t *d_stream_off = nullptr; // [kMaxWaves][G + 2]: offsets, then the wave's record cursor
+    int64_t *d_stream_len = nullptr; // [kMaxWaves][G] records per stream, END included
     uint32_t *d_dbg = nullptr;       // 16 words written by the tile kernel's watchdog
     uint8_t *d_maps = nullptr;       // every CUtensorMap of the plan (placements, overlays, canvases)
     uint32_t *d_masks = nullptr;     // [tiles][mask_chunks][2] keep / opaque masks from the count kernel
     int4 *d_boxes = nullptr;         // destination boxes (x, y, w, h) of the placements: the binning hit test
     int mask_chunks = 1;             // ceil(max placements per canvas / 32)
     std::vector<int64_t> tiles_before;  // prefix sum of tiles per canvas (n_canvases + 1)
+    std::vector<int64_t> records_before;  // prefix sum of the record upper bounds per canvas (n_canvases + 1)
+    // waves of a run (b200comp_plan_run_canvases): binning of wave w+1 runs on `s_bin` under the tile kernel of
+    // wave w; tile kernels alternate between the caller's stream and `s_tile` so one fills the other's tail
+    cudaStream_t s_bin = nullptr, s_tile = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_tile = nullptr, ev_bin[kMaxWaves] = {};
+    int last_waves = 0;  // waves of the most recent run
     // b200comp_plan_profile: events around the phases of every run (4 per run: before prepare, before
     // binning, before the tile kernel, after it); a prepare without a run contributes nothing
     bool profile = false;
@@ -638,6 +646,15 @@ static void keep_pool_memory(int device) {
 static void keep_pool_memory() {
     int device = 0;
     if (cudaGetDevice(&device) == cudaSuccess) keep_pool_memory(device);
+}
+
+// number of waves a run over `count` canvases / `n_tiles` tiles is cut into (b200comp_plan_run_canvases)
+static int wave_count(const b200comp_plan *plan, int64_t n_tiles, int count) {
+    const char *e = std::getenv("B200COMP_WAVES");  // read at every run: the parity tests compare wave counts
+    const int forced = e && e[0] ? std::max(1, std::min(kMaxWaves, std::atoi(e))) : 0;
+    if (plan->profile) return 1;  // the phase events of b200comp_plan_profile want the phases one after another
+    int n = forced ? forced : (int)std::min<int64_t>(kMaxWaves, n_tiles / (32 * 2048));  // >= ~32 4K canvases per wave
+    return std::max(1, std::min(n, count));
 }
 
 static const size_t kMaxSmemBytes = 200 * 1024;    // opt-in dynamic shared memory limit we request
@@ -853,6 +870,11 @@ int b200comp_plan_destroy(b200comp_plan *plan) {
     for (void *p : plan->owned) cudaFreeAsync(p, plan->create_stream);
     for (cudaEvent_t e : plan->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : plan->prof_prepare) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : plan->ev_bin) if (e) cudaEventDestroy(e);
+    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    if (plan->ev_tile) cudaEventDestroy(plan->ev_tile);
+    if (plan->s_bin) cudaStreamDestroy(plan->s_bin);  // pending work (already joined into the caller's stream) still completes
+    if (plan->s_tile) cudaStreamDestroy(plan->s_tile);
     if (cur != plan->device) cudaSetDevice(cur);
     delete plan;
     return 0;
@@ -983,6 +1005,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         d.tiles_y = (cv.H + kTileH - 1) / kTileH;
         d.tile_base = tiles;
         plan->tiles_before.push_back(tiles);
+        plan->records_before.push_back(tiles + step_records);
         tiles += (int64_t)d.tiles_x * d.tiles_y;
         if ((int64_t)d.tiles_x * d.tiles_y > INT32_MAX) return fail(B200COMP_EINVAL, "plan_create: canvas too large");
         plan->max_tiles = std::max(plan->max_tiles, d.tiles_x * d.tiles_y);
@@ -998,6 +1021,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         }
     }
     plan->tiles_before.push_back(tiles);
+    plan->records_before.push_back(tiles + step_records);
     plan->n_tiles = tiles;
     {
         int sms = 148;
@@ -1212,10 +1236,12 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     // command streams: records + ring read-ahead slack; per-tile counts; stream offsets
     {
         const int64_t K = (tiles + plan->G - 1) / plan->G;
-        CUDA_TRY(dev_alloc((void **)&plan->d_streams, (size_t)(plan->stream_capacity + kCmdBlk) * sizeof(Cmd)));
-        CUDA_TRY(dev_alloc((void **)&plan->d_bin, (size_t)plan->G * (size_t)std::max<int64_t>(1, K) * sizeof(int32_t)));
-        CUDA_TRY(dev_alloc((void **)&plan->d_stream_off, (size_t)(plan->G + 1) * sizeof(int64_t)));
-        CUDA_TRY(dev_alloc((void **)&plan->d_stream_len, (size_t)plan->G * sizeof(int64_t)));
+        // every wave of a run has its own END records and read-ahead slack, its own rows of counts and offsets
+        CUDA_TRY(dev_alloc((void **)&plan->d_streams,
+                           (size_t)(plan->stream_capacity + (int64_t)kMaxWaves * (plan->G + kCmdBlk)) * sizeof(Cmd)));
+        CUDA_TRY(dev_alloc((void **)&plan->d_bin, (size_t)plan->G * (size_t)(std::max<int64_t>(1, K) + kMaxWaves) * sizeof(int32_t)));
+        CUDA_TRY(dev_alloc((void **)&plan->d_stream_off, (size_t)kMaxWaves * (plan->G + 2) * sizeof(int64_t)));
+        CUDA_TRY(dev_alloc((void **)&plan->d_stream_len, (size_t)kMaxWaves * plan->G * sizeof(int64_t)));
         CUDA_TRY(dev_alloc((void **)&plan->d_dbg, 16 * sizeof(uint32_t)));
         CUDA_TRY(cudaMemsetAsync(plan->d_dbg, 0, 16 * sizeof(uint32_t), st));
         int max_count = 1;
@@ -1258,7 +1284,8 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     CUDA_TRY(cudaFuncSetAttribute(composite_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemBytes));
 
     plan->info[B200COMP_INFO_ALGORITHMIC_BYTES] = algo;
-    plan->info[B200COMP_INFO_LAUNCHES_PER_RUN] = 4 + (plan->n_prep > 0 ? 1 : 0);  // 3 binning kernels + tile kernel
+    // 3 binning kernels + tile kernel per wave of a whole-plan run
+    plan->info[B200COMP_INFO_LAUNCHES_PER_RUN] = 4 * wave_count(plan, tiles, n_canvases) + (plan->n_prep > 0 ? 1 : 0);
     for (auto &pr : plan->pre) plan->info[B200COMP_INFO_LAUNCHES_PER_RUN] += (pr.w != pr.sw && pr.h != pr.sh) ? 2 : 1;
     plan->info[B200COMP_INFO_FUSED_PLACEMENTS] = n_fused;
     plan->info[B200COMP_INFO_IDENTITY_PLACEMENTS] = n_ident;
@@ -1305,7 +1332,15 @@ int b200comp_plan_prepare(b200comp_plan *plan, void *stream) {
     return 0;
 }
 
-// Stage 2: the fused tile kernel over canvases [first, first + count).
+// Stage 2: binning + the fused tile kernel over canvases [first, first + count).
+//
+// A large run is cut into waves of whole canvases.  Every wave has its own slice of the plan's binning buffers
+// (masks by absolute tile, count rows, stream offsets / lengths / cursor, a region of the record array), so the
+// waves only depend on the prepared cutouts.  Binning of all waves is queued on the plan's `s_bin`; the tile kernel of
+// wave w waits for its binning and runs on the caller's stream (even waves) or on `s_tile` (odd waves).  The binning
+// kernels are small blocks that fit beside the two resident tile CTAs of an SM, and most of their time is the HBM copy
+// of the tiles nothing is drawn on, which the issue-bound tile kernel leaves room for; the next wave's tile CTAs
+// fill the slots the previous wave's stragglers free.  Everything is joined back into the caller's stream.
 int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *stream) {
     if (!plan) return fail(B200COMP_EINVAL, "plan_run_canvases: null plan");
     if (first < 0 || count < 0 || (int64_t)first + count > plan->n_canvases)
@@ -1313,13 +1348,11 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
     cudaStream_t st = S(stream);
     if (count == 0) return 0;
     // Runs of one plan share its command-stream buffers: they must be ordered on the stream.
-    const int64_t tile0 = plan->tiles_before[(size_t)first];
-    const int64_t n_tiles = plan->tiles_before[(size_t)first + count] - tile0;
-    if (n_tiles >= (int64_t)1 << 31) return fail(B200COMP_EINVAL, "plan_run_canvases: more than 2^31 tiles in one run");
+    const int64_t run_tile0 = plan->tiles_before[(size_t)first];
+    const int64_t run_tiles = plan->tiles_before[(size_t)first + count] - run_tile0;
+    if (run_tiles >= (int64_t)1 << 31) return fail(B200COMP_EINVAL, "plan_run_canvases: more than 2^31 tiles in one run");
     const int G = plan->G;
-    const int K = (int)((n_tiles + G - 1) / G);
     const unsigned gx = (unsigned)((plan->max_tiles + kBinWarps - 1) / kBinWarps);  // warp = tile
-    unsigned long long *cursor = reinterpret_cast<unsigned long long *>(plan->d_stream_off + G);  // record allocator
     cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
     if (plan->profile) {
         for (auto &e : pe) {
@@ -1328,7 +1361,7 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
         }
         CUDA_TRY(cudaEventRecord(pe[0], st));
     }
-    // B200COMP_DEBUG_SYNC=1: synchronise after every launch so a device fault names its kernel
+    // B200COMP_DEBUG_SYNC=1: one wave, synchronise after every launch so a device fault names its kernel
     static const bool debug_sync = std::getenv("B200COMP_DEBUG_SYNC") != nullptr;
     auto checkpoint = [&](const char *what) -> int {
         if (!debug_sync) return 0;
@@ -1340,29 +1373,86 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
     // B200COMP_NO_CULL=1 keeps the steps an opaque, tile-covering later placement hides (A/B parity tests)
     const char *no_cull = std::getenv("B200COMP_NO_CULL");
     const int cull = !(no_cull && no_cull[0] == '1');
-    for (int c0 = first; c0 < first + count; c0 += 65535) {  // grid.y is limited to 65535 canvases per launch
-        const int nc = std::min(65535, first + count - c0);
-        bin_count_kernel<<<dim3(gx, (unsigned)nc), kBinWarps * 32, 0, st>>>(
-            plan->d_canvases + c0, plan->d_placements, plan->d_boxes, tile0, G, K, plan->d_bin, plan->d_masks,
-            plan->mask_chunks, plan->iw_words, c0 == first ? cursor : nullptr, plan->d_status, cull);
+
+    const int n_waves = debug_sync ? 1 : wave_count(plan, run_tiles, count);
+    plan->last_waves = n_waves;
+    if (n_waves > 1) {
+        if (!plan->s_bin) CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_bin, cudaStreamNonBlocking));
+        if (!plan->s_tile) CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_tile, cudaStreamNonBlocking));
+        if (!plan->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
+        if (!plan->ev_tile) CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_tile, cudaEventDisableTiming));
+        for (int w = 0; w < n_waves; ++w)
+            if (!plan->ev_bin[w]) CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_bin[w], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(plan->ev_fork, st));  // behind the prepare pass and every earlier run
+        CUDA_TRY(cudaStreamWaitEvent(plan->s_bin, plan->ev_fork, 0));
+        CUDA_TRY(cudaStreamWaitEvent(plan->s_tile, plan->ev_fork, 0));
     }
-    if (int rc = checkpoint("bin_count_kernel")) return rc;
-    bin_scan_kernel<<<(unsigned)((G + 7) / 8), 256, 0, st>>>(plan->d_bin, G, K, n_tiles, plan->d_stream_off, plan->d_stream_len, cursor,
-                                                             plan->d_streams, plan->stream_capacity, plan->d_status);
-    if (int rc = checkpoint("bin_scan_kernel")) return rc;
-    for (int c0 = first; c0 < first + count; c0 += 65535) {
-        const int nc = std::min(65535, first + count - c0);
-        bin_fill_kernel<<<dim3(gx, (unsigned)nc), kBinWarps * 32, 0, st>>>(
-            plan->d_canvases + c0, c0, plan->d_placements, tile0, G, K, plan->d_bin, plan->d_masks, plan->mask_chunks,
-            plan->d_stream_off, plan->d_streams, plan->stream_capacity, plan->d_maps,
-            reinterpret_cast<const uint32_t *>(plan->d_tables));
+    int64_t bin_row0 = 0;  // first count row (of G entries each... rows are [G][K_wave]) of this wave in d_bin
+    int c0 = first;
+    bool odd_used = false;
+    for (int w = 0; w < n_waves; ++w) {
+        // canvases of this wave: cut at the canvas whose first tile is nearest to an equal share of the tiles
+        int c1 = first + count;
+        if (w + 1 < n_waves) {
+            const int64_t target = run_tile0 + run_tiles * (w + 1) / n_waves;
+            c1 = (int)(std::lower_bound(plan->tiles_before.begin() + c0 + 1, plan->tiles_before.begin() + first + count, target) -
+                       plan->tiles_before.begin());
+            c1 = std::max(c0 + 1, std::min(c1, first + count - (n_waves - 1 - w)));
+        }
+        const int64_t tile0 = plan->tiles_before[(size_t)c0];
+        const int64_t n_tiles = plan->tiles_before[(size_t)c1] - tile0;
+        const int K = (int)((n_tiles + G - 1) / G);
+        int32_t *bin = plan->d_bin + bin_row0 * G;
+        bin_row0 += K;
+        int64_t *stream_off = plan->d_stream_off + (size_t)w * (G + 2);
+        int64_t *stream_len = plan->d_stream_len + (size_t)w * G;
+        unsigned long long *cursor = reinterpret_cast<unsigned long long *>(stream_off + G);  // record allocator
+        const int64_t rec0 = plan->records_before[(size_t)c0] - plan->records_before[(size_t)first] + (int64_t)w * (G + kCmdBlk);
+        const int64_t capacity = plan->records_before[(size_t)c1] - plan->records_before[(size_t)c0] + G;
+        Cmd *streams = plan->d_streams + rec0;
+        uint32_t *masks = plan->d_masks + (tile0 - run_tile0) * (int64_t)plan->mask_chunks * 2;
+        cudaStream_t sb = n_waves > 1 ? plan->s_bin : st;
+        for (int b0 = c0; b0 < c1; b0 += 65535) {  // grid.y is limited to 65535 canvases per launch
+            const int nc = std::min(65535, c1 - b0);
+            bin_count_kernel<<<dim3(gx, (unsigned)nc), kBinWarps * 32, 0, sb>>>(
+                plan->d_canvases + b0, plan->d_placements, plan->d_boxes, tile0, G, K, bin, masks, plan->mask_chunks,
+                plan->iw_words, b0 == c0 ? cursor : nullptr, plan->d_status, cull);
+        }
+        if (int rc = checkpoint("bin_count_kernel")) return rc;
+        bin_scan_kernel<<<(unsigned)((G + 7) / 8), 256, 0, sb>>>(bin, G, K, n_tiles, stream_off, stream_len, cursor, streams,
+                                                                 capacity, plan->d_status);
+        if (int rc = checkpoint("bin_scan_kernel")) return rc;
+        for (int b0 = c0; b0 < c1; b0 += 65535) {
+            const int nc = std::min(65535, c1 - b0);
+            bin_fill_kernel<<<dim3(gx, (unsigned)nc), kBinWarps * 32, 0, sb>>>(
+                plan->d_canvases + b0, b0, plan->d_placements, tile0, G, K, bin, masks, plan->mask_chunks, stream_off, streams,
+                capacity, plan->d_maps, reinterpret_cast<const uint32_t *>(plan->d_tables));
+        }
+        if (int rc = checkpoint("bin_fill_kernel")) return rc;
+        cudaStream_t stt = st;
+        if (n_waves > 1) {
+            CUDA_TRY(cudaEventRecord(plan->ev_bin[w], sb));
+            if (w & 1) {
+                stt = plan->s_tile;
+                odd_used = true;
+            }
+            CUDA_TRY(cudaStreamWaitEvent(stt, plan->ev_bin[w], 0));
+        }
+        if (pe[1]) CUDA_TRY(cudaEventRecord(pe[1], st));
+        static const size_t extra_smem = [] {  // B200COMP_EXTRA_SMEM=bytes: occupancy experiments (1 CTA per SM)
+            const char *e = std::getenv("B200COMP_EXTRA_SMEM");
+            return e ? (size_t)std::atol(e) : (size_t)0;
+        }();
+        composite_slab_kernel<<<(unsigned)G, kThreads, plan->smem_bytes + extra_smem, stt>>>(
+            streams, stream_off, stream_len, plan->d_canvases, plan->d_maps, reinterpret_cast<const uint32_t *>(plan->d_tables),
+            plan->slot_words, plan->iw_words, plan->d_status, plan->d_dbg);
+        CUDA_TRY(cudaGetLastError());
+        c0 = c1;
     }
-    if (int rc = checkpoint("bin_fill_kernel")) return rc;
-    if (pe[1]) CUDA_TRY(cudaEventRecord(pe[1], st));
-    composite_slab_kernel<<<(unsigned)G, kThreads, plan->smem_bytes, st>>>(
-        plan->d_streams, plan->d_stream_off, plan->d_stream_len, plan->d_canvases, plan->d_maps,
-        reinterpret_cast<const uint32_t *>(plan->d_tables), plan->slot_words, plan->iw_words, plan->d_status, plan->d_dbg);
-    CUDA_TRY(cudaGetLastError());
+    if (odd_used) {  // join: the caller's stream carries the even waves and waits for the odd ones
+        CUDA_TRY(cudaEventRecord(plan->ev_tile, plan->s_tile));
+        CUDA_TRY(cudaStreamWaitEvent(st, plan->ev_tile, 0));
+    }
     if (pe[2]) {
         CUDA_TRY(cudaEventRecord(pe[2], st));
         ++plan->prof_runs;
@@ -1503,10 +1593,12 @@ int b200comp_plan_status_async_(b200comp_plan *plan, int *pinned_host_dst, void 
 
 int b200comp_plan_last_records(b200comp_plan *plan, void *stream, int64_t *records) {
     if (!plan || !records) return fail(B200COMP_EINVAL, "plan_last_records: null argument");
-    unsigned long long h = 0;
-    CUDA_TRY(cudaMemcpyAsync(&h, plan->d_stream_off + plan->G, sizeof h, cudaMemcpyDeviceToHost, S(stream)));
+    // one cursor per wave of the last run, at the end of the wave's row of stream offsets
+    std::vector<int64_t> rows((size_t)kMaxWaves * (plan->G + 2));
+    CUDA_TRY(cudaMemcpyAsync(rows.data(), plan->d_stream_off, rows.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, S(stream)));
     CUDA_TRY(cudaStreamSynchronize(S(stream)));
-    *records = (int64_t)h;
+    *records = 0;
+    for (int w = 0; w < plan->last_waves; ++w) *records += rows[(size_t)w * (plan->G + 2) + plan->G];
     return 0;
 }
 

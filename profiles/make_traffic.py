@@ -24,17 +24,26 @@ def main():
     step = [launches[i] for i in ids if first <= i <= last_tile]
     dram = sum(l["dram__bytes_read.sum"] + l["dram__bytes_write.sum"] for l in step)
     t = sum(l["gpu__time_duration.sum"] for l in step)
-    tile = launches[last_tile]
+    # a run over many canvases is cut into waves: several launches of every kernel but the prepare pass per step
+    tiles = [l for l in step if l["name"].startswith("composite_slab_kernel")]
+    by_name = {}
+    for l in step:
+        by_name[l["name"]] = by_name.get(l["name"], 0.0) + l["gpu__time_duration.sum"]
+    names = []
+    for l in step:
+        if l["name"] not in names:
+            names.append(l["name"])
     bench = json.loads(open(bench_json).read().strip().splitlines()[-1])
     res = {
         "source": f"profiles/{src.split('/')[-1]} (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
                   f"--clock-control none; last step of bench.py --batch {bench['config']['canvases_per_gpu_per_step']}: "
-                  + " + ".join(l["name"] for l in step) + ")",
+                  + " + ".join(f"{sum(1 for l in step if l['name'] == n)} x {n}" for n in names) + ")",
         "dram_bytes_per_launch": dram,
         "algorithmic_bytes_per_launch": bench["roofline"]["algorithmic_bytes_per_launch"],
-        "tile_kernel_dram_bytes": tile["dram__bytes_read.sum"] + tile["dram__bytes_write.sum"],
-        "tile_kernel_share_of_step_time": tile["gpu__time_duration.sum"] / t,
-        "launch_ns": {l["name"]: l["gpu__time_duration.sum"] for l in step},
+        "tile_kernel_dram_bytes": sum(l["dram__bytes_read.sum"] + l["dram__bytes_write.sum"] for l in tiles),
+        "tile_kernel_share_of_step_time": sum(l["gpu__time_duration.sum"] for l in tiles) / t,
+        "launch_ns": by_name,
+        "launches_per_step": len(step),
     }
     json.dump(res, open(out, "w"), indent=1)
     print(json.dumps(res, indent=1))

@@ -343,6 +343,20 @@ def test_batch_properties_at_scale(B):
     o2, _ = run_batch(B, pool, [(3840, 2160)] * n, pls, solid=(10, 20, 30, 255))
     for a, b in zip(o1, o2):
         assert np.array_equal(a, b)
+    # large runs are cut into waves (binning of wave w+1 under the tile kernel of wave w, side streams): same pixels
+    # whatever the number of waves, also with mixed canvas sizes and with more waves asked for than canvases
+    mixed_sizes = [(3840, 2160) if i % 3 else (1000 + 37 * i, 700 + 11 * i) for i in range(n)]
+    mixed_pls = [synth.canvas_placements(sizes_by_id, s, i, n_objects=20) for i, s in enumerate(mixed_sizes)]
+    m1, _ = run_batch(B, pool, mixed_sizes, mixed_pls, solid=(10, 20, 30, 255))
+    for waves in ("2", "5", "16"):
+        os.environ["B200COMP_WAVES"] = waves
+        try:
+            ow, _ = run_batch(B, pool, [(3840, 2160)] * n, pls, solid=(10, 20, 30, 255))
+            mw, _ = run_batch(B, pool, mixed_sizes, mixed_pls, solid=(10, 20, 30, 255))
+        finally:
+            os.environ.pop("B200COMP_WAVES", None)
+        for a, b in zip(o1 + m1, ow + mw):
+            assert np.array_equal(a, b), f"waves={waves}"
     for i in (0, n - 1):
         single, _ = run_batch(B, pool, [(3840, 2160)], [pls[i]], solid=(10, 20, 30, 255))
         assert np.array_equal(single[0], o1[i])
