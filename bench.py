@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fresh-plan", action="store_true", help="skip the new-plan-every-step measurement")
+    ap.add_argument("--no-numa-pin", action="store_true", help="multi-rank runs: do not pin a rank to its GPU's NUMA node")
     ap.add_argument("--stats-in-step", action="store_true",
                     help="every step also computes the fill_solid statistics (masked median) of a background of the canvas "
                          "size and synthesises the canvases from that colour in-kernel (default for c5_8k_64obj)")
@@ -288,6 +289,68 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+def pin_rank_to_gpu_numa(torch, local: int):
+    """Multi-rank runs: keep this rank's threads (and so the pages of the pinned buffers it allocates and first touches)
+    on the NUMA node its GPU hangs off.  Returns a description for the JSON line, or None if sysfs has no answer."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(f"{base}/numa_node").read().strip())
+        cpus = set()
+        for part in open(f"{base}/local_cpulist").read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return {"numa_node": node, "pinned": False, "why": "no NUMA locality reported for the GPU"}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "pinned": True, "cpus": len(cpus), "gpu": bdf}
+    except Exception as e:  # noqa: BLE001 - informational
+        return {"pinned": False, "why": f"{type(e).__name__}: {e}"}
+
+
+def host_copy_ceiling(torch, dist, world: int, dev, h2d_bytes: int, d2h_bytes: int, px: int):
+    """What the box's PCIe root / host memory can move with every rank copying both ways at once (pinned buffers,
+    no kernels): the end-to-end metric cannot exceed px / max(h2d_bytes / h2d_rate, d2h_bytes / d2h_rate)."""
+    n = 256 << 20
+    h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_in.fill_(1)
+    d_in = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_out = torch.zeros(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        with torch.cuda.stream(s1):
+            ev[0].record()
+            for _ in range(reps):
+                d_in.copy_(h_in, non_blocking=True)
+            ev[1].record()
+        with torch.cuda.stream(s2):
+            ev[2].record()
+            for _ in range(reps):
+                h_out.copy_(d_out, non_blocking=True)
+            ev[3].record()
+        torch.cuda.synchronize()
+        return reps * n / (ev[0].elapsed_time(ev[1]) * 1e6), reps * n / (ev[2].elapsed_time(ev[3]) * 1e6)
+
+    run(1)
+    if world > 1:
+        dist.barrier()
+    up, down = run(8)
+    t = torch.tensor([max(h2d_bytes / (up * 1e9), d2h_bytes / (down * 1e9)), -up, -down], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # slowest rank bounds the step; min rates reported
+    return {"h2d_gbs_per_gpu_min": -float(t[1].item()), "d2h_gbs_per_gpu_min": -float(t[2].item()),
+            "value": world * px / 1e6 / float(t[0].item()), "unit": UNIT,
+            "how": f"{world} rank(s) copying 256 MB pinned buffers both ways at once, no kernels: the metric's ceiling on this host"}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -302,6 +365,9 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the compositor has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    affinity = None
+    if world > 1 and not args.no_numa_pin:
+        affinity = pin_rank_to_gpu_numa(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -496,6 +562,8 @@ def run_b200(args):
             pls[j] = _native.Placement(tp.data_ptr(), tp.shape[1] * 4, tp.shape[1], tp.shape[0], x, y, w, h, fl, 0)
 
         n_threads = max(1, host_cores() // max(1, world))  # the ranks of one box share its host cores
+        if affinity and affinity.get("pinned"):
+            n_threads = max(1, min(n_threads, affinity["cpus"]))
 
         def e2e_step():
             t_call = time.perf_counter()
@@ -522,20 +590,27 @@ def run_b200(args):
                "api": "b200comp_composite_batch_host (pinned host buffers; coefficient tables rebuilt every step)"}
         # For information: the same call when the caller states the canvases' solid colour (what fill_solid
         # produces) instead of uploading 33 MB of identical pixels per canvas.  Not the judged e2e.
-        if host_bg is not None and world == 1:
+        if host_bg is not None:
             cvs_solid = (_native.Canvas * nb)()
             for i in range(nb):
                 c = cvs[i]
                 cvs_solid[i] = _native.Canvas(c.out, c.out_pitch, None, 0, c.solid_rgba, c.W, c.H, c.first_placement, c.n_placements, 0)
             rc = L.b200comp_composite_batch_host(cvs_solid, nb, pls, len(recs), n_threads, args.e2e_chunk, 3)
             _native.check(rc, "composite_batch_host")
+            barrier()
             t0 = time.perf_counter()
             for _ in range(args.e2e_steps):
                 _native.check(L.b200comp_composite_batch_host(cvs_solid, nb, pls, len(recs), n_threads, args.e2e_chunk, 3), "composite_batch_host")
-            dts = (time.perf_counter() - t0) / args.e2e_steps
-            e2e["solid_canvas_variant"] = {"value": e2e_px / 1e6 / dts, "unit": UNIT, "canvases_per_s": nb / dts,
+            ts_ = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
+            dts = float(ts_.item())
+            e2e["solid_canvas_variant"] = {"value": world * e2e_px / 1e6 / dts, "unit": UNIT, "canvases_per_s": world * nb / dts,
                                            "h2d_bytes_per_step": int(sum(pool[k].nbytes for k in used_pool)),
                                            "note": "same batch with the canvases' colour passed as a value (no background upload); informational"}
+        e2e["host_ceiling"] = host_copy_ceiling(torch, dist, world, dev, int(h2d), int(e2e_px * 4), e2e_px)
+        if affinity is not None:
+            e2e["affinity"] = affinity
         # spot-check one e2e canvas against the device-resident result path's oracle
         if rank == 0:
             import oracle

@@ -56,7 +56,11 @@ def fill_solid(background_path: str, canvas_size: Tuple[int, int]) -> Image.Imag
     rc = _native.lib().b200comp_fill_solid_host(a.ctypes.data, a.shape[1], a.shape[0], a.strides[0], out.ctypes.data,
                                                 W, H, out.strides[0], rgb)
     _native.check(rc, "fill_solid")
-    return result if result is not None else _native.image_from_rgba(out)
+    img = result if result is not None else _native.image_from_rgba(out)
+    # composite() passes this colour as a value instead of uploading W*H*4 bytes, as long as the canvas is still
+    # all this colour when it gets there (compositor._solid_colour_of)
+    img._b200_solid = int(rgb[0]) | int(rgb[1]) << 8 | int(rgb[2]) << 16 | 255 << 24
+    return img
 
 
 def _edge_strip_median_colors(img: Image.Image, strip_px: int = 8) -> Tuple[RGB, RGB, RGB, RGB]:

@@ -101,6 +101,21 @@ def _cutout_cache_enabled() -> bool:
     return os.environ.get("B200COMP_CUTOUT_CACHE", "1") != "0"
 
 
+def _solid_colour_of(img: Image.Image, arr: np.ndarray):
+    """RGBA value (little-endian uint32) of a canvas made by fill_solid() that is still all one colour, else None.
+    The tag alone is not trusted: the caller may have drawn on the canvas since.  One memcmp of the buffer against
+    itself shifted by a pixel proves every pixel equals the first (cheaper than the upload it saves)."""
+    colour = getattr(img, "_b200_solid", None)
+    if colour is None or not arr.flags.c_contiguous or arr.nbytes < 4:
+        return None
+    if int(arr.reshape(-1)[:4].view(np.uint32)[0]) != colour:
+        return None
+    base = arr.ctypes.data
+    if arr.nbytes > 4 and _memcmp(base, base + 4, arr.nbytes - 4) != 0:
+        return None
+    return colour
+
+
 def composite(background_img: Image.Image, object_images: Dict[int, Image.Image], placements: List[Dict]) -> Image.Image:
     """Composite objects onto the background according to placements (compositor.py:6-22).
 
@@ -141,8 +156,12 @@ def composite(background_img: Image.Image, object_images: Dict[int, Image.Image]
                                         flags | _native.SRC_DEVICE, 0)
             continue
         recs[i] = _native.Placement(a.ctypes.data, a.strides[0], a.shape[1], a.shape[0], x, y, w, h, flags, 0)
-    rc = _native.lib().b200comp_composite_host_ex(bg.ctypes.data, 0, W, H, bg.strides[0], out.ctypes.data, out.strides[0],
-                                                  recs, len(resolved))
+    solid = _solid_colour_of(background_img, bg)
+    if solid is not None:  # fill_solid() canvas, untouched: synthesised on the device from the colour
+        rc = _native.lib().b200comp_composite_host_ex(None, solid, W, H, 0, out.ctypes.data, out.strides[0], recs, len(resolved))
+    else:
+        rc = _native.lib().b200comp_composite_host_ex(bg.ctypes.data, 0, W, H, bg.strides[0], out.ctypes.data, out.strides[0],
+                                                      recs, len(resolved))
     _native.check(rc, "composite")
     del keep
     return result if result is not None else _native.image_from_rgba(out)

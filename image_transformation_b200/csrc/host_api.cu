@@ -22,12 +22,17 @@ namespace {
 
 thread_local std::string g_host_err;
 
-// Device memory from the stream-ordered pool: the pool keeps freed blocks (release threshold raised below),
-// so the staging buffers of repeated host-buffer calls cost a pool lookup, not a cudaMalloc / cudaFree pair.
+// Device memory from the stream-ordered pool, allocated and freed on one of the call's own streams (never the
+// legacy default stream, which would serialise concurrent callers).  The pool keeps freed blocks (release
+// threshold raised below), so the staging buffers of repeated host-buffer calls cost a pool lookup.
 struct DevBuf {
     void *p = nullptr;
-    ~DevBuf() { if (p) cudaFreeAsync(p, nullptr); }
-    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, std::max<size_t>(bytes, 16), nullptr); }
+    cudaStream_t st = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+        st = stream;
+        return cudaMallocAsync(&p, std::max<size_t>(bytes, 16), stream);
+    }
 };
 
 void keep_pool_memory(int device) {
@@ -124,14 +129,6 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
     // streams, so neither PCIe direction idles
     constexpr int kBufs = 3;
     const int n_buf = std::min(n_super, kBufs);
-    DevBuf pool, d_out[kBufs], d_bg[kBufs];
-    if (pool.alloc(pool_bytes) != cudaSuccess) return b200comp_set_error_(B200COMP_ENOMEM, "cutout pool allocation failed");
-    for (int b = 0; b < n_buf; ++b)
-        if (d_out[b].alloc(max_canvas_bytes * super_canvases) != cudaSuccess ||
-            (any_bg && d_bg[b].alloc(max_canvas_bytes * super_canvases) != cudaSuccess))
-            return b200comp_set_error_(B200COMP_ENOMEM, "canvas staging allocation failed");
-    cudaStreamSynchronize(nullptr);  // the allocations above are ordered on the default stream
-    stamp("staging allocated", 0);
     cudaStream_t s_in = nullptr, s_exec = nullptr, s_out = nullptr, s_plan = nullptr;
     struct StreamGuard {
         cudaStream_t *s[4];
@@ -142,6 +139,22 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
         cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s_plan, cudaStreamNonBlocking) != cudaSuccess)
         return b200comp_set_error_(B200COMP_ECUDA, "stream creation failed");
+    // this call's streams only: nothing here waits for, or makes wait, other threads' work on the device
+    auto sync_all = [&] {
+        cudaStreamSynchronize(s_in);
+        cudaStreamSynchronize(s_exec);
+        cudaStreamSynchronize(s_out);
+        cudaStreamSynchronize(s_plan);
+    };
+    // staging memory: declared after the streams, so it is freed (stream-ordered, on s_exec) before they are destroyed
+    DevBuf pool, d_out[kBufs], d_bg[kBufs];
+    if (pool.alloc(pool_bytes, s_exec) != cudaSuccess) return b200comp_set_error_(B200COMP_ENOMEM, "cutout pool allocation failed");
+    for (int b = 0; b < n_buf; ++b)
+        if (d_out[b].alloc(max_canvas_bytes * super_canvases, s_exec) != cudaSuccess ||
+            (any_bg && d_bg[b].alloc(max_canvas_bytes * super_canvases, s_exec) != cudaSuccess))
+            return b200comp_set_error_(B200COMP_ENOMEM, "canvas staging allocation failed");
+    cudaStreamSynchronize(s_exec);  // the allocations are ordered on s_exec; the other streams may use them from here on
+    stamp("staging allocated", 0);
     const int max_sub = (super_canvases + chunk_canvases - 1) / chunk_canvases;
     std::vector<cudaEvent_t> ev_in((size_t)max_sub * 3), ev_exec((size_t)max_sub * 3);  // one set per staging buffer
     struct EventGuard {
@@ -213,7 +226,7 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
     SuperPlan built;    // plan being resolved by the helper thread
     auto retire = [&](int buf) {  // wait for the super-chunk that used `buf`, check it, free its plan
         if (!live[buf].plan) return;
-        if (rc) cudaDeviceSynchronize();  // error path: nothing may still be using the plan's memory
+        if (rc) sync_all();  // error path: nothing may still be using the plan's memory
         cudaError_t e = cudaEventSynchronize(ev_done[buf]);
         if (rc == 0 && e != cudaSuccess) {
             rc = B200COMP_ECUDA;
@@ -303,7 +316,7 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
             err = keep_err;
         }
     }
-    cudaDeviceSynchronize();
+    sync_all();  // everything this call queued is done: the staging buffers can go back to the pool
     stamp("all done", 0);
     if (ev_pool) cudaEventDestroy(ev_pool);
     for (int b = 0; b < kBufs; ++b) if (ev_done[b]) cudaEventDestroy(ev_done[b]);
@@ -411,13 +424,8 @@ void upload_rows(uint8_t *dev, size_t dev_pitch, const uint8_t *host, size_t hos
     }
 }
 
-}  // namespace
-
-int b200comp_composite_host_ex(const uint8_t *bg, uint32_t solid_rgba, int W, int H, size_t bg_pitch, uint8_t *out,
-                               size_t out_pitch, const b200comp_placement *placements, int n_placements) {
-    if (!out || W < 1 || H < 1 || out_pitch < (size_t)W * 4 || (bg && bg_pitch < (size_t)W * 4) || n_placements < 0 ||
-        (n_placements > 0 && !placements))
-        return b200comp_set_error_(B200COMP_EINVAL, "composite_host: bad canvas or placement argument");
+// the calling thread's context on its current device (created on first use)
+int acquire_lean(LeanCtx **out, const char *who) {
     int device = 0;
     if (cudaGetDevice(&device) != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, "no CUDA device");
     LeanCtx &cx = g_lean;
@@ -427,9 +435,55 @@ int b200comp_composite_host_ex(const uint8_t *bg, uint32_t solid_rgba, int W, in
         if (cudaStreamCreateWithFlags(&cx.st, cudaStreamNonBlocking) != cudaSuccess ||
             cudaHostAlloc((void **)&cx.h_status, sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
             cx.release();
-            return b200comp_set_error_(B200COMP_ECUDA, "composite_host: stream / pinned status allocation failed");
+            return b200comp_set_error_(B200COMP_ECUDA, (std::string(who) + ": stream / pinned status allocation failed").c_str());
         }
     }
+    *out = &cx;
+    return 0;
+}
+
+// device canvas (pitch dp) -> caller's host canvas, in chunks: while the copy engine fills the next chunk of the
+// pinned buffer, the host copies the previous one into the caller's (pageable) memory.  Synchronises cx.st.
+int download_rows(LeanCtx &cx, uint8_t *out, size_t out_pitch, const uint8_t *dev, size_t dp, size_t row_bytes, int H,
+                  const char *who) {
+    cudaStream_t st = cx.st;
+    const int chunk_rows = (int)std::max<size_t>(1, ((size_t)8 << 20) / dp);
+    const int n_chunks = (H + chunk_rows - 1) / chunk_rows;
+    while ((int)cx.events.size() < n_chunks) {
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            cudaStreamSynchronize(st);
+            return b200comp_set_error_(B200COMP_ECUDA, (std::string(who) + ": event creation failed").c_str());
+        }
+        cx.events.push_back(ev);
+    }
+    std::vector<cudaEvent_t> &evs = cx.events;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int r0 = c * chunk_rows, n = std::min(chunk_rows, H - r0);
+        cudaMemcpyAsync(cx.pin_out + (size_t)r0 * dp, dev + (size_t)r0 * dp, (size_t)n * dp, cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(evs[(size_t)c], st);
+    }
+    cudaError_t e = cudaSuccess;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int r0 = c * chunk_rows, n = std::min(chunk_rows, H - r0);
+        const cudaError_t ec = cudaEventSynchronize(evs[(size_t)c]);
+        if (ec != cudaSuccess) e = ec;
+        if (e == cudaSuccess) copy_rows(out + (size_t)r0 * out_pitch, out_pitch, cx.pin_out + (size_t)r0 * dp, dp, row_bytes, n);
+    }
+    if (e != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace
+
+int b200comp_composite_host_ex(const uint8_t *bg, uint32_t solid_rgba, int W, int H, size_t bg_pitch, uint8_t *out,
+                               size_t out_pitch, const b200comp_placement *placements, int n_placements) {
+    if (!out || W < 1 || H < 1 || out_pitch < (size_t)W * 4 || (bg && bg_pitch < (size_t)W * 4) || n_placements < 0 ||
+        (n_placements > 0 && !placements))
+        return b200comp_set_error_(B200COMP_EINVAL, "composite_host: bad canvas or placement argument");
+    LeanCtx *cxp = nullptr;
+    if (int rc = acquire_lean(&cxp, "composite_host")) return rc;
+    LeanCtx &cx = *cxp;
     cudaStream_t st = cx.st;
     const size_t dp = align_up((size_t)W * 4, 16), canvas_bytes = dp * H;
 
@@ -494,36 +548,10 @@ int b200comp_composite_host_ex(const uint8_t *bg, uint32_t solid_rgba, int W, in
         b200comp_plan_destroy(plan);
         return rc;
     }
-    // copy-out in chunks: while the copy engine fills the next chunk of the pinned buffer, the host copies the
-    // previous one into the caller's (pageable) canvas
-    const int chunk_rows = (int)std::max<size_t>(1, ((size_t)8 << 20) / dp);
-    const int n_chunks = (H + chunk_rows - 1) / chunk_rows;
-    while ((int)cx.events.size() < n_chunks) {
-        cudaEvent_t ev = nullptr;
-        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
-            cudaStreamSynchronize(st);
-            b200comp_plan_destroy(plan);
-            return b200comp_set_error_(B200COMP_ECUDA, "composite_host: event creation failed");
-        }
-        cx.events.push_back(ev);
-    }
-    std::vector<cudaEvent_t> &evs = cx.events;
-    for (int c = 0; c < n_chunks; ++c) {
-        const int r0 = c * chunk_rows, n = std::min(chunk_rows, H - r0);
-        cudaMemcpyAsync(cx.pin_out + (size_t)r0 * dp, cx.d_out + (size_t)r0 * dp, (size_t)n * dp, cudaMemcpyDeviceToHost, st);
-        cudaEventRecord(evs[(size_t)c], st);
-    }
-    cudaError_t e = cudaSuccess;
-    for (int c = 0; c < n_chunks; ++c) {
-        const int r0 = c * chunk_rows, n = std::min(chunk_rows, H - r0);
-        const cudaError_t ec = cudaEventSynchronize(evs[(size_t)c]);
-        if (ec != cudaSuccess) e = ec;
-        if (e == cudaSuccess)
-            copy_rows(out + (size_t)r0 * out_pitch, out_pitch, cx.pin_out + (size_t)r0 * dp, dp, (size_t)W * 4, n);
-    }
+    rc = download_rows(cx, out, out_pitch, cx.d_out, dp, (size_t)W * 4, H, "composite_host");
     const int status = *cx.h_status;  // travelled on the stream ahead of the canvas
     b200comp_plan_destroy(plan);      // (its stream is idle: every chunk event has fired)
-    if (e != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, cudaGetErrorString(e));
+    if (rc) return rc;
     if (status != 0)
         return b200comp_set_error_(B200COMP_EINTERNAL, ("tile kernel / binning status " + std::to_string(status)).c_str());
     return 0;
@@ -541,7 +569,15 @@ int b200comp_device_upload(const uint8_t *img, int w, int h, size_t pitch, uint8
     const size_t dp = align_up((size_t)w * 4, 16);
     uint8_t *d = nullptr;
     if (cudaMalloc((void **)&d, dp * h) != cudaSuccess) return b200comp_set_error_(B200COMP_ENOMEM, "device_upload: allocation failed");
-    const cudaError_t e = cudaMemcpy2D(d, dp, img, pitch, (size_t)w * 4, h, cudaMemcpyHostToDevice);
+    // through the calling thread's pinned bounce buffer and stream (no legacy-stream copy of pageable memory)
+    LeanCtx *cx = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (acquire_lean(&cx, "device_upload") != 0 || !LeanCtx::grow_pinned(&cx->pin_in, &cx->pin_in_cap, dp * h)) {
+        e = cudaErrorMemoryAllocation;
+    } else {
+        upload_rows(d, dp, img, pitch, (size_t)w * 4, h, cx->pin_in, cx->st);
+        e = cudaStreamSynchronize(cx->st);
+    }
     if (e != cudaSuccess) {
         cudaFree(d);
         return b200comp_set_error_(B200COMP_ECUDA, cudaGetErrorString(e));
@@ -561,26 +597,29 @@ int b200comp_trim(void) {
     return 0;
 }
 
-// decoded image (HOST) -> tightly packed device copy
-static int upload_image(const uint8_t *img, int W, int H, size_t pitch, DevBuf &d, const char *who) {
+// decoded image (HOST) -> device copy in the calling thread's staging buffer (pitch = 16-byte aligned row), on its stream
+static int upload_image(LeanCtx &cx, const uint8_t *img, int W, int H, size_t pitch, const uint8_t **dev, size_t *dev_pitch,
+                        const char *who) {
     if (!img || W < 1 || H < 1 || pitch < (size_t)W * 4)
         return b200comp_set_error_(B200COMP_EINVAL, (std::string(who) + ": bad image argument").c_str());
-    if (d.alloc((size_t)W * 4 * H) != cudaSuccess)
-        return b200comp_set_error_(B200COMP_ENOMEM, (std::string(who) + ": device allocation failed").c_str());
-    cudaError_t e = cudaMemcpy2D(d.p, (size_t)W * 4, img, pitch, (size_t)W * 4, H, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, cudaGetErrorString(e));
+    const size_t dp = align_up((size_t)W * 4, 16), bytes = dp * H;
+    if (!LeanCtx::grow_pinned(&cx.pin_in, &cx.pin_in_cap, bytes) || !LeanCtx::grow_device(&cx.d_bg, &cx.d_bg_cap, bytes, cx.st))
+        return b200comp_set_error_(B200COMP_ENOMEM, (std::string(who) + ": staging allocation failed").c_str());
+    upload_rows(cx.d_bg, dp, img, pitch, (size_t)W * 4, H, cx.pin_in, cx.st);
+    *dev = cx.d_bg;
+    *dev_pitch = dp;
     return 0;
 }
 
 // _edge_strip_median_colors (background_resizing.py:36-55): left, right, top, bottom strips
-static int edge_medians_dev(const uint8_t *d_img, int W, int H, int strip_px, int32_t edges[12]) {
+static int edge_medians_dev(const uint8_t *d_img, size_t pitch, int W, int H, int strip_px, int32_t edges[12], cudaStream_t st) {
     const int rects[4][4] = {{0, 0, std::min(strip_px, W), H},
                              {std::max(0, W - strip_px), 0, W, H},
                              {0, 0, W, std::min(strip_px, H)},
                              {0, std::max(0, H - strip_px), W, H}};
     for (int i = 0; i < 4; ++i) {
-        int rc = b200comp_masked_median_rgb(d_img, W, H, (size_t)W * 4, rects[i][0], rects[i][1], rects[i][2],
-                                            rects[i][3], edges + 3 * i, nullptr);
+        int rc = b200comp_masked_median_rgb(d_img, W, H, pitch, rects[i][0], rects[i][1], rects[i][2], rects[i][3],
+                                            edges + 3 * i, st);
         if (rc) return rc;
     }
     return 0;
@@ -588,38 +627,51 @@ static int edge_medians_dev(const uint8_t *d_img, int W, int H, int strip_px, in
 
 int b200comp_masked_median_rgb_host(const uint8_t *img, int W, int H, size_t pitch, int x0, int y0, int x1, int y1,
                                     int32_t out_rgb[3]) {
-    DevBuf d;
-    int rc = upload_image(img, W, H, pitch, d, "masked_median_rgb_host");
-    if (rc) return rc;
-    return b200comp_masked_median_rgb((const uint8_t *)d.p, W, H, (size_t)W * 4, x0, y0, x1, y1, out_rgb, nullptr);
+    LeanCtx *cx = nullptr;
+    if (int rc = acquire_lean(&cx, "masked_median_rgb_host")) return rc;
+    const uint8_t *d = nullptr;
+    size_t dp = 0;
+    if (int rc = upload_image(*cx, img, W, H, pitch, &d, &dp, "masked_median_rgb_host")) return rc;
+    return b200comp_masked_median_rgb(d, W, H, dp, x0, y0, x1, y1, out_rgb, cx->st);
 }
 
 int b200comp_edge_strip_medians_host(const uint8_t *img, int W, int H, size_t pitch, int strip_px,
                                      int32_t out_edges[12]) {
     if (strip_px < 1 || !out_edges) return b200comp_set_error_(B200COMP_EINVAL, "edge_strip_medians_host: bad argument");
-    DevBuf d;
-    int rc = upload_image(img, W, H, pitch, d, "edge_strip_medians_host");
-    if (rc) return rc;
-    return edge_medians_dev((const uint8_t *)d.p, W, H, strip_px, out_edges);
+    LeanCtx *cx = nullptr;
+    if (int rc = acquire_lean(&cx, "edge_strip_medians_host")) return rc;
+    const uint8_t *d = nullptr;
+    size_t dp = 0;
+    if (int rc = upload_image(*cx, img, W, H, pitch, &d, &dp, "edge_strip_medians_host")) return rc;
+    return edge_medians_dev(d, dp, W, H, strip_px, out_edges, cx->st);
+}
+
+// canvas of the thread's staging set, filled on its stream by `fill`, copied out to the caller
+extern "C++" template <typename Fill>
+int fill_and_download(LeanCtx &cx, uint8_t *out, int W, int H, size_t out_pitch, const char *who, Fill fill) {
+    const size_t dp = align_up((size_t)W * 4, 16), bytes = dp * H;
+    if (!LeanCtx::grow_pinned(&cx.pin_out, &cx.pin_out_cap, bytes) || !LeanCtx::grow_device(&cx.d_out, &cx.d_out_cap, bytes, cx.st))
+        return b200comp_set_error_(B200COMP_ENOMEM, (std::string(who) + ": staging allocation failed").c_str());
+    if (int rc = fill(cx.d_out, dp)) return rc;
+    return download_rows(cx, out, out_pitch, cx.d_out, dp, (size_t)W * 4, H, who);
 }
 
 int b200comp_fill_solid_host(const uint8_t *bg, int Wb, int Hb, size_t bg_pitch, uint8_t *out, int W, int H,
                              size_t out_pitch, int32_t out_rgb[3]) {
     if (!out || W < 1 || H < 1 || out_pitch < (size_t)W * 4)
         return b200comp_set_error_(B200COMP_EINVAL, "fill_solid_host: bad canvas argument");
-    DevBuf d_bg, d_out;
-    int rc = upload_image(bg, Wb, Hb, bg_pitch, d_bg, "fill_solid_host");
-    if (rc) return rc;
-    if (d_out.alloc((size_t)W * 4 * H) != cudaSuccess)
-        return b200comp_set_error_(B200COMP_ENOMEM, "fill_solid_host: device allocation failed");
+    LeanCtx *cx = nullptr;
+    if (int rc = acquire_lean(&cx, "fill_solid_host")) return rc;
+    const uint8_t *d_bg = nullptr;
+    size_t bp = 0;
+    if (int rc = upload_image(*cx, bg, Wb, Hb, bg_pitch, &d_bg, &bp, "fill_solid_host")) return rc;
     int32_t rgb[3];
-    rc = b200comp_masked_median_rgb((const uint8_t *)d_bg.p, Wb, Hb, (size_t)Wb * 4, 0, 0, Wb, Hb, rgb, nullptr);
-    if (rc) return rc;
+    if (int rc = b200comp_masked_median_rgb(d_bg, Wb, Hb, bp, 0, 0, Wb, Hb, rgb, cx->st)) return rc;
     const uint32_t rgba = (uint32_t)rgb[0] | ((uint32_t)rgb[1] << 8) | ((uint32_t)rgb[2] << 16) | 0xff000000u;
-    rc = b200comp_fill_rgba((uint8_t *)d_out.p, W, H, (size_t)W * 4, rgba, nullptr);
+    cudaStream_t st = cx->st;
+    int rc = fill_and_download(*cx, out, W, H, out_pitch, "fill_solid_host",
+                               [&](uint8_t *d, size_t dp) { return b200comp_fill_rgba(d, W, H, dp, rgba, st); });
     if (rc) return rc;
-    cudaError_t e = cudaMemcpy2D(out, out_pitch, d_out.p, (size_t)W * 4, (size_t)W * 4, H, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, cudaGetErrorString(e));
     if (out_rgb) std::memcpy(out_rgb, rgb, sizeof rgb);
     return 0;
 }
@@ -628,14 +680,13 @@ int b200comp_fill_gradient_host(const uint8_t *bg, int Wb, int Hb, size_t bg_pit
                                 size_t out_pitch, int strip_px, int32_t out_edges[12], int *out_horizontal) {
     if (!out || W < 1 || H < 1 || strip_px < 1 || out_pitch < (size_t)W * 4)
         return b200comp_set_error_(B200COMP_EINVAL, "fill_gradient_host: bad argument");
-    DevBuf d_bg, d_out;
-    int rc = upload_image(bg, Wb, Hb, bg_pitch, d_bg, "fill_gradient_host");
-    if (rc) return rc;
-    if (d_out.alloc((size_t)W * 4 * H) != cudaSuccess)
-        return b200comp_set_error_(B200COMP_ENOMEM, "fill_gradient_host: device allocation failed");
+    LeanCtx *cx = nullptr;
+    if (int rc = acquire_lean(&cx, "fill_gradient_host")) return rc;
+    const uint8_t *d_bg = nullptr;
+    size_t bp = 0;
+    if (int rc = upload_image(*cx, bg, Wb, Hb, bg_pitch, &d_bg, &bp, "fill_gradient_host")) return rc;
     int32_t edges[12];
-    rc = edge_medians_dev((const uint8_t *)d_bg.p, Wb, Hb, strip_px, edges);
-    if (rc) return rc;
+    if (int rc = edge_medians_dev(d_bg, bp, Wb, Hb, strip_px, edges, cx->st)) return rc;
     // _axis_variance (:58-60) and the direction choice (:69-80): squared colour distance, ties -> horizontal
     auto dist = [&](int a, int b) {
         double s = 0;
@@ -648,10 +699,11 @@ int b200comp_fill_gradient_host(const uint8_t *bg, int Wb, int Hb, size_t bg_pit
     const int horizontal = dist(0, 1) <= dist(2, 3) ? 1 : 0;
     const int32_t *c1 = horizontal ? edges : edges + 6;
     const int32_t *c2 = horizontal ? edges + 3 : edges + 9;
-    rc = b200comp_fill_gradient((uint8_t *)d_out.p, W, H, (size_t)W * 4, horizontal, c1, c2, nullptr);
+    cudaStream_t st = cx->st;
+    int rc = fill_and_download(*cx, out, W, H, out_pitch, "fill_gradient_host", [&](uint8_t *d, size_t dp) {
+        return b200comp_fill_gradient(d, W, H, dp, horizontal, c1, c2, st);
+    });
     if (rc) return rc;
-    cudaError_t e = cudaMemcpy2D(out, out_pitch, d_out.p, (size_t)W * 4, (size_t)W * 4, H, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, cudaGetErrorString(e));
     if (out_edges) std::memcpy(out_edges, edges, sizeof edges);
     if (out_horizontal) *out_horizontal = horizontal;
     return 0;

@@ -139,6 +139,32 @@ def test_results_are_fully_mutable(tmp_path):
         assert img.getpixel((3, 3)) != (1, 1, 1, 1)
 
 
+def test_fill_solid_canvas_is_passed_by_colour_until_it_is_drawn_on(tmp_path):
+    """fill_solid -> composite (macro_placement_test.py:1497-1511): the canvas colour travels as a value, the W*H*4
+    bytes are not uploaded -- but only while the canvas still is that colour."""
+    from PIL import Image
+
+    from image_transformation_b200 import _native
+    from image_transformation_b200 import compositor as C
+    from image_transformation_b200.background_resizing import fill_solid
+
+    rng = np.random.default_rng(5)
+    bgp = tmp_path / "background.png"
+    Image.fromarray(rng.integers(0, 256, (30, 40, 4), dtype=np.uint8)).save(bgp)
+    obj = rng.integers(0, 256, (90, 120, 4), dtype=np.uint8)
+    pl = [{"object_id": 1, "box": [10, 5, 170, 125]}, {"object_id": 1, "box": [150, 60, 270, 150]}]
+    canvas = fill_solid(str(bgp), (300, 200))
+    colour = C._solid_colour_of(canvas, _native.rgba_array(canvas))
+    assert colour is not None and colour >> 24 == 255
+    exp = oracle.composite(np.array(canvas), {1: obj}, pl)
+    assert_same(np.array(C.composite(canvas, {1: pil(obj)}, pl)), exp, "solid canvas by value")
+    canvas.putpixel((299, 199), (1, 2, 3, 4))  # last pixel: the cheapest place to miss
+    assert C._solid_colour_of(canvas, _native.rgba_array(canvas)) is None
+    exp = oracle.composite(np.array(canvas), {1: obj}, pl)
+    assert_same(np.array(C.composite(canvas, {1: pil(obj)}, pl)), exp, "drawn-on canvas by buffer")
+    assert C._solid_colour_of(canvas.copy(), _native.rgba_array(canvas)) is None  # copies carry no tag
+
+
 def test_load_object_images_and_cutout_cache_around_the_refine_loop(tmp_path):
     """compositor.py:25-35 through the drop-in: ids, modes, pixels; and the loop of macro_placement_test.py:1679-1699
     (reload the bundle, new layout, composite) uploads every cutout once."""
