@@ -348,7 +348,8 @@ def host_copy_ceiling(torch, dist, world: int, dev, h2d_bytes: int, d2h_bytes: i
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # slowest rank bounds the step; min rates reported
     return {"h2d_gbs_per_gpu_min": -float(t[1].item()), "d2h_gbs_per_gpu_min": -float(t[2].item()),
             "value": world * px / 1e6 / float(t[0].item()), "unit": UNIT,
-            "how": f"{world} rank(s) copying 256 MB pinned buffers both ways at once, no kernels: the metric's ceiling on this host"}
+            "how": f"probe: {world} rank(s) copying 256 MB pinned buffers both ways at once, no kernels; value = the metric if every "
+                   "rank moved this step's bytes at the SLOWEST rank's rates (what the host's PCIe root / memory allows)"}
 
 
 def run_b200(args):
@@ -608,7 +609,7 @@ def run_b200(args):
             e2e["solid_canvas_variant"] = {"value": world * e2e_px / 1e6 / dts, "unit": UNIT, "canvases_per_s": world * nb / dts,
                                            "h2d_bytes_per_step": int(sum(pool[k].nbytes for k in used_pool)),
                                            "note": "same batch with the canvases' colour passed as a value (no background upload); informational"}
-        e2e["host_ceiling"] = host_copy_ceiling(torch, dist, world, dev, int(h2d), int(e2e_px * 4), e2e_px)
+        e2e["host_copy_probe"] = host_copy_ceiling(torch, dist, world, dev, int(h2d), int(e2e_px * 4), e2e_px)
         if affinity is not None:
             e2e["affinity"] = affinity
         # spot-check one e2e canvas against the device-resident result path's oracle
