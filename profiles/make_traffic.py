@@ -36,7 +36,8 @@ def main():
     bench = json.loads(open(bench_json).read().strip().splitlines()[-1])
     res = {
         "source": f"profiles/{src.split('/')[-1]} (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
-                  f"--clock-control none; last step of bench.py --batch {bench['config']['canvases_per_gpu_per_step']}: "
+                  f"--clock-control none; last plan run of bench.py --batch {bench['config']['canvases_per_gpu_per_step']} "
+                  f"-- the phase-split pass, wave split off, kernels one after another: "
                   + " + ".join(f"{sum(1 for l in step if l['name'] == n)} x {n}" for n in names) + ")",
         "dram_bytes_per_launch": dram,
         "algorithmic_bytes_per_launch": bench["roofline"]["algorithmic_bytes_per_launch"],
