@@ -50,6 +50,12 @@ def main():
     ms = timed(lambda: B.masked_median_rgb(bg))
     row("hist_rgb_kernel + median_from_hist_kernel (fill_solid statistics, 8K background)", 4 * W * H, ms,
         "includes the D2H of the 3 medians and the host sync of the call")
+    flat = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
+    flat[...] = torch.tensor([220, 238, 245, 255], dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: B.masked_median_rgb(flat))
+    row("hist_rgb_kernel + median_from_hist_kernel (flat 8K background: every pixel in the same three bins)", 4 * W * H, ms,
+        "includes the D2H of the 3 medians and the host sync of the call")
+    del flat
     canvas = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
     ms = timed(lambda: B.fill_rgba_(canvas, (38, 73, 115, 255)))
     row("fill_flat_kernel (solid 8K canvas)", 4 * W * H, ms)

@@ -281,6 +281,10 @@ def test_solid_canvas_and_device_sources_through_the_c_abi():
         for p, _ in dev.values():
             L.b200comp_device_free(p)
     assert L.b200comp_trim() == 0
+    for i, p in enumerate(pl):  # host sources again: the device copies are gone
+        x1, y1, x2, y2 = p["box"]
+        a = cut[p["object_id"]]
+        recs[i] = _native.Placement(a.ctypes.data, a.strides[0], a.shape[1], a.shape[0], x1, y1, x2 - x1, y2 - y1, 0, 0)
     out = np.zeros((H, W, 4), np.uint8)  # the per-thread context comes back after a trim
     _native.check(L.b200comp_composite_host(bg.ctypes.data, W, H, bg.strides[0], out.ctypes.data, out.strides[0], recs, len(pl)))
     assert_same(out, exp, "after trim")
