@@ -152,20 +152,33 @@ gradient_fill_kernel(uint8_t *__restrict__ dst, int W, int H, int64_t pitch, con
 // 13.5 for random bins of a warp-private histogram; the statistics pass needs 10.3 to read at 60 % of HBM.
 // VEC: 16-byte loads, lane = 4 consecutive pixels, kHistUnroll loads in flight per lane; otherwise (base or pitch
 // not 16-byte aligned) 4-byte loads, lane = pixel.
+#ifndef B200COMP_HIST_BRANCH
+#define B200COMP_HIST_BRANCH 0
+#endif
 constexpr int kHistThreads = 512;
 constexpr int kHistUnroll = 4;
 constexpr size_t kHistSmem = 3 * 256 * 32 * sizeof(unsigned int);  // 96 KB: two CTAs per SM
 
 __device__ __forceinline__ void hist_add_px(uint32_t smem_lane, uint32_t p, bool valid, unsigned int &cnt) {
+    // byte offset of word (bin, lane) = bin * 128 + lane * 4; channel planes 256 bins = 32 KB apart (the immediate
+    // of the ATOMS address).  One PRMT (byte -> zero-extended word) and one multiply-add per channel.
+    const uint32_t a0 = __byte_perm(p, 0u, 0x4440) * 128u + smem_lane, a1 = __byte_perm(p, 0u, 0x4441) * 128u + smem_lane,
+                   a2 = __byte_perm(p, 0u, 0x4442) * 128u + smem_lane;
+#if B200COMP_HIST_BRANCH
     if (valid) {
         ++cnt;
-        // byte offset of word (bin, lane) = bin * 128 + lane * 4; channel planes 256 bins = 32 KB apart
-        const uint32_t a0 = smem_lane + ((p & 0xffu) << 7), a1 = smem_lane + (((p >> 8) & 0xffu) << 7) + 32768u,
-                       a2 = smem_lane + (((p >> 16) & 0xffu) << 7) + 65536u;
         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0) : "memory");
-        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1) : "memory");
-        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a2) : "memory");
+        asm volatile("red.shared.add.u32 [%0+32768], 1;" ::"r"(a1) : "memory");
+        asm volatile("red.shared.add.u32 [%0+65536], 1;" ::"r"(a2) : "memory");
     }
+#else
+    // masked-out pixels are scattered: instead of a divergent branch per pixel they add 0
+    const uint32_t one = valid ? 1u : 0u;
+    cnt += one;
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a0), "r"(one) : "memory");
+    asm volatile("red.shared.add.u32 [%0+32768], %1;" ::"r"(a1), "r"(one) : "memory");
+    asm volatile("red.shared.add.u32 [%0+65536], %1;" ::"r"(a2), "r"(one) : "memory");
+#endif
 }
 
 template <bool VEC>
@@ -199,13 +212,23 @@ hist_rgb_kernel(const uint8_t *__restrict__ img, int64_t pitch, int x0, int y0, 
                 const int x = c0 + j * 128 + lane * 4;
                 v[j] = x < c1 ? __ldg(reinterpret_cast<const uint4 *>(rp + (int64_t)x * 4)) : make_uint4(0u, 0u, 0u, 0u);
             }
+            if (c1 - c0 == kChunk) {  // whole chunk (warp-uniform): no per-pixel bounds tests
 #pragma unroll
-            for (int j = 0; j < kHistUnroll; ++j) {
-                const int x = c0 + j * 128 + lane * 4;  // the 16-byte load may reach past c1 inside the row's pitch: masked here
-                hist_add_px(smem_lane, v[j].x, x < c1 && (all_pixels || (v[j].x >> 24) != 0u), cnt);
-                hist_add_px(smem_lane, v[j].y, x + 1 < c1 && (all_pixels || (v[j].y >> 24) != 0u), cnt);
-                hist_add_px(smem_lane, v[j].z, x + 2 < c1 && (all_pixels || (v[j].z >> 24) != 0u), cnt);
-                hist_add_px(smem_lane, v[j].w, x + 3 < c1 && (all_pixels || (v[j].w >> 24) != 0u), cnt);
+                for (int j = 0; j < kHistUnroll; ++j) {
+                    hist_add_px(smem_lane, v[j].x, all_pixels || (v[j].x >> 24) != 0u, cnt);
+                    hist_add_px(smem_lane, v[j].y, all_pixels || (v[j].y >> 24) != 0u, cnt);
+                    hist_add_px(smem_lane, v[j].z, all_pixels || (v[j].z >> 24) != 0u, cnt);
+                    hist_add_px(smem_lane, v[j].w, all_pixels || (v[j].w >> 24) != 0u, cnt);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kHistUnroll; ++j) {
+                    const int x = c0 + j * 128 + lane * 4;  // the 16-byte load may reach past c1 inside the row's pitch: masked here
+                    hist_add_px(smem_lane, v[j].x, x < c1 && (all_pixels || (v[j].x >> 24) != 0u), cnt);
+                    hist_add_px(smem_lane, v[j].y, x + 1 < c1 && (all_pixels || (v[j].y >> 24) != 0u), cnt);
+                    hist_add_px(smem_lane, v[j].z, x + 2 < c1 && (all_pixels || (v[j].z >> 24) != 0u), cnt);
+                    hist_add_px(smem_lane, v[j].w, x + 3 < c1 && (all_pixels || (v[j].w >> 24) != 0u), cnt);
+                }
             }
         } else {
             uint32_t px[2 * kHistUnroll];
