@@ -56,7 +56,10 @@ constexpr int kIdentRows = 16;               // overlay rows per chunk (one ring
 constexpr int kTileBufs = B200COMP_TILE_BUFS;  // resident canvas tiles per CTA: one being composited, one being stored and then pre-loaded
 // Source patches stream through a ring of chunks: kChunkQuads row quads (4 rows each) x 4 channel planes x the
 // placement's patch width.  A chunk is one TMA box; every compute warp consumes every chunk.
-constexpr int kChunkQuads = 4;
+#ifndef B200COMP_CHUNK_QUADS
+#define B200COMP_CHUNK_QUADS 4
+#endif
+constexpr int kChunkQuads = B200COMP_CHUNK_QUADS;
 #ifndef B200COMP_PRING
 #define B200COMP_PRING 3
 #endif
