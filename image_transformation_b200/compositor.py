@@ -32,6 +32,10 @@ def _tall_image_vertical_first() -> bool:
 TALL_IMAGE_VERTICAL_FIRST = _tall_image_vertical_first()
 
 
+_INT32_MAX = 2**31 - 1
+_GEOMETRY_MAX = 2**30  # b200comp_plan_create's range check
+
+
 def resolve_placements(placements: Sequence[dict], sizes: Dict[int, Tuple[int, int]]) -> List[Tuple[int, int, int, int, int, int]]:
     """Host-side coercions of compositor.py:12-18 -> [(object_id, x, y, w, h, flags)].
 
@@ -48,6 +52,18 @@ def resolve_placements(placements: Sequence[dict], sizes: Dict[int, Tuple[int, i
         x1, y1, x2, y2 = (int(v) for v in p["box"])
         w = max(1, x2 - x1)
         h = max(1, y2 - y1)
+        # Python ints are unbounded, the C ABI's are int32 (and its geometry wants |x|, |y|, w, h <= 2^30).  Pillow's own
+        # C entry points fail the same way the checks below do: sizes or offsets beyond a C int -> OverflowError from
+        # the argument parser, a resize target it cannot allocate -> MemoryError.
+        for v in (w, h, x1, y1):
+            if v > _INT32_MAX:
+                raise OverflowError("signed integer is greater than maximum")
+            if v < -_INT32_MAX - 1:
+                raise OverflowError("signed integer is less than minimum")
+        if w > _GEOMETRY_MAX or h > _GEOMETRY_MAX:
+            raise MemoryError(f"resize target {w}x{h} is too large")
+        if abs(x1) > _GEOMETRY_MAX or abs(y1) > _GEOMETRY_MAX:
+            continue  # cannot touch any canvas (w, h <= 2^30): alpha_composite would clip it away entirely
         sw, sh = sizes[oid]
         flags = _native.VERTICAL_FIRST if (TALL_IMAGE_VERTICAL_FIRST and sh > 100 * sw and h < sh) else 0
         out.append((oid, x1, y1, w, h, flags))

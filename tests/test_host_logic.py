@@ -89,6 +89,17 @@ def test_resolve_placements_reference_semantics():
         resolve_placements([{"object_id": 1, "box": [0, 0, 1]}], sizes)
     with pytest.raises((ValueError, TypeError)):
         resolve_placements([{"object_id": 1, "box": [0, 0, 1, None]}], sizes)
+    # Python ints do not wrap into the int32 fields of the C ABI: Pillow's own failures for such boxes
+    # (Image.resize / alpha_composite argument parsing: OverflowError; an unallocatable target: MemoryError)
+    with pytest.raises(OverflowError):
+        resolve_placements([{"object_id": 1, "box": [0, 0, 2**31, 10]}], sizes)
+    with pytest.raises(OverflowError):
+        resolve_placements([{"object_id": 1, "box": [2**40, 0, 2**40 + 5, 10]}], sizes)
+    with pytest.raises(OverflowError):
+        resolve_placements([{"object_id": 1, "box": [-2**40, 0, -2**40 + 5, 10]}], sizes)
+    with pytest.raises(MemoryError):
+        resolve_placements([{"object_id": 1, "box": [0, 0, 2**30 + 5, 2]}], sizes)
+    assert resolve_placements([{"object_id": 1, "box": [2**30 + 1, 0, 2**30 + 11, 10]}], sizes) == []  # clipped away entirely
 
 
 def test_synthetic_workload_is_deterministic_and_in_spec():
