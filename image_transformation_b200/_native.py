@@ -10,6 +10,9 @@ import ctypes
 import os
 from ctypes import POINTER, c_char_p, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 
+import numpy as np
+from PIL import Image
+
 _PKG = os.path.dirname(os.path.abspath(__file__))
 # B200COMP_LIB selects another build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("B200COMP_LIB") or os.path.join(_PKG, "_lib", "libb200comp.so")
@@ -144,12 +147,19 @@ def device_count_quiet() -> int:
         return 0
 
 
+_gpu_seen = False
+
+
 def require_gpu() -> None:
+    global _gpu_seen
+    if _gpu_seen:  # devices do not go away; the C entry points still fail loudly if one does
+        return
     if _load().b200comp_device_count() < 1:
         raise B200CompError(
             "no CUDA device visible: the B200 compositor has no CPU fallback "
             "(use the reference's own compositor.py on machines without a GPU)"
         )
+    _gpu_seen = True
 
 
 # ---------------------------------------------------------------------------- PIL <-> memory
@@ -170,39 +180,78 @@ _capsule_ptr.restype = c_void_p
 _capsule_ptr.argtypes = [ctypes.py_object, c_char_p]
 
 
-def _arrow_view(img):
-    """(H, W, 4) uint8 view of a single-block RGBA image's own pixels, or None if Pillow cannot export it without a
-    copy (older Pillow, image spread over several blocks, buffer-backed image)."""
-    import numpy as np
+_memview = ctypes.pythonapi.PyMemoryView_FromMemory
+_memview.restype = ctypes.py_object
+_memview.argtypes = [c_void_p, ctypes.c_ssize_t, ctypes.c_int]
+_PyBUF_WRITE = 0x200
 
-    if img.mode != "RGBA" or not hasattr(img, "__arrow_c_array__") or getattr(img, "readonly", 0):
+
+def _make_view_type():
+    class _PixelView(np.ndarray):
+        # attributes: _b200_capsules (owner of the memory), ptr (address of pixel (0, 0))
+        pass
+
+    return _PixelView
+
+
+_PixelViewType = None
+
+
+def pixel_block(img):
+    """(address, owner) of a single-block RGBA image's own pixel memory -- rows of width * 4 bytes, no padding -- or
+    None if Pillow cannot export it without a copy (older Pillow, image spread over several blocks, buffer-backed
+    image).  `owner` (an Arrow capsule) holds a reference to the block: keep it for as long as the address is used."""
+    if img.mode != "RGBA" or getattr(img, "readonly", 0):
         return None
     try:
-        capsules = img.__arrow_c_array__()
-    except (ValueError, NotImplementedError):
+        img.load()
+        capsule = img.im.__arrow_c_array__()  # (Image.__arrow_c_array__ would also build a schema capsule nobody reads)
+    except (ValueError, NotImplementedError, AttributeError):
         return None
-    arr = _ArrowArray.from_address(_capsule_ptr(capsules[1], b"arrow_array"))
-    w, h = img.size
+    arr = _ArrowArray.from_address(_capsule_ptr(capsule, b"arrow_array"))
     if arr.n_children != 1 or arr.offset != 0:
         return None
     child = arr.children[0].contents
-    if child.length != w * h * 4 or child.offset != 0 or child.n_buffers < 2 or not child.buffers[1]:
+    w, h = img.size
+    if child.length != w * h * 4 or child.offset != 0 or child.n_buffers < 2:
         return None
-    buf = (ctypes.c_uint8 * (w * h * 4)).from_address(child.buffers[1])
-    view = np.frombuffer(buf, np.uint8).reshape(h, w, 4)
-    _keepalive[id(buf)] = None  # (placeholder so linters see the import used)
-    _keepalive.pop(id(buf))
-    buf._b200_capsules = capsules  # the capsules own a reference to the image memory: they live as long as the view
+    ptr = child.buffers[1]
+    return (ptr, capsule) if ptr else None
+
+
+def _arrow_view(img):
+    """(H, W, 4) uint8 numpy view of pixel_block(img), or None."""
+    global _PixelViewType
+    blk = pixel_block(img)
+    if blk is None:
+        return None
+    if _PixelViewType is None:
+        _PixelViewType = _make_view_type()
+    w, h = img.size
+    view = np.frombuffer(_memview(blk[0], w * h * 4, _PyBUF_WRITE), np.uint8).reshape(h, w, 4).view(_PixelViewType)
+    view._b200_capsules = blk[1]  # lives as long as the view
+    view.ptr = blk[0]
     return view
 
 
-_keepalive: dict = {}
+def data_ptr(a) -> int:
+    """Address of element 0 of an array handed to the C ABI (views of image blocks carry it; ndarray.ctypes is slow)."""
+    p = getattr(a, "ptr", None)
+    return p if p is not None else a.ctypes.data
+
+
+def new_rgba_block(w: int, h: int):
+    """A fresh single-block RGBA image (uninitialised pixels) and pixel_block() of it, or (None, None)."""
+    if hasattr(Image.core, "new_block"):
+        img = Image.Image()._new(Image.core.new_block("RGBA", (w, h)))
+        blk = pixel_block(img)
+        if blk is not None:
+            return img, blk
+    return None, None
 
 
 def new_rgba_image(w: int, h: int):
-    """A fresh single-block RGBA image (uninitialised pixels) and the writable view of its memory."""
-    from PIL import Image
-
+    """A fresh single-block RGBA image (uninitialised pixels) and the writable numpy view of its memory."""
     if hasattr(Image.core, "new_block"):
         img = Image.Image()._new(Image.core.new_block("RGBA", (w, h)))
         view = _arrow_view(img)
@@ -216,14 +265,11 @@ def rgba_array(img):
     own memory when Pillow can export it (single-block images: everything up to 16 MB, and every image this package
     returned), else a copy -- through a single-block image and Pillow's C paste when possible (about three times
     faster than np.asarray / tobytes()), np.asarray as the last resort."""
-    import numpy as np
-    from PIL import Image
-
     if img.mode == "RGBA":
-        img.load()
-        view = _arrow_view(img)
+        view = _arrow_view(img)  # (loads the image)
         if view is not None:
             return view
+        img.load()
         if hasattr(Image.core, "new_block") and img.size[0] > 0 and img.size[1] > 0:
             try:
                 blk = Image.core.new_block("RGBA", img.size)
@@ -239,8 +285,6 @@ def rgba_array(img):
 def image_from_rgba(out):
     """PIL RGBA image holding the pixels of a (H, W, 4) uint8 array (one copy into an image Pillow owns; callers on
     the hot path avoid even that by letting the library write into new_rgba_image())."""
-    from PIL import Image
-
     h, w = out.shape[:2]
     img, view = new_rgba_image(w, h) if w > 0 and h > 0 else (None, None)
     if img is None:

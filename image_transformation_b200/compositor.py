@@ -70,10 +70,6 @@ def resolve_placements(placements: Sequence[dict], sizes: Dict[int, Tuple[int, i
     return out
 
 
-def _rgba_array(img: Image.Image) -> np.ndarray:
-    return _native.rgba_array(img)
-
-
 # ---- device-resident cutouts of a bundle (macro_placement_test.py:1493, 1679 reload the same results.json before
 # every composite of the refine loop) ----------------------------------------------------------------------------
 _memcmp = ctypes.CDLL(None).memcmp
@@ -117,17 +113,30 @@ def _cutout_cache_enabled() -> bool:
     return os.environ.get("B200COMP_CUTOUT_CACHE", "1") != "0"
 
 
-def _solid_colour_of(img: Image.Image, arr: np.ndarray):
+def _pixels(img: Image.Image):
+    """(address, pitch, keepalive) of an RGBA image's pixels for one library call: the image's own block when Pillow
+    exports it (no copy, no numpy), else a contiguous copy."""
+    blk = _native.pixel_block(img)
+    if blk is not None:
+        return blk[0], img.size[0] * 4, blk[1]
+    a = _native.rgba_array(img)
+    return _native.data_ptr(a), a.strides[0], a
+
+
+_u32_at = ctypes.c_uint32.from_address
+
+
+def _solid_colour_of(img: Image.Image, ptr: int, nbytes: int):
     """RGBA value (little-endian uint32) of a canvas made by fill_solid() that is still all one colour, else None.
-    The tag alone is not trusted: the caller may have drawn on the canvas since.  One memcmp of the buffer against
-    itself shifted by a pixel proves every pixel equals the first (cheaper than the upload it saves)."""
+    `ptr` / `nbytes`: the canvas pixels, tightly packed.  The tag alone is not trusted: the caller may have drawn on
+    the canvas since.  One memcmp of the buffer against itself shifted by a pixel proves every pixel equals the first
+    (cheaper than the upload it saves)."""
     colour = getattr(img, "_b200_solid", None)
-    if colour is None or not arr.flags.c_contiguous or arr.nbytes < 4:
+    if colour is None or nbytes < 4:
         return None
-    if int(arr.reshape(-1)[:4].view(np.uint32)[0]) != colour:
+    if _u32_at(ptr).value != colour:
         return None
-    base = arr.ctypes.data
-    if arr.nbytes > 4 and _memcmp(base, base + 4, arr.nbytes - 4) != 0:
+    if nbytes > 4 and _memcmp(ptr, ptr + 4, nbytes - 4) != 0:
         return None
     return colour
 
@@ -151,35 +160,38 @@ def composite(background_img: Image.Image, object_images: Dict[int, Image.Image]
 
     _native.require_gpu()
     W, H = background_img.size
-    bg = _rgba_array(background_img)
-    result, out = _native.new_rgba_image(W, H)
-    if result is None:  # Pillow without the Arrow export: plain array, one more copy at the end
+    bg_ptr, bg_pitch, bg_keep = _pixels(background_img)
+    result, blk = _native.new_rgba_block(W, H)  # the library writes straight into an image Pillow owns
+    if result is not None:
+        out, out_ptr, out_pitch = None, blk[0], W * 4
+    else:  # Pillow without the Arrow export: plain array, one more copy at the end
         out = np.empty((H, W, 4), np.uint8)
-    arrays: Dict[int, np.ndarray] = {}
-    keep = []
+        out_ptr, out_pitch = out.ctypes.data, out.strides[0]
+    pixels: Dict[int, tuple] = {}
+    keep = [bg_keep, blk]
     recs = (_native.Placement * len(resolved))()
     for i, (oid, x, y, w, h, flags) in enumerate(resolved):
         img = object_images[oid]
+        px = pixels.get(oid)
+        if px is None:
+            px = pixels[oid] = _pixels(img)
+        ptr, pitch, _ = px
+        sw, sh = img.size
         dev = getattr(img, "_b200_dev", None)
-        if oid not in arrays:
-            arrays[oid] = _rgba_array(img)
-        a = arrays[oid]
-        if (dev is not None and dev.ptr and a.shape == dev.host.shape and a.flags.c_contiguous and dev.host.flags.c_contiguous
-                and _memcmp(a.ctypes.data, dev.host.ctypes.data, a.nbytes) == 0):
+        if dev is not None and dev.ptr and pitch == sw * 4 and dev.host.shape == (sh, sw, 4) and dev.host.flags.c_contiguous \
+                and _memcmp(ptr, _native.data_ptr(dev.host), sw * sh * 4) == 0:
             # uploaded by load_object_images and still pixel for pixel what was uploaded
             keep.append(dev)
-            recs[i] = _native.Placement(dev.ptr, dev.pitch, img.size[0], img.size[1], x, y, w, h,
-                                        flags | _native.SRC_DEVICE, 0)
+            recs[i] = _native.Placement(dev.ptr, dev.pitch, sw, sh, x, y, w, h, flags | _native.SRC_DEVICE, 0)
             continue
-        recs[i] = _native.Placement(a.ctypes.data, a.strides[0], a.shape[1], a.shape[0], x, y, w, h, flags, 0)
-    solid = _solid_colour_of(background_img, bg)
+        recs[i] = _native.Placement(ptr, pitch, sw, sh, x, y, w, h, flags, 0)
+    solid = _solid_colour_of(background_img, bg_ptr, W * H * 4) if bg_pitch == W * 4 else None
     if solid is not None:  # fill_solid() canvas, untouched: synthesised on the device from the colour
-        rc = _native.lib().b200comp_composite_host_ex(None, solid, W, H, 0, out.ctypes.data, out.strides[0], recs, len(resolved))
+        rc = _native.lib().b200comp_composite_host_ex(None, solid, W, H, 0, out_ptr, out_pitch, recs, len(resolved))
     else:
-        rc = _native.lib().b200comp_composite_host_ex(bg.ctypes.data, 0, W, H, bg.strides[0], out.ctypes.data, out.strides[0],
-                                                      recs, len(resolved))
+        rc = _native.lib().b200comp_composite_host_ex(bg_ptr, 0, W, H, bg_pitch, out_ptr, out_pitch, recs, len(resolved))
     _native.check(rc, "composite")
-    del keep
+    del keep, pixels
     return result if result is not None else _native.image_from_rgba(out)
 
 
@@ -216,7 +228,7 @@ def load_object_images(results_json_path: str) -> Dict[int, Image.Image]:
         for oid, img in images.items():
             dev = None
             if img.size[0] > 0 and img.size[1] > 0:
-                dev = _DeviceCutout(_rgba_array(img))
+                dev = _DeviceCutout(_native.rgba_array(img))
                 CUTOUT_CACHE_STATS["uploads"] += 1
             entry[oid] = (img, dev)
         while len(_CUTOUT_CACHE) >= _CUTOUT_CACHE_MAX:

@@ -301,6 +301,42 @@ __global__ void __launch_bounds__(96) median_from_hist_kernel(const unsigned lon
 
 namespace b200comp {
 
+// ---- the library's own stream-ordered memory pool -------------------------------------------------------
+// Scratch buffers and plans come and go (one plan per chunk in the host-buffer pipeline).  They are taken from a
+// pool this library creates per device, with a release threshold that keeps freed blocks cached: a repeated call
+// pays a pool lookup, not a device allocation (about a millisecond).  The process's default pool, and whatever
+// policy the host application gave it, is left alone; b200comp_trim() hands the cached memory back.
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pools[64] = {};
+static cudaMemPool_t lib_pool(int device) {
+    if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    if (!g_pools[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        g_pools[device] = pool;
+    }
+    return g_pools[device];
+}
+static cudaError_t lib_malloc_async(void **p, size_t bytes, cudaStream_t st) {
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return e;
+    cudaMemPool_t pool = lib_pool(device);
+    if (!pool) return cudaMallocAsync(p, bytes, st);  // pools unsupported: the default pool as it is
+    return cudaMallocFromPoolAsync(p, bytes, pool, st);
+}
+
 // =====================================================================================
 // Host side
 // =====================================================================================
@@ -546,9 +582,9 @@ static int build_packed_on_device(const TableSet &ts, int32_t *d_tables, cudaStr
         return -1;
     };
     cudaError_t e;
-    if ((e = cudaMallocAsync((void **)&d_jobs, jobs.size() * sizeof(CoefJob), st)) != cudaSuccess) return fail_cuda(e);
-    if ((e = cudaMallocAsync((void **)&d_fix, (size_t)fix_cap * sizeof(CoefFix), st)) != cudaSuccess) return fail_cuda(e);
-    if ((e = cudaMallocAsync((void **)&d_count, sizeof(int), st)) != cudaSuccess) return fail_cuda(e);
+    if ((e = lib_malloc_async((void **)&d_jobs, jobs.size() * sizeof(CoefJob), st)) != cudaSuccess) return fail_cuda(e);
+    if ((e = lib_malloc_async((void **)&d_fix, (size_t)fix_cap * sizeof(CoefFix), st)) != cudaSuccess) return fail_cuda(e);
+    if ((e = lib_malloc_async((void **)&d_count, sizeof(int), st)) != cudaSuccess) return fail_cuda(e);
     if ((e = cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(CoefJob), cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail_cuda(e);
     if ((e = cudaMemsetAsync(d_count, 0, sizeof(int), st)) != cudaSuccess) return fail_cuda(e);
     const unsigned gx = (unsigned)std::min(16, (max_out + 127) / 128);
@@ -592,7 +628,7 @@ static int build_packed_on_device(const TableSet &ts, int32_t *d_tables, cudaStr
                 }
         }
         WordPatch *d_patches = nullptr;
-        if ((e = cudaMallocAsync((void **)&d_patches, patches.size() * sizeof(WordPatch), st)) != cudaSuccess) return fail_cuda(e);
+        if ((e = lib_malloc_async((void **)&d_patches, patches.size() * sizeof(WordPatch), st)) != cudaSuccess) return fail_cuda(e);
         e = cudaMemcpyAsync(d_patches, patches.data(), patches.size() * sizeof(WordPatch), cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) {
             patch_words_kernel<<<(unsigned)((patches.size() + 255) / 256), 256, 0, st>>>(reinterpret_cast<uint32_t *>(d_tables),
@@ -682,27 +718,6 @@ struct b200comp_plan {
     std::vector<void *> owned;  // device allocations freed with the plan
 };
 
-// Every entry point that takes scratch memory from the stream-ordered pool calls this first: scratch buffers
-// and plans come and go (one plan per chunk in the host-buffer pipeline), and with the default release threshold
-// (0) the pool hands its memory back to the driver at every synchronisation, so each call would pay a fresh
-// device allocation (about a millisecond) instead of a pool lookup.
-static void keep_pool_memory(int device) {
-    static std::mutex mu;
-    static std::vector<int> tuned;
-    std::lock_guard<std::mutex> lock(mu);
-    if (std::find(tuned.begin(), tuned.end(), device) != tuned.end()) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    tuned.push_back(device);
-}
-static void keep_pool_memory() {
-    int device = 0;
-    if (cudaGetDevice(&device) == cudaSuccess) keep_pool_memory(device);
-}
-
 // number of waves a run over `count` canvases / `n_tiles` tiles is cut into (b200comp_plan_run_canvases)
 static int wave_count(const b200comp_plan *plan, int64_t n_tiles, int count) {
     const char *e = std::getenv("B200COMP_WAVES");  // read at every run: the parity tests compare wave counts
@@ -728,6 +743,14 @@ static_assert(sizeof(b200comp_placement) == 48 && sizeof(b200comp_canvas) == 56,
 extern "C" {
 
 int b200comp_abi_version(void) { return B200COMP_ABI_VERSION; }
+// internal helpers shared with host_api.cu (not part of the public header): the library pool
+int b200comp_pool_alloc_(void **p, size_t bytes, void *stream) { return (int)lib_malloc_async(p, bytes, S(stream)); }
+void b200comp_pool_trim_(void) {
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64) return;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    if (g_pools[device]) cudaMemPoolTrimTo(g_pools[device], 0);
+}
 // internal helper shared with host_api.cu (not part of the public header)
 int b200comp_set_error_(int code, const char *msg) { return fail(code, msg ? msg : ""); }
 const char *b200comp_last_error(void) { return g_err.c_str(); }
@@ -775,7 +798,6 @@ int b200comp_resize_rgba_lanczos(const uint8_t *src, int sw, int sh, size_t src_
     if (w == sw && h == sh)
         return resample_two_pass(src, sw, sh, (int64_t)src_pitch, dst, w, h, (int64_t)dst_pitch, nullptr, nullptr, 0,
                                  nullptr, nullptr, 0, nullptr, flags, st);
-    keep_pool_memory();
     // The fused tile kernel in "replace" mode onto a canvas that is the destination: prepared planar source, TMA patch
     // chunks, dp4a passes, device-built coefficient tables (scales down to 2.66x; buffers of any 4-byte alignment).
     // Only what it cannot take -- more taps, Pillow 12's vertical-first order -- goes through the generic kernels below.
@@ -815,7 +837,7 @@ int b200comp_resize_rgba_lanczos(const uint8_t *src, int sw, int sh, size_t src_
     const size_t tbytes = ts.host.size() * sizeof(int32_t);
     const size_t sbytes = (size_t)std::max((int64_t)sh * w, (int64_t)h * sw) * 4;
     uint8_t *d_mem = nullptr;
-    CUDA_TRY(cudaMallocAsync((void **)&d_mem, tbytes + sbytes + 16, st));
+    CUDA_TRY(lib_malloc_async((void **)&d_mem, tbytes + sbytes + 16, st));
     int32_t *d_t = reinterpret_cast<int32_t *>(d_mem);
     uint8_t *d_s = d_mem + ((tbytes + 15) & ~(size_t)15);
     cudaError_t e = cudaMemcpyAsync(d_t, ts.host.data(), tbytes, cudaMemcpyHostToDevice, st);
@@ -868,10 +890,9 @@ int b200comp_fill_gradient(uint8_t *dst, int W, int H, size_t pitch, int horizon
     if (!dst || W < 1 || H < 1 || !c1 || !c2) return fail(B200COMP_EINVAL, "fill_gradient: bad argument");
     if (!aligned4(dst, (int64_t)pitch)) return fail(B200COMP_EINVAL, "fill_gradient: buffer must be 4-byte aligned");
     cudaStream_t st = S(stream);
-    keep_pool_memory();
     const int n = horizontal ? W : H;
     uint32_t *lut = nullptr;
-    CUDA_TRY(cudaMallocAsync((void **)&lut, (size_t)n * 4, st));
+    CUDA_TRY(lib_malloc_async((void **)&lut, (size_t)n * 4, st));
     gradient_lut_kernel<<<(n + 255) / 256, 256, 0, st>>>(lut, n, c1[0], c1[1], c1[2], c2[0], c2[1], c2[2]);
     const int vec_ok = ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)pitch) & 15u) == 0;
     const int64_t items = (int64_t)H * ((W + 1023) / 1024);
@@ -890,10 +911,9 @@ int b200comp_masked_median_rgb(const uint8_t *img, int W, int H, size_t pitch, i
         return fail(B200COMP_EINVAL, "median: rectangle outside the image or empty");
     if (!aligned4(img, (int64_t)pitch)) return fail(B200COMP_EINVAL, "median: buffer must be 4-byte aligned");
     cudaStream_t st = S(stream);
-    keep_pool_memory();
     unsigned long long *d = nullptr;  // [2*3*256] hist + [2] counts + 3 int32 result
     const size_t bytes = (2 * 3 * 256 + 2) * sizeof(unsigned long long) + 4 * sizeof(int32_t);
-    CUDA_TRY(cudaMallocAsync((void **)&d, bytes, st));
+    CUDA_TRY(lib_malloc_async((void **)&d, bytes, st));
     cudaError_t e = cudaMemsetAsync(d, 0, bytes, st);
     int32_t *d_out = reinterpret_cast<int32_t *>(d + 2 * 3 * 256 + 2);
     if (e == cudaSuccess) {
@@ -964,7 +984,6 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
         ~Guard() { if (p) b200comp_plan_destroy(p); }
     } guard{plan};
     CUDA_TRY(cudaGetDevice(&plan->device));
-    keep_pool_memory(plan->device);
     plan->create_stream = st;
     plan->n_canvases = n_canvases;
 
@@ -1108,7 +1127,7 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
     bool tables_on_device = !host_tables;
     const size_t tbytes = ((size_t)ts.total + 4) * sizeof(int32_t);
     auto dev_alloc = [&](void **p, size_t bytes) -> cudaError_t {
-        cudaError_t e = cudaMallocAsync(p, std::max<size_t>(bytes, 16), st);
+        cudaError_t e = lib_malloc_async(p, std::max<size_t>(bytes, 16), st);
         if (e == cudaSuccess) plan->owned.push_back(*p);
         return e;
     };

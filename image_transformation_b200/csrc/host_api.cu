@@ -18,6 +18,9 @@
 
 #include "../../include/b200comp.h"
 
+extern "C" int b200comp_pool_alloc_(void **p, size_t bytes, void *stream);  // b200comp.cu: the library's own memory pool
+extern "C" void b200comp_pool_trim_(void);
+
 namespace {
 
 thread_local std::string g_host_err;
@@ -31,17 +34,9 @@ struct DevBuf {
     ~DevBuf() { if (p) cudaFreeAsync(p, st); }
     cudaError_t alloc(size_t bytes, cudaStream_t stream) {
         st = stream;
-        return cudaMallocAsync(&p, std::max<size_t>(bytes, 16), stream);
+        return (cudaError_t)b200comp_pool_alloc_(&p, std::max<size_t>(bytes, 16), stream);
     }
 };
-
-void keep_pool_memory(int device) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-}
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -82,7 +77,6 @@ int b200comp_composite_batch_host(const b200comp_canvas *canvases, int n_canvase
         return b200comp_set_error_(B200COMP_EINVAL, "composite_batch_host: empty batch or null arrays");
     int device = 0;
     if (cudaGetDevice(&device) != cudaSuccess) return b200comp_set_error_(B200COMP_ECUDA, "no CUDA device");
-    keep_pool_memory(device);
     // B200COMP_TRACE=1: host-side timeline of the pipeline on stderr
     static const bool trace = std::getenv("B200COMP_TRACE") != nullptr;
     const auto t_start = std::chrono::steady_clock::now();
@@ -618,9 +612,7 @@ int b200comp_device_free(uint8_t *dev) { return cudaFree(dev) == cudaSuccess ? 0
 
 int b200comp_trim(void) {
     g_lean.release();
-    int device = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&device) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    b200comp_pool_trim_();
     return 0;
 }
 

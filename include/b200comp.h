@@ -199,8 +199,9 @@ int b200comp_composite_host_ex(const uint8_t *bg, uint32_t solid_rgba, int W, in
 /* Device-resident copy of a decoded RGBA image (16-byte aligned pitch); free with b200comp_device_free. */
 int b200comp_device_upload(const uint8_t *img, int w, int h, size_t pitch, uint8_t **dev, size_t *dev_pitch);
 int b200comp_device_free(uint8_t *dev);
-/* Give cached memory back to the driver: the stream-ordered pool the library allocates from and the calling
- * thread's cached host-call context (pinned bounce buffers, device staging). */
+/* Give cached memory back to the driver: the library's own stream-ordered memory pool (created per device; the
+ * process's default pool and its release threshold are never touched) and the calling thread's cached host-call
+ * context (pinned bounce buffers, device staging). */
 int b200comp_trim(void);
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
 int b200comp_host_alloc(void **ptr, size_t bytes);

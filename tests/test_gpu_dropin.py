@@ -154,15 +154,19 @@ def test_fill_solid_canvas_is_passed_by_colour_until_it_is_drawn_on(tmp_path):
     obj = rng.integers(0, 256, (90, 120, 4), dtype=np.uint8)
     pl = [{"object_id": 1, "box": [10, 5, 170, 125]}, {"object_id": 1, "box": [150, 60, 270, 150]}]
     canvas = fill_solid(str(bgp), (300, 200))
-    colour = C._solid_colour_of(canvas, _native.rgba_array(canvas))
+    def tagged(img, pixels_of):
+        a = _native.rgba_array(pixels_of)
+        return C._solid_colour_of(img, _native.data_ptr(a), a.nbytes)
+
+    colour = tagged(canvas, canvas)
     assert colour is not None and colour >> 24 == 255
     exp = oracle.composite(np.array(canvas), {1: obj}, pl)
     assert_same(np.array(C.composite(canvas, {1: pil(obj)}, pl)), exp, "solid canvas by value")
     canvas.putpixel((299, 199), (1, 2, 3, 4))  # last pixel: the cheapest place to miss
-    assert C._solid_colour_of(canvas, _native.rgba_array(canvas)) is None
+    assert tagged(canvas, canvas) is None
     exp = oracle.composite(np.array(canvas), {1: obj}, pl)
     assert_same(np.array(C.composite(canvas, {1: pil(obj)}, pl)), exp, "drawn-on canvas by buffer")
-    assert C._solid_colour_of(canvas.copy(), _native.rgba_array(canvas)) is None  # copies carry no tag
+    assert tagged(canvas.copy(), canvas) is None  # copies carry no tag
 
 
 def test_load_object_images_and_cutout_cache_around_the_refine_loop(tmp_path):
