@@ -497,6 +497,13 @@ enum : uint32_t {
 // four source rows of one channel: NW LDS.128, 12 * NW dp4a, one word of four clipped bytes stored to
 // Iw[jl][rq][c].  An item whose source words are all zero -- transparent pixels: premultiplied colours are zero
 // as well -- stores zero without computing (whole-warp vote, so the pipes see no divergence).
+// B200COMP_ABLATE: MEASUREMENT builds only (tools/ablate.sh) -- the pixels are wrong.  Parts of a step are compiled out to
+// see what they cost inside the running pipeline: bit 0 the H pass arithmetic, bit 1 the V pass, bit 2 the V pass's taps /
+// over / store (its loads, votes and addressing stay), bit 3 the V pass's window start and coefficient row.
+#ifndef B200COMP_ABLATE
+#define B200COMP_ABLATE 0
+#endif
+
 template <int NW, int NCH>
 __device__ __forceinline__ void slab_hpass(const uint32_t *__restrict__ P, int slot_words, SlabBars *bars, uint32_t &cseq,
                                            const Watch &watch, uint32_t *__restrict__ Iw, int CS, int NRQ, int pwc,
@@ -620,9 +627,17 @@ __device__ __forceinline__ void slab_vpass(const uint32_t *__restrict__ Iw, int 
     for (int r0 = 0; r0 < tho; r0 += 32) {
         const int lrow = min(r0 + lane, tho - 1);
         const int y = oy0 + lrow;
+#if B200COMP_ABLATE & 8  // no window start, no coefficient row
+        const int wb4 = 0;
+        uint32_t k0[NW], k1[NW], k2[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) k0[i] = k1[i] = k2[i] = (uint32_t)y * 0x01010101u;
+        (void)scale; (void)support; (void)ply; (void)rw0;
+#else
         const int wb4 = ((first_tap(y, scale, support) >> 2) - rw0) * 4;
         uint32_t k0[NW], k1[NW], k2[NW];
         load_coef_row<NW>(ply, y, k0, k1, k2);
+#endif
         const int r = dy + lrow;
         const uint32_t crow = smem_u32(ct) + 4u * (uint32_t)((r << 5) + ((col0 & 32) ? kTileH * 32 : 0));
         const uint32_t p_lo = crow + 4u * (uint32_t)((((col0 >> 2) ^ r) & 7) << 2);
@@ -634,6 +649,13 @@ __device__ __forceinline__ void slab_vpass(const uint32_t *__restrict__ Iw, int 
 #pragma unroll
             for (int i = 0; i < NW; ++i) v[i] = lds128(col + 16u * i);
             const uint32_t cpx = ((xx & 4) ? p_hi : p_lo) + 4u * (uint32_t)(xx & 3);
+#if B200COMP_ABLATE & 4  // loads, votes and addresses, no taps / over / store
+            uint32_t sink = cpx;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) sink ^= v[i].x ^ v[i].y ^ v[i].z ^ v[i].w ^ k0[i] ^ k1[i] ^ k2[i];
+            if (__any_sync(0xffffffffu, sink == 0x12345u)) sts32(cpx, sink);
+            continue;
+#endif
             if (NCH == 3) {
                 vcol3<NW>(v, cpx, k0, k1, k2);
             } else {
@@ -908,6 +930,14 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                     const int j = ox0 + (active ? X : xa) - dx;  // lanes off the step read a valid column's table
 #define B200_HPASS(NWX, NCH_) \
     slab_hpass<NWX, NCH_>(P, slot_words, bars, cseq, watch, Iw, CS, NRQ, pwc, cw0, j, active, scale_x, support_x, plx, n_out_x)
+#if B200COMP_ABLATE & 1  // the H pass does nothing but hand the chunks on
+                    for (int q0 = 0; q0 < NRQ; q0 += kChunkQuads, ++cseq) {
+                        const int ps = (int)(cseq % kPRing);
+                        mbar_wait(&bars->p_full[ps], (cseq / kPRing) & 1u, watch, kTagRoleConsumer | kTagPatchFull, cseq);
+                        named_bar_arrive(1 + ps, (kSlabWarps + 1) * 32);
+                    }
+                    (void)j; (void)cw0; (void)pwc; (void)plx; (void)n_out_x; (void)support_x;
+#else
                     if (nch == 4) {
                         if (nwx == 3) B200_HPASS(3, 4);
                         else if (nwx == 4) B200_HPASS(4, 4);
@@ -917,11 +947,15 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                         else if (nwx == 4) B200_HPASS(4, 3);
                         else B200_HPASS(5, 3);
                     }
+#endif
 #undef B200_HPASS
                     __syncwarp();  // the slab's intermediate is complete
                     if (ready_pending) tile_wait();
 #define B200_VPASS(NWY, NCH_) \
     slab_vpass<NWY, NCH_>(Iw, CS, ct, xa, xb, col0, rw0, oy0, tho, dy, scale_y, support_y, ply, replace)
+#if B200COMP_ABLATE & 2  // no V pass, no over
+                    (void)rw0; (void)n_out_y; (void)support_y; (void)replace;
+#else
                     if (nch == 4) {
                         if (nwy == 3) B200_VPASS(3, 4);
                         else if (nwy == 4) B200_VPASS(4, 4);
@@ -931,6 +965,7 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                         else if (nwy == 4) B200_VPASS(4, 3);
                         else B200_VPASS(5, 3);
                     }
+#endif
 #undef B200_VPASS
                     __syncwarp();  // the next step's H pass overwrites the intermediate
                 }
