@@ -672,6 +672,7 @@ struct b200comp_plan {
     DevCanvas *d_canvases = nullptr;
     int *d_status = nullptr;
     int slot_words = 0, iw_words = 0;  // ring slot of the widest patch class / private intermediate of one warp
+    int n_ring = kPRingMin;            // slots of the patch chunk ring (as many as keep kCtasPerSm CTAs per SM resident)
     size_t smem_bytes = 0;
     int64_t info[B200COMP_INFO_COUNT] = {0};
     // placements resampled by the generic kernels before the tile kernel (extreme scales, vertical-first)
@@ -728,11 +729,13 @@ static int wave_count(const b200comp_plan *plan, int64_t n_tiles, int count) {
 }
 
 static const size_t kMaxSmemBytes = 200 * 1024;    // opt-in dynamic shared memory limit we request
-static const size_t kFusedSmemCap = 112 * 1024;    // placements needing more go through the generic kernels
-// dynamic shared memory of the tile kernel: alignment slack + resident tiles + patch chunk ring + one private
-// intermediate per compute warp + command blocks + TILE records + mbarriers
-static size_t tile_smem_bytes(int64_t slot_words, int64_t iw_words) {
-    return 1024 + ((size_t)kTileBufs * kTileWords + (size_t)kPRing * slot_words + (size_t)kSlabWarps * iw_words) * 4 +
+// Two CTAs per SM: 228 KB of shared memory less the 1 KB the system reserves per CTA.  Placements needing more (with the
+// shallowest ring) go through the generic kernels.
+static const size_t kFusedSmemCap = 113 * 1024;
+// dynamic shared memory of the tile kernel: resident tiles + patch chunk ring + one private intermediate per compute
+// warp + command blocks + TILE records + mbarriers
+static size_t tile_smem_bytes(int64_t slot_words, int64_t iw_words, int n_ring = kPRingMin) {
+    return ((size_t)kTileBufs * kTileWords + (size_t)n_ring * slot_words + (size_t)kSlabWarps * iw_words) * 4 +
            (size_t)kCmdRing * kCmdBlk * sizeof(Cmd) + (size_t)kTileBufs * 16 * sizeof(uint32_t) + sizeof(SlabBars) + 16;
 }
 // ring slot of a placement whose patch rows are `pwc` word columns wide: kChunkQuads quads x 4 planes x 4 * pwc words
@@ -1369,9 +1372,27 @@ int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const 
 
     plan->slot_words = (max_slot + 31) & ~31;  // slots stay 128-byte aligned
     plan->iw_words = max_iw;
-    plan->smem_bytes = tile_smem_bytes(plan->slot_words, plan->iw_words);
-    if (plan->smem_bytes > kMaxSmemBytes) return fail(B200COMP_EINTERNAL, "plan_create: tile kernel shared memory over the limit");
     CUDA_TRY(cudaFuncSetAttribute(composite_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemBytes));
+    {
+        // deepest ring that keeps the CTAs per SM the kernel is built for (asked of the occupancy calculator, so the
+        // reserved shared memory and register limits of the device at hand are respected); B200COMP_RING=n overrides
+        const char *env = std::getenv("B200COMP_RING");
+        const int forced = env && env[0] ? std::max(kPRingMin, std::min(kPRingMax, std::atoi(env))) : 0;
+        plan->n_ring = kPRingMin;
+        for (int n = forced ? forced : kPRingMax; n > kPRingMin; --n) {
+            const size_t bytes = tile_smem_bytes(plan->slot_words, plan->iw_words, n);
+            int resident = 0;
+            if (bytes <= kMaxSmemBytes &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, composite_slab_kernel, kThreads, bytes) == cudaSuccess &&
+                (resident >= kCtasPerSm || forced)) {
+                plan->n_ring = n;
+                break;
+            }
+        }
+        cudaGetLastError();
+    }
+    plan->smem_bytes = tile_smem_bytes(plan->slot_words, plan->iw_words, plan->n_ring);
+    if (plan->smem_bytes > kMaxSmemBytes) return fail(B200COMP_EINTERNAL, "plan_create: tile kernel shared memory over the limit");
 
     plan->info[B200COMP_INFO_ALGORITHMIC_BYTES] = algo;
     // 3 binning kernels + tile kernel per wave of a whole-plan run
@@ -1535,7 +1556,7 @@ int b200comp_plan_run_canvases(b200comp_plan *plan, int first, int count, void *
         }();
         composite_slab_kernel<<<(unsigned)G, kThreads, plan->smem_bytes + extra_smem, stt>>>(
             streams, stream_off, stream_len, plan->d_canvases, plan->d_maps, reinterpret_cast<const uint32_t *>(plan->d_tables),
-            plan->slot_words, plan->iw_words, plan->d_status, plan->d_dbg);
+            plan->slot_words, plan->iw_words, plan->n_ring, plan->d_status, plan->d_dbg);
         CUDA_TRY(cudaGetLastError());
         c0 = c1;
     }

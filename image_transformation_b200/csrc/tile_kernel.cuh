@@ -448,7 +448,7 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
 // Shared-memory rendezvous points of one CTA.  Every ring uses the n-th use of a slot <-> phase parity
 // (n / ring size) & 1 convention; a producer re-fills a slot only after the matching `empty` / `free` phase.
 struct SlabBars {
-    uint64_t p_full[kPRing], p_empty[kPRing];                            // patch chunks
+    uint64_t p_full[kPRingMax], p_empty[kPRingMax];                      // patch chunks (n_ring of them in use)
     uint64_t t_ready[kTileBufs], t_done[kTileBufs], t_free[kTileBufs];  // resident tiles
     uint64_t c_full[kCmdRing], c_empty[kCmdRing];                        // command blocks
 };
@@ -505,7 +505,7 @@ enum : uint32_t {
 #endif
 
 template <int NW, int NCH>
-__device__ __forceinline__ void slab_hpass(const uint32_t *__restrict__ P, int slot_words, SlabBars *bars, uint32_t &cseq,
+__device__ __forceinline__ void slab_hpass(const uint32_t *__restrict__ P, int slot_words, int n_ring, SlabBars *bars, RingPos &rp,
                                            const Watch &watch, uint32_t *__restrict__ Iw, int CS, int NRQ, int pwc,
                                            int cw0, int j, bool active, double scale, double support,
                                            const uint32_t *__restrict__ plx, int n_out) {
@@ -521,9 +521,9 @@ __device__ __forceinline__ void slab_hpass(const uint32_t *__restrict__ P, int s
     const uint32_t lane_dst = smem_u32(Iw) + 4u * (uint32_t)(jl * CS + ch0);
     const uint32_t soff0 = active ? (uint32_t)rq0 * QSb + (uint32_t)ch0 * PSb : 0u;
 #pragma unroll 1
-    for (int q0 = 0; q0 < NRQ; q0 += kChunkQuads, ++cseq) {
-        const int s = (int)(cseq % kPRing);
-        mbar_wait(&bars->p_full[s], (cseq / kPRing) & 1u, watch, kTagRoleConsumer | kTagPatchFull, cseq);
+    for (int q0 = 0; q0 < NRQ; q0 += kChunkQuads, ring_next(rp, n_ring)) {
+        const int s = (int)rp.slot;
+        mbar_wait(&bars->p_full[s], rp.phase, watch, kTagRoleConsumer | kTagPatchFull, rp.seq);
         const uint32_t slot = lane_src + (uint32_t)(s * slot_words) * 4u;
         const int n_items = NCH * min(kChunkQuads, NRQ - q0);
         const int n_iter = (n_items + 3) >> 2;
@@ -677,13 +677,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict__ stream_off,
                       const int64_t *__restrict__ stream_len, const DevCanvas *__restrict__ canvases,
                       const uint8_t *__restrict__ maps, const uint32_t *__restrict__ tables, int slot_words, int iw_words,
-                      int *__restrict__ status, uint32_t *__restrict__ dbg) {
-    extern __shared__ uint32_t smem_raw[];
-    // tile buffers need 1024-byte alignment (swizzle atom); the launch reserves the slack
-    uint32_t *ctile = reinterpret_cast<uint32_t *>(
-        reinterpret_cast<uint8_t *>(smem_raw) + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-    uint32_t *P = ctile + kTileBufs * kTileWords;  // kPRing slots of slot_words (a multiple of 32 words)
-    uint32_t *Iw_all = P + kPRing * slot_words;    // one private intermediate of iw_words per compute warp
+                      int n_ring, int *__restrict__ status, uint32_t *__restrict__ dbg) {
+    // tile buffers need 1024-byte alignment (swizzle atom): asked of the launch, no slack reserved by hand
+    extern __shared__ __align__(1024) uint32_t smem_raw[];
+    uint32_t *ctile = smem_raw;
+    uint32_t *P = ctile + kTileBufs * kTileWords;  // n_ring slots of slot_words (a multiple of 32 words)
+    uint32_t *Iw_all = P + n_ring * slot_words;    // one private intermediate of iw_words per compute warp
     Cmd *ring = reinterpret_cast<Cmd *>(Iw_all + kSlabWarps * iw_words);
     uint32_t *trec = reinterpret_cast<uint32_t *>(ring + kCmdRing * kCmdBlk);  // TILE record of each resident tile
     SlabBars *bars = reinterpret_cast<SlabBars *>(trec + kTileBufs * 16);
@@ -692,7 +691,7 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const Watch watch{status, dbg};
     if (tid == 0) {
-        for (int i = 0; i < kPRing; ++i) {
+        for (int i = 0; i < kPRingMax; ++i) {
             mbar_init(&bars->p_full[i], 1);
             mbar_init(&bars->p_empty[i], kSlabWarps);
         }
@@ -727,7 +726,7 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
         if (nblk > 0) load_block(0);
         if (nblk > 1) load_block(1);
         int tseq = 0;
-        uint32_t cseq = 0;
+        RingPos rp;
         for (int pos = 0;; ++pos) {
             const int b = pos / kCmdBlk, s = b % kCmdRing, e = pos % kCmdBlk;
             if (e == 0) {
@@ -786,9 +785,9 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                 const void *map = maps + ((uint64_t)uni(c.w[8]) << 7);
                 const uint32_t bytes = resample ? uni(c.w[11]) * (uint32_t)(kChunkQuads * 64)
                                                 : (uint32_t)(kOverlayBoxW * kIdentRows * 4);
-                for (int ci = c_lo; ci < c_hi; ++ci, ++cseq) {
-                    const int ps = (int)(cseq % kPRing);
-                    if (cseq >= kPRing) named_bar_sync(1 + ps, (kSlabWarps + 1) * 32);
+                for (int ci = c_lo; ci < c_hi; ++ci, ring_next(rp, n_ring)) {
+                    const int ps = (int)rp.slot;
+                    if (rp.seq >= (uint32_t)n_ring) named_bar_sync(1 + ps, (kSlabWarps + 1) * 32);
                     if (lane == 0) {
                         fence_async_smem();
                         mbar_expect_tx(&bars->p_full[ps], bytes);
@@ -848,7 +847,8 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
     const int X = col0 + jl;  // this lane's tile column in the element-wise loops and the H pass
     uint32_t *Iw = Iw_all + warp * iw_words;
     int tseq = -1, steps_left = 0;
-    uint32_t cseq = 0, t_flags = 0u;
+    RingPos rp;  // chunk ring position (same sequence as the producer's)
+    uint32_t t_flags = 0u;
     bool ready_pending = false;  // the wait for the resident tile is deferred to the first access (the H pass does not need it)
     uint32_t *ct = ctile;
     const uint32_t *tr = trec;
@@ -902,9 +902,9 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                 const bool replace = ((w1 >> 23) & 1u) != 0u;  // stand-alone resize: store, do not composite
                 if (xa >= xb) {
                     // not on this warp's slab: pass the chunks on
-                    for (int q0 = 0; q0 < NRQ; q0 += kChunkQuads, ++cseq) {
-                        const int ps = (int)(cseq % kPRing);
-                        mbar_wait(&bars->p_full[ps], (cseq / kPRing) & 1u, watch, kTagRoleConsumer | kTagPatchFull, cseq);
+                    for (int q0 = 0; q0 < NRQ; q0 += kChunkQuads, ring_next(rp, n_ring)) {
+                        const int ps = (int)rp.slot;
+                        mbar_wait(&bars->p_full[ps], rp.phase, watch, kTagRoleConsumer | kTagPatchFull, rp.seq);
                         named_bar_arrive(1 + ps, (kSlabWarps + 1) * 32);
                     }
                 } else {
@@ -929,11 +929,11 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                     const bool active = X >= xa && X < xb;
                     const int j = ox0 + (active ? X : xa) - dx;  // lanes off the step read a valid column's table
 #define B200_HPASS(NWX, NCH_) \
-    slab_hpass<NWX, NCH_>(P, slot_words, bars, cseq, watch, Iw, CS, NRQ, pwc, cw0, j, active, scale_x, support_x, plx, n_out_x)
+    slab_hpass<NWX, NCH_>(P, slot_words, n_ring, bars, rp, watch, Iw, CS, NRQ, pwc, cw0, j, active, scale_x, support_x, plx, n_out_x)
 #if B200COMP_ABLATE & 1  // the H pass does nothing but hand the chunks on
-                    for (int q0 = 0; q0 < NRQ; q0 += kChunkQuads, ++cseq) {
-                        const int ps = (int)(cseq % kPRing);
-                        mbar_wait(&bars->p_full[ps], (cseq / kPRing) & 1u, watch, kTagRoleConsumer | kTagPatchFull, cseq);
+                    for (int q0 = 0; q0 < NRQ; q0 += kChunkQuads, ring_next(rp, n_ring)) {
+                        const int ps = (int)rp.slot;
+                        mbar_wait(&bars->p_full[ps], rp.phase, watch, kTagRoleConsumer | kTagPatchFull, rp.seq);
                         named_bar_arrive(1 + ps, (kSlabWarps + 1) * 32);
                     }
                     (void)j; (void)cw0; (void)pwc; (void)plx; (void)n_out_x; (void)support_x;
@@ -973,9 +973,9 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                 // identity-size overlay: chunks of kIdentRows tile rows of the raw overlay (zero outside it)
                 const int shift = (int)uni(cmd.w[5]);
                 if (ready_pending) tile_wait();
-                for (int ci = dy / kIdentRows; ci <= (dy + tho - 1) / kIdentRows; ++ci, ++cseq) {
-                    const int ps = (int)(cseq % kPRing);
-                    mbar_wait(&bars->p_full[ps], (cseq / kPRing) & 1u, watch, kTagRoleConsumer | kTagPatchFull, cseq);
+                for (int ci = dy / kIdentRows; ci <= (dy + tho - 1) / kIdentRows; ++ci, ring_next(rp, n_ring)) {
+                    const int ps = (int)rp.slot;
+                    mbar_wait(&bars->p_full[ps], rp.phase, watch, kTagRoleConsumer | kTagPatchFull, rp.seq);
                     const uint32_t *slot = P + ps * slot_words;
                     if (X >= xa && X < xb) {
 #pragma unroll
