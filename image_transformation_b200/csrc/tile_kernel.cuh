@@ -499,7 +499,8 @@ enum : uint32_t {
 // as well -- stores zero without computing (whole-warp vote, so the pipes see no divergence).
 // B200COMP_ABLATE: MEASUREMENT builds only (tools/ablate.sh) -- the pixels are wrong.  Parts of a step are compiled out to
 // see what they cost inside the running pipeline: bit 0 the H pass arithmetic, bit 1 the V pass, bit 2 the V pass's taps /
-// over / store (its loads, votes and addressing stay), bit 3 the V pass's window start and coefficient row.
+// over / store (its loads, votes and addressing stay), bit 3 the V pass's window start and coefficient row, bit 4 the patch
+// copies (slots are declared full without a TMA load).
 #ifndef B200COMP_ABLATE
 #define B200COMP_ABLATE 0
 #endif
@@ -788,6 +789,11 @@ composite_slab_kernel(const Cmd *__restrict__ streams, const int64_t *__restrict
                 for (int ci = c_lo; ci < c_hi; ++ci, ring_next(rp, n_ring)) {
                     const int ps = (int)rp.slot;
                     if (rp.seq >= (uint32_t)n_ring) named_bar_sync(1 + ps, (kSlabWarps + 1) * 32);
+#if B200COMP_ABLATE & 16  // no patch traffic: the slot is declared full without a copy
+                    if (lane == 0) mbar_arrive(&bars->p_full[ps]);
+                    (void)map; (void)bytes; (void)w5;
+                    continue;
+#endif
                     if (lane == 0) {
                         fence_async_smem();
                         mbar_expect_tx(&bars->p_full[ps], bytes);
