@@ -8,7 +8,10 @@
 #include <cstdlib>
 #include <cstdint>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <tuple>
@@ -411,26 +414,119 @@ struct LeanCtx {
 };
 thread_local LeanCtx g_lean;
 
-// host memcpy of `rows` rows; large copies (a 4K canvas is 33 MB) are split over a few threads -- one core moves
-// about 10 GB/s, which would make the host copy, not PCIe, the slowest stage of a single-canvas call
-void copy_rows(uint8_t *dst, size_t dst_pitch, const uint8_t *src, size_t src_pitch, size_t row_bytes, int rows) {
-    auto part = [=](int r0, int r1) {
-        if (dst_pitch == src_pitch && row_bytes + 16 > dst_pitch) {
-            std::memcpy(dst + (size_t)r0 * dst_pitch, src + (size_t)r0 * src_pitch, (size_t)(r1 - r0) * dst_pitch - (dst_pitch - row_bytes));
-        } else {
-            for (int r = r0; r < r1; ++r) std::memcpy(dst + (size_t)r * dst_pitch, src + (size_t)r * src_pitch, row_bytes);
+// ---- a few helper threads for large host memcpys ---------------------------------------------------------
+// One core moves about 10 GB/s, which would make the host copy, not PCIe, the slowest stage of a 4K single-canvas
+// call (33 MB in, 33 MB out, tens of MB of cutouts).  The workers are started once and sleep on a condition variable
+// (spawning threads per copy cost ~30 us each); one parallel loop runs at a time -- concurrent callers queue up, which
+// costs nothing: the loop is memory-bandwidth bound.  Never destroyed: worker threads must not be joined from a static
+// destructor at process exit.
+class CopyPool {
+public:
+    static CopyPool &get() {
+        static CopyPool *pool = new CopyPool();
+        return *pool;
+    }
+    int width() const { return (int)workers_.size() + 1; }
+    // fn(i) for i in [0, n): on the workers and the calling thread
+    void parallel_for(int n, const std::function<void(int)> &fn) {
+        if (n <= 0) return;
+        if (n == 1 || workers_.empty()) {
+            for (int i = 0; i < n; ++i) fn(i);
+            return;
         }
-    };
-    const size_t bytes = row_bytes * (size_t)rows;
-    const int n_thr = bytes >= ((size_t)8 << 20) ? (int)std::min<size_t>(4, std::max(1u, std::thread::hardware_concurrency())) : 1;
-    if (n_thr <= 1 || rows < n_thr) {
-        part(0, rows);
+        std::lock_guard<std::mutex> one_loop(loop_mu_);
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            fn_ = &fn;
+            n_ = n;
+            next_.store(0);
+            left_ = n;
+            ++generation_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lock(mu_);
+        done_cv_.wait(lock, [&] { return left_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    CopyPool() {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const int n = (int)std::min(7u, hw > 1 ? hw - 1 : 0u);
+        for (int i = 0; i < n; ++i) {
+            workers_.emplace_back([this] {
+                uint64_t seen = 0;
+                for (;;) {
+                    {
+                        std::unique_lock<std::mutex> lock(mu_);
+                        cv_.wait(lock, [&] { return generation_ != seen; });
+                        seen = generation_;
+                    }
+                    work();
+                }
+            });
+            workers_.back().detach();
+        }
+    }
+    void work() {
+        for (;;) {
+            const std::function<void(int)> *fn;
+            int i;
+            {
+                std::lock_guard<std::mutex> lock(mu_);
+                fn = fn_;
+                i = fn ? next_.fetch_add(1) : n_;
+                if (!fn || i >= n_) return;
+            }
+            (*fn)(i);
+            std::lock_guard<std::mutex> lock(mu_);
+            if (--left_ == 0) done_cv_.notify_all();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex loop_mu_, mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)> *fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int n_ = 0, left_ = 0;
+    uint64_t generation_ = 0;
+};
+
+struct RowCopy {
+    uint8_t *dst;
+    size_t dst_pitch;
+    const uint8_t *src;
+    size_t src_pitch, row_bytes;
+    int rows;
+};
+inline void copy_rows_serial(const RowCopy &c, int r0, int r1) {
+    if (c.dst_pitch == c.src_pitch && c.row_bytes + 16 > c.dst_pitch) {
+        std::memcpy(c.dst + (size_t)r0 * c.dst_pitch, c.src + (size_t)r0 * c.src_pitch,
+                    (size_t)(r1 - r0) * c.dst_pitch - (c.dst_pitch - c.row_bytes));
+    } else {
+        for (int r = r0; r < r1; ++r) std::memcpy(c.dst + (size_t)r * c.dst_pitch, c.src + (size_t)r * c.src_pitch, c.row_bytes);
+    }
+}
+// host memcpy of a set of images (rows of each); small sets on the calling thread, large ones in ~1 MB pieces on the pool
+void copy_images(const RowCopy *copies, int n) {
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) total += copies[i].row_bytes * (size_t)copies[i].rows;
+    if (total < ((size_t)4 << 20)) {
+        for (int i = 0; i < n; ++i) copy_rows_serial(copies[i], 0, copies[i].rows);
         return;
     }
-    std::vector<std::thread> th;
-    for (int t = 1; t < n_thr; ++t) th.emplace_back(part, (int)((int64_t)rows * t / n_thr), (int)((int64_t)rows * (t + 1) / n_thr));
-    part(0, (int)((int64_t)rows / n_thr));
-    for (auto &t : th) t.join();
+    struct Piece { int img, r0, r1; };
+    std::vector<Piece> pieces;
+    for (int i = 0; i < n; ++i) {
+        const int step = (int)std::max<size_t>(1, ((size_t)1 << 20) / std::max<size_t>(1, copies[i].row_bytes));
+        for (int r0 = 0; r0 < copies[i].rows; r0 += step) pieces.push_back(Piece{i, r0, std::min(copies[i].rows, r0 + step)});
+    }
+    CopyPool::get().parallel_for((int)pieces.size(), [&](int k) { copy_rows_serial(copies[pieces[(size_t)k].img], pieces[(size_t)k].r0, pieces[(size_t)k].r1); });
+}
+void copy_rows(uint8_t *dst, size_t dst_pitch, const uint8_t *src, size_t src_pitch, size_t row_bytes, int rows) {
+    const RowCopy c{dst, dst_pitch, src, src_pitch, row_bytes, rows};
+    copy_images(&c, 1);
 }
 
 // rows of a pageable (or pinned) host image -> device, through the pinned bounce buffer in ~4 MB chunks
@@ -541,9 +637,12 @@ int b200comp_composite_host_ex(const uint8_t *bg, uint32_t solid_rgba, int W, in
         if (!(placements[i].flags & B200COMP_SRC_DEVICE)) pp[(size_t)i].src = cx.d_pool + reinterpret_cast<size_t>(pp[(size_t)i].src);
 
     // copy-in: cutouts first (the plan's prepare kernel reads them), then the background
-    for (const Src &s : srcs) {
-        const size_t pitch = align_up((size_t)s.sw * 4, 16);
-        upload_rows(cx.d_pool + s.off, pitch, s.p, (size_t)s.pitch, (size_t)s.sw * 4, s.sh, cx.pin_in + s.off, st);
+    if (!srcs.empty()) {
+        std::vector<RowCopy> cc;
+        for (const Src &s : srcs)
+            cc.push_back(RowCopy{cx.pin_in + s.off, align_up((size_t)s.sw * 4, 16), s.p, (size_t)s.pitch, (size_t)s.sw * 4, s.sh});
+        copy_images(cc.data(), (int)cc.size());  // all cutouts in one parallel pass over the helper threads
+        cudaMemcpyAsync(cx.d_pool, cx.pin_in, pool_bytes, cudaMemcpyHostToDevice, st);
     }
     if (bg) upload_rows(cx.d_bg, dp, bg, bg_pitch, (size_t)W * 4, H, cx.pin_in + pool_bytes, st);
 
