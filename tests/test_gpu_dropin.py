@@ -247,6 +247,40 @@ def test_concurrent_callers():
     assert not errors, errors
 
 
+def test_4k_canvas_through_the_dropin_from_two_threads():
+    """One full-size C3 canvas (3840x2160, 20 objects of 256..1536 px) through PIL in / PIL out: the host copies of
+    such a call are spread over the library's helper threads (host_api.cu CopyPool); two callers at once share them."""
+    from image_transformation_b200 import synth
+    from image_transformation_b200.compositor import composite
+
+    pool = synth.make_pool(12, 256, 1536, seed=1234)
+    sizes_by_id = {k: (v.shape[1], v.shape[0]) for k, v in pool.items()}
+    pls = [synth.canvas_placements(sizes_by_id, (3840, 2160), i) for i in (1, 2)]
+    bgs = []
+    for colour in ((220, 238, 245, 255), (12, 40, 90, 255)):
+        b = np.empty((2160, 3840, 4), np.uint8)
+        b[...] = colour
+        b[::7, ::5, :3] ^= 0x55  # not a solid colour
+        bgs.append(b)
+    exp = [oracle.composite(b, pool, pl) for b, pl in zip(bgs, pls)]
+    objs = {k: pil(v) for k, v in pool.items()}
+    errors = []
+
+    def work(t):
+        try:
+            for _ in range(3):
+                assert_same(np.array(composite(pil(bgs[t]), objs, pls[t])), exp[t], f"4K canvas, thread {t}")
+        except Exception as exc:  # noqa: BLE001
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    assert not errors, errors
+
+
 def test_solid_canvas_and_device_sources_through_the_c_abi():
     """b200comp_composite_host_ex: bg == NULL composites onto the solid colour (what fill_solid returned), and
     B200COMP_SRC_DEVICE placements read cutouts uploaded once with b200comp_device_upload."""
