@@ -6,7 +6,9 @@
 The layout resolver below is a small flex-style placer written for this generator (rows /
 columns, justify, align, gap, then the clamp-into-canvas rule of
 macro_placement_test.py:954-964).  Flex-DSL itself stays in the reference's host Python and
-is out of scope; the hot path only ever sees the resulting integer boxes.
+is out of scope; the hot path only ever sees the resulting integer boxes.  Workload
+``c3_refplacer`` uses layouts resolved by the reference's own placer instead (a committed fixture):
+its coverage statistics agree with this generator's.
 """
 from __future__ import annotations
 
@@ -137,6 +139,28 @@ def flex_layout(rng: np.random.Generator, canvas: Tuple[int, int], items: Sequen
     return [out[int(i)] for i in perm]
 
 
+_REF_LAYOUTS = None
+
+
+def reference_placer_layout(canvas: Tuple[int, int], canvas_idx: int) -> List[Placement]:
+    """Layout `canvas_idx` (modulo the fixture's 256) of tests/golden/c3_reference_layouts.npz: the same object draws as
+    canvas_placements(), a random Flex-DSL tree over them resolved by the REFERENCE's `_place_flex_container` +
+    `_clamp_boxes_to_canvas` on size proxies (generated by tests/golden/make_c3_reference_layouts.py where the reference
+    is available).  Coverage statistics match flex_layout's (74 % of the canvas covered, mean depth 1.24)."""
+    global _REF_LAYOUTS
+    if _REF_LAYOUTS is None:
+        import os
+
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "c3_reference_layouts.npz")
+        d = np.load(path)
+        _REF_LAYOUTS = (d["oid"], d["box"], tuple(int(v) for v in d["canvas"]))
+    oid, box, size = _REF_LAYOUTS
+    if tuple(canvas) != size:
+        raise ValueError(f"reference-placer layouts exist for {size} canvases only")
+    i = canvas_idx % oid.shape[0]
+    return [{"object_id": int(o), "box": [int(v) for v in b]} for o, b in zip(oid[i], box[i]) if o > 0]
+
+
 def canvas_placements(pool_sizes: Dict[int, Tuple[int, int]], canvas: Tuple[int, int], canvas_idx: int,
                       n_objects: int = 20, seed: int = 1234, scale_lo: float = 0.5, scale_hi: float = 1.0,
                       identity_frac: float = 0.1, layout: str = "flex") -> List[Placement]:
@@ -150,6 +174,8 @@ def canvas_placements(pool_sizes: Dict[int, Tuple[int, int]], canvas: Tuple[int,
         sw, sh = pool_sizes[oid]
         s = 1.0 if rng.random() < identity_frac else float(rng.uniform(scale_lo, scale_hi))
         items.append((oid, max(1, int(round(sw * s))), max(1, int(round(sh * s)))))
+    if layout == "refplacer":
+        return reference_placer_layout(canvas, canvas_idx)
     if layout == "flex":
         return flex_layout(rng, canvas, items)
     W, H = canvas
@@ -166,6 +192,9 @@ WORKLOADS = {
     # BASELINE.json configs[2]: synthetic 4K canvases, 20 RGBA objects each, batch 1024
     "c3_4k_20obj": dict(canvas=(3840, 2160), n_objects=20, pool_n=64, pool_lo=256, pool_hi=1536,
                         scale_lo=0.5, scale_hi=1.0, layout="flex", batch=1024),
+    # C3 with the layouts resolved by the reference's own Flex-DSL placer (fixture, 256 layouts repeated)
+    "c3_refplacer": dict(canvas=(3840, 2160), n_objects=20, pool_n=64, pool_lo=256, pool_hi=1536,
+                         scale_lo=0.5, scale_hi=1.0, layout="refplacer", batch=1024),
     # kernel-tuning variant of C3: scales 0.75..1.0 only (smaller source patches, 9-tap windows)
     "c3_s75": dict(canvas=(3840, 2160), n_objects=20, pool_n=64, pool_lo=256, pool_hi=1536,
                    scale_lo=0.75, scale_hi=1.0, layout="flex", batch=1024),

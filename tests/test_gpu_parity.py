@@ -330,6 +330,24 @@ def test_batch_c3_canvas_full_size_vs_oracle(B):
     assert info["preresampled_placements"] == 0 and info["launches_per_run"] == 5
 
 
+def test_batch_c3_reference_placer_layouts_vs_oracle(B):
+    """C3 canvases whose Flex-DSL trees were resolved by the reference's own placer (fixture c3_reference_layouts.npz,
+    tests/golden/make_c3_reference_layouts.py), bit-exact vs the oracle."""
+    from image_transformation_b200 import synth
+
+    pool = synth.workload_pool("c3_refplacer")
+    sizes_by_id = {k: (v.shape[1], v.shape[0]) for k, v in pool.items()}
+    idx = [0, 7, 255]
+    pls = [synth.workload_placements("c3_refplacer", sizes_by_id, i) for i in idx]
+    assert all(len(p) == 20 for p in pls)
+    outs, info = run_batch(B, pool, [(3840, 2160)] * len(idx), pls, solid=(220, 238, 245, 255))
+    for i, o, pl in zip(idx, outs, pls):
+        bg = np.empty((2160, 3840, 4), np.uint8)
+        bg[...] = (220, 238, 245, 255)
+        assert_same(o, oracle.composite(bg, pool, pl), f"reference-placer layout {i}")
+    assert info["preresampled_placements"] == 0
+
+
 def test_batch_properties_at_scale(B):
     """Size-independent properties on a larger batch: determinism, batch == single-canvas
     launches, transparent overlays are the identity, opaque identity overlay replaces pixels."""

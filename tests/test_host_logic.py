@@ -102,6 +102,23 @@ def test_resolve_placements_reference_semantics():
     assert resolve_placements([{"object_id": 1, "box": [2**30 + 1, 0, 2**30 + 11, 10]}], sizes) == []  # clipped away entirely
 
 
+def test_reference_placer_layout_fixture_is_in_spec():
+    """tests/golden/c3_reference_layouts.npz (reference placer on size proxies): 20 boxes per canvas, inside the
+    canvas, isotropic scales 0.5..1 of the pool cutouts -- and the same object draws as the in-repo generator."""
+    pool = synth.workload_pool("c3_refplacer")
+    sizes = {k: (v.shape[1], v.shape[0]) for k, v in pool.items()}
+    for i in (0, 3, 255, 256 + 3):
+        ref = synth.workload_placements("c3_refplacer", sizes, i)
+        own = synth.workload_placements("c3_4k_20obj", sizes, i % 256)
+        assert len(ref) == 20
+        assert sorted(p["object_id"] for p in ref) == sorted(p["object_id"] for p in own)
+        for p in ref:
+            x1, y1, x2, y2 = p["box"]
+            sw, sh = sizes[p["object_id"]]
+            assert 0 <= x1 < x2 <= 3840 and 0 <= y1 < y2 <= 2160
+            assert 0.5 - 0.01 <= (x2 - x1) / sw <= 1.0 + 0.01 and abs((x2 - x1) / sw - (y2 - y1) / sh) < 0.01
+
+
 def test_synthetic_workload_is_deterministic_and_in_spec():
     sizes = {i: (300 + 7 * i, 900 - 5 * i) for i in range(1, 9)}
     a = synth.canvas_placements(sizes, (3840, 2160), 5)
