@@ -667,6 +667,7 @@ def run_b200(args):
                        "host_cores": host_cores()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (ratio * algo if ratio else None), "peak_source": peak_src,
+                         "frac_of_nominal_8tbs": achieved / 8000.0,  # also against north_star's nominal 8.0 TB/s
                          "traffic_source": ratio_src, "algorithmic_bytes_per_launch": algo,
                          "kernel": "b200comp_plan_run = prepare_cutouts + 3 binning kernels + composite_slab_kernel "
                                    "(persistent tile kernel, the dominant launch); achieved = algorithmic bytes of the "
