@@ -132,7 +132,11 @@ typedef struct b200comp_plan b200comp_plan;
 int b200comp_plan_create(const b200comp_canvas *canvases, int n_canvases, const b200comp_placement *placements,
                          int n_placements, int n_host_threads, void *stream, b200comp_plan **plan);
 /* Launch the batch (asynchronous on `stream`).  Re-runnable.  Equivalent to b200comp_plan_prepare
- * followed by b200comp_plan_run_canvases over every canvas. */
+ * followed by b200comp_plan_run_canvases over every canvas.  Stream semantics are the caller's stream's: the work
+ * starts after everything queued on `stream` before the call and is complete for everything queued after it.  A large
+ * run is cut into waves whose binning runs on plan-owned side streams under the previous wave's tile kernel; the side
+ * streams fork from and join back into `stream` with events before the call returns (B200COMP_WAVES=1 switches the
+ * split off).  Runs of one plan share its buffers and must be ordered (same stream, or synchronised). */
 int b200comp_plan_run(b200comp_plan *plan, void *stream);
 /* The two stages separately, so a caller can pipeline copies with compute: `prepare` builds what the
  * tile kernel reads besides the caller's buffers (premultiplied planar cutouts, pre-resampled overlays
