@@ -349,12 +349,30 @@ bin_fill_kernel(const DevCanvas *__restrict__ canvases, int canvas0, const DevPl
                 }
             }
         } else {
-            for (int yy = 0; yy < th; ++yy)
-                for (int xx = lane; xx < tw; xx += 32) {
-                    const int64_t px = (int64_t)(tx0 + xx) * 4;
-                    const uint32_t v = cv.bg ? ld_px(cv.bg, (int64_t)(ty0 + yy) * cv.bg_pitch + px) : cv.solid;
-                    *reinterpret_cast<uint32_t *>(cv.out + (int64_t)(ty0 + yy) * cv.out_pitch + px) = v;
-                }
+            // buffers or tile widths the 16-byte path cannot take: 4-byte accesses, lane = column (two per lane), eight
+            // rows of loads in flight before their stores (one load-store pair at a time costs a DRAM round trip each)
+            const uint8_t *bg = cv.bg;
+            uint8_t *out = cv.out;
+            const int64_t bgp = cv.bg_pitch, outp = cv.out_pitch;
+            const uint32_t solid = cv.solid;
+            for (int y0 = 0; y0 < th; y0 += 8) {
+                uint32_t v[8][2];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int yy = y0 + k, xx = lane + 32 * h;
+                        v[k][h] = (bg && yy < th && xx < tw) ? ld_px(bg, (int64_t)(ty0 + yy) * bgp + (int64_t)(tx0 + xx) * 4) : solid;
+                    }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int yy = y0 + k, xx = lane + 32 * h;
+                        if (yy < th && xx < tw)
+                            *reinterpret_cast<uint32_t *>(out + (int64_t)(ty0 + yy) * outp + (int64_t)(tx0 + xx) * 4) = v[k][h];
+                    }
+            }
         }
         return;
     }
