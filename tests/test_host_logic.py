@@ -179,3 +179,20 @@ def test_rgba_array_paths():
         assert fresh.getpixel((6, 4)) == (11, 11, 11, 11)
         fresh.putpixel((0, 0), (1, 2, 3, 4))
         assert tuple(view[0, 0]) == (1, 2, 3, 4)  # the view IS the image's memory
+    # pixel_block / new_rgba_block: the raw address the drop-in hands to the C ABI (no numpy in between)
+    import ctypes
+
+    blk = _native.pixel_block(owned)
+    if blk is not None:
+        ptr, keep = blk
+        assert ptr == _native.data_ptr(_native.rgba_array(owned)) and keep is not None
+        first = (ctypes.c_uint8 * 4).from_address(ptr)
+        assert tuple(first) == owned.getpixel((0, 0))
+        owned.putpixel((0, 0), (4, 3, 2, 1))
+        assert tuple(first) == (4, 3, 2, 1)
+        img2, blk2 = _native.new_rgba_block(9, 4)
+        ctypes.memset(blk2[0], 7, 9 * 4 * 4)
+        assert img2.getpixel((8, 3)) == (7, 7, 7, 7) and not getattr(img2, "readonly", 0)
+    assert _native.pixel_block(Image.new("RGB", (4, 4))) is None  # only RGBA blocks are handed over
+    ro = Image.frombuffer("RGBA", (40, 60), a.tobytes(), "raw", "RGBA", 0, 1)  # buffer-backed, read-only: copied, not viewed
+    assert _native.pixel_block(ro) is None and np.array_equal(_native.rgba_array(ro), a)
