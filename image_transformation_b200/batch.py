@@ -183,6 +183,16 @@ class CompositeBatch:
         with torch.cuda.device(self.pool.device):
             _native.check(_native.lib().b200comp_plan_run(self._plan, _stream_handle(stream)), "CompositeBatch.run")
 
+    def run_canvases(self, first: int, count: int, stream: Optional[torch.cuda.Stream] = None, prepare: bool = True) -> None:
+        """Composite canvases [first, first + count) only (b200comp_plan_prepare + b200comp_plan_run_canvases): what a
+        caller pipelining copies with compute does chunk by chunk.  `prepare=False` when the cutouts were prepared by an
+        earlier call on the same stream and have not changed."""
+        with torch.cuda.device(self.pool.device):
+            if prepare:
+                _native.check(_native.lib().b200comp_plan_prepare(self._plan, _stream_handle(stream)), "CompositeBatch.prepare")
+            _native.check(_native.lib().b200comp_plan_run_canvases(self._plan, int(first), int(count), _stream_handle(stream)),
+                          "CompositeBatch.run_canvases")
+
     def check(self, stream: Optional[torch.cuda.Stream] = None) -> None:
         """Synchronise and verify the kernel's status word."""
         with torch.cuda.device(self.pool.device):

@@ -375,6 +375,28 @@ def test_batch_properties_at_scale(B):
             os.environ.pop("B200COMP_WAVES", None)
         for a, b in zip(o1 + m1, ow + mw):
             assert np.array_equal(a, b), f"waves={waves}"
+    # a sub-range of the plan's canvases, itself cut into waves: only those canvases are written, with the same pixels
+    os.environ["B200COMP_WAVES"] = "4"
+    try:
+        cb = B.CompositeBatch(B.CutoutPool(pool), mixed_sizes, mixed_pls, solid=(10, 20, 30, 255))
+        for o in cb.outputs():
+            o.fill_(7)
+        cb.run_canvases(3, 7)
+        cb.check()
+        part = [host(o) for o in cb.outputs()]
+        cb.run_canvases(0, 3, prepare=False)
+        cb.run_canvases(10, 2, prepare=False)
+        cb.check()
+        rest = [host(o) for o in cb.outputs()]
+        cb.close()
+    finally:
+        os.environ.pop("B200COMP_WAVES", None)
+    for i in range(n):
+        if 3 <= i < 10:
+            assert np.array_equal(part[i], m1[i]), f"sub-range canvas {i}"
+        else:
+            assert (part[i] == 7).all(), f"canvas {i} outside the sub-range was touched"
+        assert np.array_equal(rest[i], m1[i]), f"canvas {i} after the remaining ranges"
     for i in (0, n - 1):
         single, _ = run_batch(B, pool, [(3840, 2160)], [pls[i]], solid=(10, 20, 30, 255))
         assert np.array_equal(single[0], o1[i])
