@@ -63,10 +63,11 @@ def main():
     row("gradient fill (8K canvas)", 4 * W * H, ms)
     rng = np.random.default_rng(1)
     src = torch.from_numpy(synth.make_cutout(rng, 3072, 2304)).cuda()
-    for (w, h) in ((2304, 1728), (1536, 1152), (4096, 3072)):
+    for (w, h) in ((2304, 1728), (1536, 1152), (4096, 3072), (768, 576), (384, 288)):
         ms = timed(lambda: B.resize_rgba_lanczos(src, (w, h)))
-        row(f"resize_rgba_lanczos 3072x2304 -> {w}x{h} (generic two-pass kernels)", 4 * 3072 * 2304 + 4 * w * h, ms,
-            "not on the headline path: the batch path resamples inside the fused tile kernel")
+        path = "fused tile kernel, replace mode" if 3072 / w <= 2.6 else "generic two-pass kernels: more than 17 taps"
+        row(f"resize_rgba_lanczos 3072x2304 -> {w}x{h} ({path})", 4 * 3072 * 2304 + 4 * w * h, ms,
+            "stand-alone call: plan creation for one placement included")
     ov = torch.from_numpy(synth.make_cutout(rng, 3072, 2304)).cuda()
     big = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
     B.fill_rgba_(big, (1, 2, 3, 255))
