@@ -446,6 +446,63 @@ static int packed_words(int ks) {
     return 0;  // more than 17 taps (downscale beyond 2.66x): generic kernels
 }
 
+// Legacy (int32) tap tables of the generic kernels are built with double arithmetic and libm on the host: a few tenths
+// of a millisecond for an extreme downscale, more than its two kernels take.  The callers that reach them repeat the
+// same geometry (thumbnails of the same cutouts every refine iteration, uploads downscaled to the same side), so the
+// last tables are kept: 32 MB at most, least recently used first out, values exactly what build_lanczos_table returns.
+class LegacyTableCache {
+public:
+    // k: out_size * ks taps, bounds: out_size * 2
+    void get(int in_size, int out_size, int ks, int32_t *k, int32_t *bounds) {
+        const size_t nk = (size_t)out_size * ks, nb = (size_t)out_size * 2;
+        const uint64_t key = ((uint64_t)(uint32_t)in_size << 32) | (uint32_t)out_size;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            auto it = map_.find(key);
+            if (it != map_.end() && it->second.data.size() == nk + nb) {
+                it->second.stamp = ++clock_;
+                std::memcpy(k, it->second.data.data(), nk * sizeof(int32_t));
+                std::memcpy(bounds, it->second.data.data() + nk, nb * sizeof(int32_t));
+                return;
+            }
+        }
+        build_lanczos_table(in_size, out_size, k, bounds);
+        Entry e;
+        e.data.resize(nk + nb);
+        std::memcpy(e.data.data(), k, nk * sizeof(int32_t));
+        std::memcpy(e.data.data() + nk, bounds, nb * sizeof(int32_t));
+        const size_t bytes = e.data.size() * sizeof(int32_t);
+        if (bytes > kMaxBytes / 4) return;  // a single huge table would evict everything else
+        std::lock_guard<std::mutex> lock(mu_);
+        e.stamp = ++clock_;
+        bytes_ += bytes;
+        auto ins = map_.emplace(key, std::move(e));
+        if (!ins.second) bytes_ -= bytes;  // another thread was faster
+        while (bytes_ > kMaxBytes && map_.size() > 1) {
+            auto oldest = map_.begin();
+            for (auto it = map_.begin(); it != map_.end(); ++it)
+                if (it->second.stamp < oldest->second.stamp) oldest = it;
+            bytes_ -= oldest->second.data.size() * sizeof(int32_t);
+            map_.erase(oldest);
+        }
+    }
+    static LegacyTableCache &instance() {
+        static LegacyTableCache *c = new LegacyTableCache();  // never destroyed (used from any thread until exit)
+        return *c;
+    }
+
+private:
+    struct Entry {
+        std::vector<int32_t> data;
+        uint64_t stamp = 0;
+    };
+    static constexpr size_t kMaxBytes = (size_t)32 << 20;
+    std::mutex mu_;
+    std::unordered_map<uint64_t, Entry> map_;
+    size_t bytes_ = 0;
+    uint64_t clock_ = 0;
+};
+
 struct TableSet {
     struct Key {
         int in_size, out_size, kind;  // kind 0 legacy, 1 packed, 2 packed identity (skipped pass)
@@ -518,7 +575,7 @@ struct TableSet {
                 int32_t *h = host.data();
                 if (skip_packed && key.kind != 0) continue;
                 if (key.kind == 0) {
-                    build_lanczos_table(key.in_size, key.out_size, h + r.k_off, h + r.b_off);
+                    LegacyTableCache::instance().get(key.in_size, key.out_size, r.ks, h + r.k_off, h + r.b_off);
                     continue;
                 }
                 const int n = key.out_size;
@@ -836,7 +893,7 @@ int b200comp_resize_rgba_lanczos(const uint8_t *src, int sw, int sh, size_t src_
     TableRef tx, ty;
     if (w != sw) tx = ts.want_legacy(sw, w);
     if (h != sh) ty = ts.want_legacy(sh, h);
-    ts.build((int64_t)w + h > 1024 ? 2 : 1);  // the two tables (double + libm) on two threads when they are large
+    ts.build((int64_t)w + h > 8192 ? 2 : 1);  // two threads only for very long tables (spawning one costs as much as a cached or mid-sized table)
     const size_t tbytes = ts.host.size() * sizeof(int32_t);
     const size_t sbytes = (size_t)std::max((int64_t)sh * w, (int64_t)h * sw) * 4;
     uint8_t *d_mem = nullptr;
