@@ -60,6 +60,20 @@ def test_resize_random_sweep_vs_oracle(B):
         assert_same(host(B.resize_rgba_lanczos(dev(src), (w, h))), exp, f"{sw}x{sh}->{w}x{h}")
 
 
+def test_resize_extreme_downscale_repeated(B):
+    """More than 17 taps: the generic kernels with host-built tap tables, which are cached by geometry -- the second and
+    third call (cached tables) give the first call's pixels, all equal to the oracle; other geometries in between."""
+    rng = np.random.default_rng(24)
+    src = rng.integers(0, 256, (700, 900, 4), dtype=np.uint8)
+    src[..., 3] = np.where(rng.random((700, 900)) < 0.3, 0, src[..., 3])
+    exp = oracle.resize_rgba_lanczos(src, (100, 64), vertical_first_rule=False)
+    t = dev(src)
+    for rep in range(3):
+        assert_same(host(B.resize_rgba_lanczos(t, (100, 64))), exp, f"9x / 10.9x downscale, call {rep}")
+        other = (90 + rep, 70)
+        assert_same(host(B.resize_rgba_lanczos(t, other)), oracle.resize_rgba_lanczos(src, other, vertical_first_rule=False), str(other))
+
+
 def test_resize_with_pitch(B):
     rng = np.random.default_rng(22)
     big = rng.integers(0, 256, (90, 160, 4), dtype=np.uint8)
